@@ -1,0 +1,19 @@
+"""headct_foundation_b200 -- B200-native (sm_100a) implementation of the HeadCT-Foundation 3-D ViT hot path.
+
+The classes below keep the reference's `src/models` surface (constructor kwargs, methods, state_dict layout);
+their compute runs in hand-written CUDA behind the C ABI in include/hct_b200.h.
+"""
+from .models.mae import MaskedAutoencoderViT
+from .models.vit import ViT
+from .models.attentionblock import AttentionBlock, SelfAttention, MLPBlock
+from .models.dino_head import DINOHead
+from .models.classifier import LinearClassifier
+from .utils.patch_embedding import PatchEmbeddingBlock
+from .utils.pos_embed import build_sincos_position_embedding
+from .utils.misc import MultiCropWrapper, _update_momentum_encoder, update_momentum_encoder
+from .losses.losses import DINOLoss
+from .data.transforms import MultipleWindowScaleStack
+
+__all__ = ["MaskedAutoencoderViT", "ViT", "AttentionBlock", "SelfAttention", "MLPBlock", "DINOHead",
+           "LinearClassifier", "PatchEmbeddingBlock", "build_sincos_position_embedding", "MultiCropWrapper",
+           "update_momentum_encoder", "DINOLoss", "MultipleWindowScaleStack"]

@@ -1,0 +1,122 @@
+"""ctypes binding of libhct_b200.so -- the thin layer between the PyTorch host code and the C ABI.
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every kernel on the hot
+path is reached through the `extern "C"` entry points declared in include/hct_b200.h.  There is
+no CPU or eager-PyTorch fallback: if the library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libhct_b200.so")
+_lib: Optional[C.CDLL] = None
+
+EPI_BF16, EPI_GELU_BF16, EPI_RES_F32, EPI_POS_F32, EPI_DGELU_BF16, EPI_F32, EPI_ATOMIC_F32 = range(7)
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("b_mn_major", C.c_int32),
+        ("epilogue", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64),
+        ("bias", C.c_void_p),
+        ("res", C.c_void_p), ("ldres", C.c_int64),
+        ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("pos", C.c_void_p), ("ldpos", C.c_int64),
+        ("pos_idx", C.c_void_p), ("pos_period", C.c_int32),
+        ("rows_in", C.c_int32), ("rows_out", C.c_int32), ("row_off", C.c_int32),
+        ("alpha", C.c_float),
+        ("splits", C.c_int32),
+    ]
+
+
+_P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+_SIGNATURES = {
+    "hct_gemm_bf16": [C.POINTER(GemmDesc), _P],
+    "hct_layernorm_fwd": [_P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _F, _P],
+    "hct_layernorm_bwd": [_P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    "hct_cast_f32_to_bf16": [_P, _P, _I64, _P],
+    "hct_cast_bf16_to_f32": [_P, _P, _I64, _P],
+    "hct_colsum": [_P, _I32, _I64, _P, _I64, _I32, _P],
+    "hct_broadcast_rows": [_P, _P, _I32, _I32, _I64, _I32, _I32, _P],
+    "hct_reduce_rows": [_P, _P, _I32, _I32, _I64, _I32, _I32, _P],
+    "hct_copy_rows_f32_to_bf16": [_P, _I64, _I64, _I32, _P, _I64, _I64, _I32, _I32, _P],
+    "hct_scatter_add_rows": [_P, _P, _P, _I64, _I32, _P],
+    "hct_window_scale_stack": [_P, _I32, _P, _I32, _I64, _I64, _I32, C.POINTER(_F), C.POINTER(_F), _P],
+    "hct_patchify": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "hct_mask_indices": [_P, _P, _P, _P, _I32, _I32, _I32, _P],
+    "hct_gather_tokens": [_P, _P, _P, _I32, _I32, _I32, _I64, _I32, _I32, _P],
+    "hct_scatter_tokens": [_P, _P, _P, _I32, _I32, _I32, _I64, _I32, _I32, _P],
+    "hct_decoder_assemble": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_decoder_assemble_bwd": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_mae_loss_fwd": [_P, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "hct_mae_loss_bwd": [_P, _I32, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "hct_gelu_bwd": [_P, _P, _P, _I64, _P],
+    "hct_attention_fwd": [_P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_attention_bwd": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_l2norm_fwd": [_P, _I32, _P, _P, _I64, _I32, _P],
+    "hct_l2norm_bwd": [_P, _P, _P, _P, _I64, _I32, _P],
+    "hct_weightnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _P],
+    "hct_weightnorm_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _P],
+    "hct_dino_loss": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _F, _P],
+    "hct_center_ema": [_P, _P, _F, _F, _I32, _P],
+    "hct_ema_multi": [_P, _I32, _F, _P],
+    "hct_grad_norms_multi": [_P, _I32, _P, _P],
+    "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("hct_last_error", "hct_abi_version", "hct_launch_count")
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python -m headct_foundation_b200.build` "
+                "(there is no CPU / eager fallback for the hot path)")
+        L = C.CDLL(_LIB_PATH)
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        L.hct_last_error.restype = C.c_char_p
+        L.hct_last_error.argtypes = []
+        L.hct_abi_version.restype = C.c_int
+        L.hct_launch_count.restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def launch_count() -> int:
+    return int(lib().hct_launch_count())
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().hct_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,440 @@
+// MAE-specific HBM-bound kernels: HU windowing, patchify (im2col for Conv3d k=s), random-masking
+// indices (stable rank sort), token gather/scatter, decoder input assembly, masked-MSE loss.
+#include "../../include/hct_b200.h"
+#include "hct_common.cuh"
+
+namespace {
+
+inline int grid_for(long long work_items, int threads, int max_blocks) {
+  long long g = (work_items + threads - 1) / threads;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------ a1: HU windowing
+struct WindowParams { float a_min[8]; float inv_w[8]; int nwin; };
+
+template <bool IN_I16, bool OUT_BF16>
+__global__ void window_kernel(const void* __restrict__ hu, void* __restrict__ out, long long nvol, long long vox,
+                              WindowParams wp) {
+  const long long vox4 = vox >> 2;
+  const long long total = nvol * vox4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long v = i / vox4, k = i % vox4;
+    float4 x;
+    if (IN_I16) {
+      const short4 s = reinterpret_cast<const short4*>(reinterpret_cast<const short*>(hu) + v * vox)[k];
+      x = make_float4(s.x, s.y, s.z, s.w);
+    } else {
+      x = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(hu) + v * vox)[k];
+    }
+#pragma unroll 3
+    for (int w = 0; w < wp.nwin; ++w) {
+      // (x - a_min) / (a_max - a_min) then clip: a true division keeps bit parity with the MONAI formula
+      const float lo = wp.a_min[w], width = wp.inv_w[w];
+      const float y0 = fminf(fmaxf((x.x - lo) / width, 0.f), 1.f), y1 = fminf(fmaxf((x.y - lo) / width, 0.f), 1.f);
+      const float y2 = fminf(fmaxf((x.z - lo) / width, 0.f), 1.f), y3 = fminf(fmaxf((x.w - lo) / width, 0.f), 1.f);
+      const long long o = (v * wp.nwin + w) * vox;
+      if (OUT_BF16) {
+        uint2 u; u.x = pack_bf16x2(y0, y1); u.y = pack_bf16x2(y2, y3);
+        reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + o)[k] = u;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o)[k] = make_float4(y0, y1, y2, y3);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ a2: patchify (im2col, K order c,ph,pw,pd)
+// one CTA per output row; thread t copies run t = (c, ph, pw): p contiguous floats along D.
+__global__ void __launch_bounds__(128)
+patchify_kernel(const float* __restrict__ x, bf16* __restrict__ cols, const long long* __restrict__ patch_ids,
+                int* __restrict__ pos_idx_out, int C, int H, int W, int D, int p, int rows_per_vol) {
+  const long long row = blockIdx.x;
+  const int b = static_cast<int>(row / rows_per_vol), j = static_cast<int>(row % rows_per_vol);
+  const int gw = W / p, gd = D / p;
+  const int pid = patch_ids ? static_cast<int>(patch_ids[row]) : j;
+  if (threadIdx.x == 0 && pos_idx_out) pos_idx_out[row] = pid;
+  const int pd0 = (pid % gd) * p, pw0 = ((pid / gd) % gw) * p, ph0 = (pid / (gd * gw)) * p;
+  const int runs = C * p * p;
+  const long long K = static_cast<long long>(runs) * p;
+  bf16* dst = cols + row * K;
+  for (int r = threadIdx.x; r < runs; r += blockDim.x) {
+    const int c = r / (p * p), ph = (r / p) % p, pw = r % p;
+    const float* src = x + (((static_cast<long long>(b) * C + c) * H + ph0 + ph) * W + pw0 + pw) * D + pd0;
+    bf16* d = dst + static_cast<long long>(r) * p;
+    if ((p & 3) == 0 && (D & 3) == 0) {
+      for (int k = 0; k < p; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + k);
+        uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(d + k) = u;
+      }
+    } else {
+      for (int k = 0; k < p; ++k) d[k] = __float2bfloat16_rn(src[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ a4: masking indices (stable rank sort)
+// rank[i] = #{j : noise[j] < noise[i]  or (noise[j] == noise[i] and j < i)}  == ids_restore[i]
+// (stable ascending argsort followed by its inverse, mae.py:208-209); ids_shuffle[rank[i]] = i.
+__global__ void mask_indices_kernel(const float* __restrict__ noise, long long* __restrict__ ids_restore,
+                                    long long* __restrict__ ids_keep, float* __restrict__ mask, int L, int len_keep) {
+  extern __shared__ float snoise[];
+  const long long row = blockIdx.x;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) snoise[i] = noise[row * L + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const float v = snoise[i];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float u = snoise[j];
+      rank += (u < v) || (u == v && j < i);
+    }
+    ids_restore[row * L + i] = rank;
+    mask[row * L + i] = rank >= len_keep ? 1.f : 0.f;
+    if (rank < len_keep) ids_keep[row * len_keep + rank] = i;
+  }
+}
+
+// ------------------------------------------------------------------ token gather / scatter (fp32 rows)
+__global__ void gather_tokens_kernel(const float* __restrict__ src, const long long* __restrict__ ids,
+                                     float* __restrict__ dst, int L, int n_ids, long long dst_rows_per_batch,
+                                     int row_off, int dim, long long total_rows) {
+  const int nv = dim >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_rows * nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % nv);
+    const long long r = i / nv;
+    const long long n = r / n_ids;
+    const int j = static_cast<int>(r % n_ids);
+    const long long s = ids[r];
+    reinterpret_cast<float4*>(dst + (n * dst_rows_per_batch + row_off + j) * dim)[c] =
+        reinterpret_cast<const float4*>(src + (n * L + s) * dim)[c];
+  }
+}
+__global__ void scatter_tokens_kernel(const float* __restrict__ ddst, const long long* __restrict__ ids,
+                                      float* __restrict__ dsrc, int L, int n_ids, long long ddst_rows_per_batch,
+                                      int row_off, int dim, long long total_rows) {
+  const int nv = dim >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_rows * nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % nv);
+    const long long r = i / nv;
+    const long long n = r / n_ids;
+    const int j = static_cast<int>(r % n_ids);
+    const long long s = ids[r];
+    reinterpret_cast<float4*>(dsrc + (n * L + s) * dim)[c] =
+        reinterpret_cast<const float4*>(ddst + (n * ddst_rows_per_batch + row_off + j) * dim)[c];
+  }
+}
+
+// ------------------------------------------------------------------ a7: decoder input assembly
+__global__ void decoder_assemble_kernel(const bf16* __restrict__ y, const long long* __restrict__ ids_restore,
+                                        const float* __restrict__ mask_token, const float* __restrict__ dec_cls,
+                                        const float* __restrict__ dec_pos, float* __restrict__ out, int L, int keep,
+                                        int dim, long long total_rows) {
+  const int nv = dim >> 2;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total_rows * nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % nv);
+    const long long r = i / nv;            // output row in [0, N*(L+1))
+    const long long n = r / (L + 1);
+    const int t = static_cast<int>(r % (L + 1));
+    float4 v, add;
+    if (t == 0) {
+      const uint2 u = reinterpret_cast<const uint2*>(y + (n * (keep + 1)) * dim)[c];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      v = make_float4(a.x, a.y, b.x, b.y);
+      add = __ldg(reinterpret_cast<const float4*>(dec_cls) + c);
+    } else {
+      const long long src = ids_restore[n * L + (t - 1)];
+      if (src < keep) {
+        const uint2 u = reinterpret_cast<const uint2*>(y + (n * (keep + 1) + 1 + src) * dim)[c];
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        v = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        v = __ldg(reinterpret_cast<const float4*>(mask_token) + c);
+      }
+      add = __ldg(reinterpret_cast<const float4*>(dec_pos + static_cast<long long>(t - 1) * dim) + c);
+    }
+    reinterpret_cast<float4*>(out + r * dim)[c] = make_float4(v.x + add.x, v.y + add.y, v.z + add.z, v.w + add.w);
+  }
+}
+
+// block (dim/4 threads, <= 512) walks rows; masked rows accumulate into dmask_token, row 0 into ddec_cls
+__global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ ids_restore,
+                                            bf16* __restrict__ dy, float* __restrict__ dmask_token,
+                                            float* __restrict__ ddec_cls, int L, int keep, int dim,
+                                            long long total_rows) {
+  const int nv = dim >> 2;
+  for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+    float4 am = make_float4(0, 0, 0, 0), ac = make_float4(0, 0, 0, 0);
+    for (long long r = blockIdx.x; r < total_rows; r += gridDim.x) {
+      const long long n = r / (L + 1);
+      const int t = static_cast<int>(r % (L + 1));
+      const float4 g = reinterpret_cast<const float4*>(dout + r * dim)[c];
+      long long dst_row = -1;
+      if (t == 0) {
+        ac.x += g.x; ac.y += g.y; ac.z += g.z; ac.w += g.w;
+        dst_row = n * (keep + 1);
+      } else {
+        const long long src = ids_restore[n * L + (t - 1)];
+        if (src < keep) dst_row = n * (keep + 1) + 1 + src;
+        else { am.x += g.x; am.y += g.y; am.z += g.z; am.w += g.w; }
+      }
+      if (dst_row >= 0) {
+        uint2 u; u.x = pack_bf16x2(g.x, g.y); u.y = pack_bf16x2(g.z, g.w);
+        reinterpret_cast<uint2*>(dy + dst_row * dim)[c] = u;
+      }
+    }
+    if (dmask_token) {
+      atomicAdd(dmask_token + 4 * c, am.x); atomicAdd(dmask_token + 4 * c + 1, am.y);
+      atomicAdd(dmask_token + 4 * c + 2, am.z); atomicAdd(dmask_token + 4 * c + 3, am.w);
+    }
+    if (ddec_cls) {
+      atomicAdd(ddec_cls + 4 * c, ac.x); atomicAdd(ddec_cls + 4 * c + 1, ac.y);
+      atomicAdd(ddec_cls + 4 * c + 2, ac.z); atomicAdd(ddec_cls + 4 * c + 3, ac.w);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ a8: masked MSE loss (fwd and bwd share the staging)
+// One CTA per MASKED patch.  The target patch is staged into shared memory in the prediction's
+// (ph,pw,pd,c) order from the volume's (c,ph,pw,pd) runs, optionally normalised, then compared with
+// the bf16 prediction row using 16-byte loads.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, const float* __restrict__ mask,
+                float* __restrict__ per_patch, const float* __restrict__ dloss, const float* __restrict__ mask_sum,
+                bf16* __restrict__ dpred, int L, int C, int H, int W, int D, int p, int norm_pix, int prefix) {
+  extern __shared__ float tgt[];     // [P]
+  __shared__ float red[33];
+  const long long patch = blockIdx.x;          // n * L + l
+  const int P = C * p * p * p;
+  const float m = mask[patch];
+  const int n = static_cast<int>(patch / L), l = static_cast<int>(patch % L);
+  // prediction rows carry `prefix` extra rows (the cls token) per sample: row = n*(L+prefix) + prefix + l
+  const long long prow = static_cast<long long>(n) * (L + prefix) + prefix + l;
+  if (BWD && l == 0 && prefix > 0) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < prefix * (P >> 3); i += blockDim.x)
+      reinterpret_cast<uint4*>(dpred + static_cast<long long>(n) * (L + prefix) * P)[i] = z;
+  }
+  if (m == 0.f) {
+    if (BWD) {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) reinterpret_cast<uint4*>(dpred + prow * P)[i] = z;
+    } else if (threadIdx.x == 0) {
+      per_patch[patch] = 0.f;
+    }
+    return;
+  }
+  const int gw = W / p, gd = D / p;
+  const int pd0 = (l % gd) * p, pw0 = ((l / gd) % gw) * p, ph0 = (l / (gd * gw)) * p;
+  const int runs = C * p * p;
+  float lsum = 0.f;
+  for (int r = threadIdx.x; r < runs; r += blockDim.x) {
+    const int c = r / (p * p), ph = (r / p) % p, pw = r % p;
+    const float* src = imgs + (((static_cast<long long>(n) * C + c) * H + ph0 + ph) * W + pw0 + pw) * D + pd0;
+    float* d = tgt + (static_cast<long long>(ph * p + pw) * p) * C + c;
+    for (int k = 0; k < p; ++k) { const float v = src[k]; d[k * C] = v; lsum += v; }
+  }
+  __syncthreads();
+  float mean = 0.f, inv_std = 1.f;
+  if (norm_pix) {
+    mean = block_sum(lsum, red) / P;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) { const float dlt = tgt[i] - mean; q += dlt * dlt; }
+    const float var = block_sum(q, red) / (P - 1);     // unbiased (mae.py:292)
+    inv_std = rsqrtf(var + 1e-6f);
+  }
+  const bf16* pr = pred + prow * P;
+  if (!BWD) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) {
+      const uint4 u = reinterpret_cast<const uint4*>(pr)[i];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
+      const float pv[8] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d2.x, d2.y};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float e = pv[k] - (tgt[i * 8 + k] - mean) * inv_std; s += e * e; }
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) per_patch[patch] = s / P;
+  } else {
+    const float scale = dloss[0] * m * 2.f / (static_cast<float>(P) * mask_sum[0]);
+    for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) {
+      const uint4 u = reinterpret_cast<const uint4*>(pr)[i];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
+      const float pv[8] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d2.x, d2.y};
+      float g[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = scale * (pv[k] - (tgt[i * 8 + k] - mean) * inv_std);
+      uint4 o;
+      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]); o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+      reinterpret_cast<uint4*>(dpred + prow * P)[i] = o;
+    }
+  }
+}
+
+// deterministic final reduction: loss_out[0] = sum(per_patch * mask), loss_out[1] = sum(mask)
+__global__ void __launch_bounds__(1024)
+loss_reduce_kernel(const float* __restrict__ per_patch, const float* __restrict__ mask, float* __restrict__ loss_out,
+                   long long n) {
+  __shared__ float red[33];
+  float a = 0.f, b = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) { const float m = mask[i]; a += per_patch[i] * m; b += m; }
+  a = block_sum(a, red);
+  b = block_sum(b, red);
+  if (threadIdx.x == 0) { loss_out[0] = a; loss_out[1] = b; loss_out[2] = a / b; }
+}
+
+}  // namespace
+
+extern "C" int hct_window_scale_stack(const void* hu, int hu_i16, void* out, int out_bf16, int64_t nvol, int64_t vox,
+                                      int32_t nwin, const float* a_min, const float* a_max, hct_stream_t s) {
+  HCT_REQUIRE(nwin >= 1 && nwin <= 8, "window_scale_stack: nwin=%d", nwin);
+  HCT_REQUIRE(vox % 4 == 0, "window_scale_stack: voxels per volume must be a multiple of 4");
+  if (nvol <= 0) return HCT_OK;
+  WindowParams wp;
+  wp.nwin = nwin;
+  for (int i = 0; i < nwin; ++i) { wp.a_min[i] = a_min[i]; wp.inv_w[i] = a_max[i] - a_min[i]; }
+  const int grid = grid_for(nvol * (vox / 4), 256, hct_num_sms() * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  if (hu_i16) {
+    if (out_bf16) window_kernel<true, true><<<grid, 256, 0, st>>>(hu, out, nvol, vox, wp);
+    else window_kernel<true, false><<<grid, 256, 0, st>>>(hu, out, nvol, vox, wp);
+  } else {
+    if (out_bf16) window_kernel<false, true><<<grid, 256, 0, st>>>(hu, out, nvol, vox, wp);
+    else window_kernel<false, false><<<grid, 256, 0, st>>>(hu, out, nvol, vox, wp);
+  }
+  return hct_check_launch("window_kernel");
+}
+
+extern "C" int hct_patchify(const float* x, void* cols, const int64_t* patch_ids, int32_t* pos_idx_out, int32_t B,
+                            int32_t C, int32_t H, int32_t W, int32_t D, int32_t p, int32_t rows_per_vol,
+                            hct_stream_t s) {
+  HCT_REQUIRE(p > 0 && H % p == 0 && W % p == 0 && D % p == 0, "patchify: volume %dx%dx%d not divisible by patch %d", H, W, D, p);
+  HCT_REQUIRE(rows_per_vol > 0 && rows_per_vol <= (H / p) * (W / p) * (D / p), "patchify: rows_per_vol=%d", rows_per_vol);
+  if (B <= 0) return HCT_OK;
+  patchify_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows_per_vol), 128, 0, static_cast<cudaStream_t>(s)>>>(
+      x, static_cast<bf16*>(cols), reinterpret_cast<const long long*>(patch_ids), pos_idx_out, C, H, W, D, p, rows_per_vol);
+  return hct_check_launch("patchify_kernel");
+}
+
+extern "C" int hct_mask_indices(const float* noise, int64_t* ids_restore, int64_t* ids_keep, float* mask, int32_t N,
+                                int32_t L, int32_t len_keep, hct_stream_t s) {
+  HCT_REQUIRE(L > 0 && L <= 12288 && len_keep >= 0 && len_keep <= L, "mask_indices: L=%d len_keep=%d", L, len_keep);
+  if (N <= 0) return HCT_OK;
+  const int threads = L >= 512 ? 512 : ((L + 31) / 32) * 32;
+  mask_indices_kernel<<<N, threads, L * sizeof(float), static_cast<cudaStream_t>(s)>>>(
+      noise, reinterpret_cast<long long*>(ids_restore), reinterpret_cast<long long*>(ids_keep), mask, L, len_keep);
+  return hct_check_launch("mask_indices_kernel");
+}
+
+extern "C" int hct_gather_tokens(const float* src, const int64_t* ids, float* dst, int32_t N, int32_t L, int32_t n_ids,
+                                 int64_t dst_rows_per_batch, int32_t row_off, int32_t dim, hct_stream_t s) {
+  HCT_REQUIRE(dim % 4 == 0, "gather_tokens: dim %% 4");
+  if (N <= 0 || n_ids <= 0) return HCT_OK;
+  const long long rows = static_cast<long long>(N) * n_ids;
+  gather_tokens_kernel<<<grid_for(rows * (dim / 4), 256, hct_num_sms() * 8), 256, 0, static_cast<cudaStream_t>(s)>>>(
+      src, reinterpret_cast<const long long*>(ids), dst, L, n_ids, dst_rows_per_batch, row_off, dim, rows);
+  return hct_check_launch("gather_tokens_kernel");
+}
+
+extern "C" int hct_scatter_tokens(const float* ddst, const int64_t* ids, float* dsrc, int32_t N, int32_t L,
+                                  int32_t n_ids, int64_t ddst_rows_per_batch, int32_t row_off, int32_t dim,
+                                  hct_stream_t s) {
+  HCT_REQUIRE(dim % 4 == 0, "scatter_tokens: dim %% 4");
+  if (N <= 0) return HCT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  cudaError_t e = cudaMemsetAsync(dsrc, 0, sizeof(float) * static_cast<size_t>(N) * L * dim, st);
+  if (e != cudaSuccess) { hct_set_error("scatter_tokens memset: %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
+  if (n_ids <= 0) return HCT_OK;
+  const long long rows = static_cast<long long>(N) * n_ids;
+  scatter_tokens_kernel<<<grid_for(rows * (dim / 4), 256, hct_num_sms() * 8), 256, 0, st>>>(
+      ddst, reinterpret_cast<const long long*>(ids), dsrc, L, n_ids, ddst_rows_per_batch, row_off, dim, rows);
+  return hct_check_launch("scatter_tokens_kernel");
+}
+
+extern "C" int hct_decoder_assemble(const void* y, const int64_t* ids_restore, const float* mask_token,
+                                    const float* dec_cls, const float* dec_pos, float* out, int32_t N, int32_t L,
+                                    int32_t keep, int32_t dim, hct_stream_t s) {
+  HCT_REQUIRE(dim % 4 == 0, "decoder_assemble: dim %% 4");
+  if (N <= 0) return HCT_OK;
+  const long long rows = static_cast<long long>(N) * (L + 1);
+  decoder_assemble_kernel<<<grid_for(rows * (dim / 4), 256, hct_num_sms() * 8), 256, 0, static_cast<cudaStream_t>(s)>>>(
+      static_cast<const bf16*>(y), reinterpret_cast<const long long*>(ids_restore), mask_token, dec_cls, dec_pos, out, L,
+      keep, dim, rows);
+  return hct_check_launch("decoder_assemble_kernel");
+}
+
+extern "C" int hct_decoder_assemble_bwd(const float* dout, const int64_t* ids_restore, void* dy, float* dmask_token,
+                                        float* ddec_cls, int32_t N, int32_t L, int32_t keep, int32_t dim,
+                                        hct_stream_t s) {
+  HCT_REQUIRE(dim % 4 == 0, "decoder_assemble_bwd: dim %% 4");
+  if (N <= 0) return HCT_OK;
+  const long long rows = static_cast<long long>(N) * (L + 1);
+  int threads = ((dim / 4 + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  long long grid = rows < 4LL * hct_num_sms() ? rows : 4LL * hct_num_sms();
+  decoder_assemble_bwd_kernel<<<static_cast<int>(grid), threads, 0, static_cast<cudaStream_t>(s)>>>(
+      dout, reinterpret_cast<const long long*>(ids_restore), static_cast<bf16*>(dy), dmask_token, ddec_cls, L, keep, dim,
+      rows);
+  return hct_check_launch("decoder_assemble_bwd_kernel");
+}
+
+static int loss_common_checks(int32_t C, int32_t H, int32_t W, int32_t D, int32_t p) {
+  HCT_REQUIRE(p > 0 && H % p == 0 && W % p == 0 && D % p == 0, "mae_loss: volume not divisible by patch");
+  const long long P = static_cast<long long>(C) * p * p * p;
+  HCT_REQUIRE(P % 8 == 0 && P * 4 <= 200 * 1024, "mae_loss: patch dim %lld unsupported", P);
+  return HCT_OK;
+}
+
+// loss_out layout: [0] = sum(mask*mse), [1] = sum(mask), [2] = loss, [3..3+N*L) = per-patch workspace
+extern "C" int hct_mae_loss_fwd(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                                float* loss_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
+                                int32_t norm_pix, hct_stream_t s) {
+  int rc = loss_common_checks(C, H, W, D, p);
+  if (rc != HCT_OK) return rc;
+  if (N <= 0) return HCT_OK;
+  const int L = (H / p) * (W / p) * (D / p);
+  const int P = C * p * p * p;
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(mae_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  float* per_patch = loss_out + 4;
+  mae_loss_kernel<false><<<static_cast<unsigned>(static_cast<long long>(N) * L), 256, P * sizeof(float), st>>>(
+      static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr, nullptr, nullptr, L, C, H, W, D, p, norm_pix,
+      pred_prefix_rows);
+  rc = hct_check_launch("mae_loss_kernel<fwd>");
+  if (rc != HCT_OK) return rc;
+  loss_reduce_kernel<<<1, 1024, 0, st>>>(per_patch, mask, loss_out, static_cast<long long>(N) * L);
+  return hct_check_launch("loss_reduce_kernel");
+}
+
+extern "C" int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                                const float* dloss, const float* mask_sum, void* dpred, int32_t N, int32_t C, int32_t H,
+                                int32_t W, int32_t D, int32_t p, int32_t norm_pix, hct_stream_t s) {
+  int rc = loss_common_checks(C, H, W, D, p);
+  if (rc != HCT_OK) return rc;
+  if (N <= 0) return HCT_OK;
+  const int L = (H / p) * (W / p) * (D / p);
+  const int P = C * p * p * p;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(mae_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  mae_loss_kernel<true><<<static_cast<unsigned>(static_cast<long long>(N) * L), 256, P * sizeof(float),
+                          static_cast<cudaStream_t>(s)>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss,
+                                                          mask_sum, static_cast<bf16*>(dpred), L, C, H, W, D, p,
+                                                          norm_pix, pred_prefix_rows);
+  return hct_check_launch("mae_loss_kernel<bwd>");
+}

@@ -1,0 +1,731 @@
+"""Host-side op layer: torch.autograd.Functions whose forward/backward enqueue libhct_b200 kernels.
+
+Everything numeric on the hot path happens inside the C-ABI library (`_cabi.call`).  torch is
+used here for device memory (torch.empty / zeros), the current stream and autograd plumbing.
+Activations are bf16, the residual stream / LayerNorm statistics / parameter gradients fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import weakref
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import (EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_POS_F32,
+                    EPI_RES_F32, GemmDesc, call, ptr, stream_ptr)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor is on {t.device}; the headct_b200 hot path is CUDA-only "
+                           "(no CPU fallback)")
+
+
+# --------------------------------------------------------------------------------------------
+# bf16 shadow copies of fp32 parameters (what autocast would cast on every call), refreshed only
+# when the parameter's version counter changes (i.e. after an optimizer step / load_state_dict).
+# --------------------------------------------------------------------------------------------
+_W16: "weakref.WeakKeyDictionary[torch.Tensor, Tuple[int, int, torch.Tensor]]" = weakref.WeakKeyDictionary()
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 contiguous tensor -> new bf16 tensor (own kernel)."""
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    call("hct_cast_f32_to_bf16", x.data_ptr(), out.data_ptr(), x.numel(), stream_ptr(x.device))
+    return out
+
+
+def cast_f32(x: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=F32, device=x.device)
+    call("hct_cast_bf16_to_f32", x.data_ptr(), out.data_ptr(), x.numel(), stream_ptr(x.device))
+    return out
+
+
+def w16(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a (2-D viewable) fp32 weight, cached on (data_ptr, version)."""
+    _require_cuda(p, "weight")
+    key = (p.data_ptr(), p._version)
+    hit = _W16.get(p)
+    if hit is not None and hit[0] == key[0] and hit[1] == key[1]:
+        return hit[2]
+    t = cast_bf16(p.detach())
+    _W16[p] = (key[0], key[1], t)
+    return t
+
+
+def clear_weight_cache() -> None:
+    _W16.clear()
+
+
+# --------------------------------------------------------------------------------------------
+# GEMM helper
+# --------------------------------------------------------------------------------------------
+def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int, out: torch.Tensor,
+         ldo: int, epi: int, a_mn: bool = False, b_mn: bool = False, out2: Optional[torch.Tensor] = None,
+         ldo2: int = 0, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, ldres: int = 0,
+         aux: Optional[torch.Tensor] = None, ldaux: int = 0, pos: Optional[torch.Tensor] = None, ldpos: int = 0,
+         pos_idx: Optional[torch.Tensor] = None, pos_period: int = 0, rows_in: int = 0, rows_out: int = 0,
+         row_off: int = 0, alpha: float = 1.0, splits: int = 0) -> None:
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.a_mn_major = A.data_ptr(), lda, int(a_mn)
+    d.B, d.ldb, d.b_mn_major = B.data_ptr(), ldb, int(b_mn)
+    d.epilogue = epi
+    d.out, d.ldo = out.data_ptr(), ldo
+    d.out2, d.ldo2 = ptr(out2), ldo2
+    d.bias = ptr(bias)
+    d.res, d.ldres = ptr(res), ldres
+    d.aux, d.ldaux = ptr(aux), ldaux
+    d.pos, d.ldpos = ptr(pos), ldpos
+    d.pos_idx, d.pos_period = ptr(pos_idx), pos_period
+    d.rows_in, d.rows_out, d.row_off = rows_in, rows_out, row_off
+    d.alpha, d.splits = alpha, splits
+    call("hct_gemm_bf16", C.byref(d), stream_ptr(A.device))
+
+
+def linear_fwd(x16: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, epi: int = EPI_BF16,
+               out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
+               res: Optional[torch.Tensor] = None, rows_in: int = 0, rows_out: int = 0, row_off: int = 0,
+               out_rows: Optional[int] = None) -> torch.Tensor:
+    """y[M,N] = x16[M,K] @ w16[N,K]^T (+bias, epilogue).  x16: bf16 [M,K] contiguous."""
+    M, K = x16.shape
+    N = w.shape[0]
+    wb = w16(w).view(N, -1)
+    assert wb.shape[1] == K, (wb.shape, K)
+    f32_out = epi in (EPI_RES_F32, EPI_POS_F32, EPI_F32)
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, N), dtype=F32 if f32_out else BF16,
+                          device=x16.device)
+    gemm(x16, wb, M=M, N=N, K=K, lda=K, ldb=K, out=out, ldo=N, epi=epi, out2=out2, ldo2=N, bias=bias,
+         res=res, ldres=N, rows_in=rows_in, rows_out=rows_out, row_off=row_off)
+    return out
+
+
+def linear_dgrad(dy16: torch.Tensor, w: torch.Tensor, *, epi: int = EPI_BF16, aux: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx[M,K] = dy16[M,N] @ w16[N,K]   (B operand MN-major: the weight exactly as stored)."""
+    M, N = dy16.shape
+    wb = w16(w).view(N, -1)
+    K = wb.shape[1]
+    if out is None:
+        out = torch.empty((M, K), dtype=BF16, device=dy16.device)
+    gemm(dy16, wb, M=M, N=K, K=N, lda=N, ldb=K, b_mn=True, out=out, ldo=K, epi=epi, aux=aux, ldaux=K)
+    return out
+
+
+def linear_wgrad(dy16: torch.Tensor, x16: torch.Tensor) -> torch.Tensor:
+    """dW[N,K] (fp32) = dy16[M,N]^T @ x16[M,K]   (both operands MN-major; split-K + fp32 red.add)."""
+    M, N = dy16.shape
+    K = x16.shape[1]
+    assert x16.shape[0] == M
+    out = torch.zeros((N, K), dtype=F32, device=dy16.device)
+    gemm(dy16, x16, M=N, N=K, K=M, lda=N, ldb=K, a_mn=True, b_mn=True, out=out, ldo=K, epi=EPI_ATOMIC_F32)
+    return out
+
+
+def colsum(x: torch.Tensor, cols: int) -> torch.Tensor:
+    """fp32 [cols] = sum over rows of a contiguous [rows, cols] bf16/fp32 matrix (bias gradients)."""
+    rows = x.numel() // cols
+    out = torch.zeros((cols,), dtype=F32, device=x.device)
+    call("hct_colsum", x.data_ptr(), int(x.dtype == BF16), cols, out.data_ptr(), rows, cols, stream_ptr(x.device))
+    return out
+
+
+def rows_to_bf16(src: torch.Tensor, *, groups: int, src_rows_per_group: int, src_row_off: int, rows_per_group: int,
+                 dim: int) -> torch.Tensor:
+    out = torch.empty((groups * rows_per_group, dim), dtype=BF16, device=src.device)
+    call("hct_copy_rows_f32_to_bf16", src.data_ptr(), dim, src_rows_per_group, src_row_off, out.data_ptr(), dim,
+         groups, rows_per_group, dim, stream_ptr(src.device))
+    return out
+
+
+def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_bf16: bool, save_stats: bool):
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty(x.shape, dtype=BF16 if out_bf16 else F32, device=x.device)
+    mean = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
+    rstd = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
+    call("hct_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), int(out_bf16), ptr(mean),
+         ptr(rstd), rows, D, float(eps), stream_ptr(x.device))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd, dres: Optional[torch.Tensor],
+                  want_bf16: bool, want_param_grads: bool = True):
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = torch.empty(x.shape, dtype=F32, device=x.device)
+    dx16 = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
+    dg = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
+    db = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
+    call("hct_layernorm_bwd", dy.data_ptr(), int(dy.dtype == BF16), x.data_ptr(), w.data_ptr(), mean.data_ptr(),
+         rstd.data_ptr(), ptr(dres), dx.data_ptr(), ptr(dx16), ptr(dg), ptr(db), rows, D, stream_ptr(x.device))
+    return dx, dx16, dg, db
+
+
+# --------------------------------------------------------------------------------------------
+# a6: transformer block  (attentionblock.py:96-99)
+# --------------------------------------------------------------------------------------------
+class BlockFn(torch.autograd.Function):
+    """x -> x + proj(SDPA(qkv(LN(x)))) -> (+ linear2(GELU(linear1(LN(.))))), one autograd node.
+
+    Parameter order: att_norm.{w,b}, qkv.{w,b?}, proj.{w,b}, ffn_norm.{w,b}, linear1.{w,b}, linear2.{w,b}.
+    """
+
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, heads, eps):
+        _require_cuda(x, "AttentionBlock input")
+        B, S, D = x.shape
+        M = B * S
+        hd = D // heads
+        x = x.contiguous()
+        dev = x.device
+        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:13])
+        st = stream_ptr(dev)
+
+        h1, mean1, rstd1 = layernorm_fwd(x, n1w, n1b, eps, True, need_grad)
+        qkv = linear_fwd(h1.view(M, D), qkv_w, qkv_b)                                   # [M, 3D] bf16
+        att = torch.empty((M, D), dtype=BF16, device=dev)
+        lse = torch.empty((B, heads, S), dtype=F32, device=dev)
+        call("hct_attention_fwd", qkv.data_ptr(), att.data_ptr(), lse.data_ptr(), B, S, heads, hd, st)
+        x2 = torch.empty_like(x)
+        linear_fwd(att, proj_w, proj_b, epi=EPI_RES_F32, out=x2.view(M, D), res=x.view(M, D))
+        h2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, eps, True, need_grad)
+        F_ = fc1_w.shape[0]
+        a = torch.empty((M, F_), dtype=BF16, device=dev) if need_grad else None
+        g = linear_fwd(h2.view(M, D), fc1_w, fc1_b, epi=EPI_GELU_BF16, out2=a)
+        x3 = torch.empty_like(x)
+        linear_fwd(g, fc2_w, fc2_b, epi=EPI_RES_F32, out=x3.view(M, D), res=x2.view(M, D))
+        if need_grad:
+            ctx.save_for_backward(x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2,
+                                  mean2, rstd2, a, g)
+            ctx.heads, ctx.has_qkv_bias = heads, qkv_b is not None
+        return x3
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2, mean2, rstd2, a,
+         g) = ctx.saved_tensors
+        B, S, D = x.shape
+        M = B * S
+        heads = ctx.heads
+        hd = D // heads
+        dev = x.device
+        st = stream_ptr(dev)
+        dout = dout.contiguous()
+        d3 = take_bf16_shadow(dout)
+        if d3 is None:
+            d3 = rows_to_bf16(dout, groups=1, src_rows_per_group=M, src_row_off=0, rows_per_group=M, dim=D)
+        # ---- MLP branch
+        dfc2_w = linear_wgrad(d3, g)
+        dfc2_b = colsum(d3, D)
+        da = linear_dgrad(d3, fc2_w, epi=EPI_DGELU_BF16, aux=a)                         # [M, F] bf16
+        del d3
+        dfc1_w = linear_wgrad(da, h2.view(M, D))
+        dfc1_b = colsum(da, da.shape[1])
+        dh2 = linear_dgrad(da, fc1_w)                                                   # [M, D] bf16
+        del da
+        dx2, dx2_16, dn2w, dn2b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, True)
+        del dh2
+        # ---- attention branch
+        dx2_16 = dx2_16.view(M, D)
+        dproj_w = linear_wgrad(dx2_16, att)
+        dproj_b = colsum(dx2_16, D)
+        datt = linear_dgrad(dx2_16, proj_w)                                             # [M, D] bf16
+        del dx2_16
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty((B, heads, S), dtype=F32, device=dev)
+        call("hct_attention_bwd", qkv.data_ptr(), att.data_ptr(), datt.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+             delta.data_ptr(), B, S, heads, hd, st)
+        del datt
+        dqkv_w = linear_wgrad(dqkv, h1.view(M, D))
+        dqkv_b = colsum(dqkv, 3 * D) if ctx.has_qkv_bias else None
+        dh1 = linear_dgrad(dqkv, qkv_w)
+        del dqkv
+        dx, dx16, dn1w, dn1b = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True)
+        put_bf16_shadow(dx, dx16)
+        return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, None,
+                None)
+
+
+class AttentionFn(torch.autograd.Function):
+    """Stand-alone SDPA node (F.scaled_dot_product_attention, attentionblock.py:61): qkv bf16 [B,S,3*D] in the qkv
+    Linear's [3][H][hd] channel order -> bf16 [B,S,D]."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads):
+        B, S, D3 = qkv.shape
+        D = D3 // 3
+        qkv = qkv.contiguous()
+        if qkv.dtype != BF16:
+            qkv = cast_bf16(qkv.float())
+        out = torch.empty((B, S, D), dtype=BF16, device=qkv.device)
+        lse = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
+        call("hct_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, heads, D // heads,
+             stream_ptr(qkv.device))
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        B, S, D3 = qkv.shape
+        D, heads = D3 // 3, ctx.heads
+        dout = dout.contiguous()
+        if dout.dtype != BF16:
+            dout = cast_bf16(dout.float())
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
+        call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+             delta.data_ptr(), B, S, heads, D // heads, stream_ptr(qkv.device))
+        return dqkv, None
+
+
+# A block's backward produces both the fp32 residual-stream gradient and its bf16 copy (the next GEMM
+# operand).  autograd only carries the fp32 tensor between nodes, so the bf16 copy rides in this
+# side table keyed by the fp32 tensor's storage; the consumer pops it (and falls back to a cast).
+_SHADOW: Dict[int, Tuple[Tuple[int, ...], torch.Tensor]] = {}
+
+
+def put_bf16_shadow(t32: torch.Tensor, t16: Optional[torch.Tensor]) -> None:
+    _SHADOW.clear()
+    if t16 is not None:
+        _SHADOW[t32.data_ptr()] = (tuple(t32.shape), t16)
+
+
+def take_bf16_shadow(t32: torch.Tensor) -> Optional[torch.Tensor]:
+    hit = _SHADOW.pop(t32.data_ptr(), None)
+    _SHADOW.clear()
+    if hit is None or hit[0] != tuple(t32.shape):
+        return None
+    return hit[1].view(-1, t32.shape[-1])
+
+
+# --------------------------------------------------------------------------------------------
+# a2 (+K3): patch embedding + cls/register prefix   (patch_embedding.py:135-161, mae.py:233-234, vit.py:147-160)
+# --------------------------------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    """tokens[B, P + n, D] fp32: rows [0,P) = prefix tokens (cls, registers), rows P.. = patch embeddings of the
+    selected patches (+ their position embedding).  `ids_keep` (int64 [B, n]) selects patches; None = all."""
+
+    @staticmethod
+    def forward(ctx, vol, conv_w, conv_b, pos, prefix, ids_keep, patch):
+        _require_cuda(vol, "volume")
+        vol = vol.contiguous()
+        if vol.dtype != F32:
+            vol = vol.float()
+        B, Cin, H, W, Dd = vol.shape
+        L = (H // patch) * (W // patch) * (Dd // patch)
+        n = L if ids_keep is None else ids_keep.shape[1]
+        E = conv_w.shape[0]
+        K = Cin * patch ** 3
+        P = 0 if prefix is None else prefix.shape[-2]
+        S = P + n
+        dev = vol.device
+        st = stream_ptr(dev)
+        cols = torch.empty((B * n, K), dtype=BF16, device=dev)
+        pos_idx = torch.empty((B * n,), dtype=torch.int32, device=dev)
+        call("hct_patchify", vol.data_ptr(), cols.data_ptr(), ptr(ids_keep), pos_idx.data_ptr(), B, Cin, H, W, Dd,
+             patch, n, st)
+        out = torch.empty((B, S, E), dtype=F32, device=dev)
+        wb = w16(conv_w).view(E, K)
+        has_pos = pos is not None
+        if has_pos:
+            gemm(cols, wb, M=B * n, N=E, K=K, lda=K, ldb=K, out=out, ldo=E, epi=EPI_POS_F32, bias=conv_b,
+                 pos=pos, ldpos=E, pos_idx=pos_idx, rows_in=n, rows_out=S, row_off=P)
+        else:
+            gemm(cols, wb, M=B * n, N=E, K=K, lda=K, ldb=K, out=out, ldo=E, epi=EPI_F32, bias=conv_b,
+                 rows_in=n, rows_out=S, row_off=P)
+        if P:
+            call("hct_broadcast_rows", prefix.data_ptr(), out.data_ptr(), B, P, S, 0, E, st)
+        ctx.save_for_backward(cols, pos_idx)
+        ctx.dims = (B, n, S, P, E, K, L, ids_keep is not None, has_pos, tuple(conv_w.shape),
+                    None if pos is None else tuple(pos.shape), None if prefix is None else tuple(prefix.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cols, pos_idx = ctx.saved_tensors
+        B, n, S, P, E, K, L, has_ids, has_pos, wshape, pshape, prefshape = ctx.dims
+        dev = dout.device
+        st = stream_ptr(dev)
+        dout = dout.contiguous()
+        take_bf16_shadow(dout)
+        dy = rows_to_bf16(dout, groups=B, src_rows_per_group=S, src_row_off=P, rows_per_group=n, dim=E)
+        dw = linear_wgrad(dy, cols).view(wshape) if ctx.needs_input_grad[1] else None
+        db = colsum(dy, E) if ctx.needs_input_grad[2] else None
+        dpos = None
+        if has_pos and ctx.needs_input_grad[3]:
+            dpos = torch.zeros(pshape, dtype=F32, device=dev)
+            if has_ids:
+                call("hct_scatter_add_rows", dy.data_ptr(), pos_idx.data_ptr(), dpos.data_ptr(), B * n, E, st)
+            else:
+                call("hct_reduce_rows", dout.data_ptr(), dpos.data_ptr(), B, L, S, P, E, st)
+        dprefix = None
+        if P and ctx.needs_input_grad[4]:
+            dprefix = torch.zeros(prefshape, dtype=F32, device=dev)
+            call("hct_reduce_rows", dout.data_ptr(), dprefix.data_ptr(), B, P, S, 0, E, st)
+        return None, dw, db, dpos, dprefix, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# a4: random masking  (mae.py:194-218)
+# --------------------------------------------------------------------------------------------
+def mask_indices(noise: torch.Tensor, len_keep: int):
+    _require_cuda(noise, "noise")
+    noise = noise.contiguous().float()
+    N, L = noise.shape
+    ids_restore = torch.empty((N, L), dtype=torch.int64, device=noise.device)
+    ids_keep = torch.empty((N, len_keep), dtype=torch.int64, device=noise.device)
+    mask = torch.empty((N, L), dtype=F32, device=noise.device)
+    call("hct_mask_indices", noise.data_ptr(), ids_restore.data_ptr(), ids_keep.data_ptr(), mask.data_ptr(), N, L,
+         len_keep, stream_ptr(noise.device))
+    return ids_restore, ids_keep, mask
+
+
+class GatherTokensFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ids):
+        _require_cuda(x, "tokens")
+        x = x.contiguous().float()
+        N, L, D = x.shape
+        n = ids.shape[1]
+        out = torch.empty((N, n, D), dtype=F32, device=x.device)
+        call("hct_gather_tokens", x.data_ptr(), ids.data_ptr(), out.data_ptr(), N, L, n, n, 0, D, stream_ptr(x.device))
+        ctx.save_for_backward(ids)
+        ctx.dims = (N, L, D, n)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        N, L, D, n = ctx.dims
+        dout = dout.contiguous()
+        dx = torch.empty((N, L, D), dtype=F32, device=dout.device)
+        call("hct_scatter_tokens", dout.data_ptr(), ids.data_ptr(), dx.data_ptr(), N, L, n, n, 0, D,
+             stream_ptr(dout.device))
+        return dx, None
+
+
+# --------------------------------------------------------------------------------------------
+# LayerNorm as its own node (final norms: mae.py:240,271, vit.py:169)
+# --------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps, out_bf16):
+        _require_cuda(x, "LayerNorm input")
+        x = x.contiguous()
+        need = any(ctx.needs_input_grad[:3])
+        y, mean, rstd = layernorm_fwd(x, w, b, eps, out_bf16, need)
+        if need:
+            ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx, dx16, dg, db = layernorm_bwd(dy, x, w, mean, rstd, None, True)
+        put_bf16_shadow(dx, dx16)
+        return dx, dg, db, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# generic Linear node: bf16 in -> bf16 (or fp32) out   (decoder_embed, decoder_pred, DINO head)
+# --------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x @ W^T + b on rows of x (bf16 or fp32, last dim = in_features).
+
+    gelu=True fuses the exact-erf GELU (DINO head MLP); out_f32 selects fp32 output.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w, b, gelu, out_f32):
+        _require_cuda(x, "Linear input")
+        K = x.shape[-1]
+        M = x.numel() // K
+        N = w.shape[0]
+        x = x.contiguous()
+        x16 = x.view(M, K) if x.dtype == BF16 else rows_to_bf16(x, groups=1, src_rows_per_group=M, src_row_off=0,
+                                                                rows_per_group=M, dim=K)
+        need = any(ctx.needs_input_grad[:3])
+        pre = torch.empty((M, N), dtype=BF16, device=x.device) if (gelu and need) else None
+        epi = EPI_GELU_BF16 if gelu else (EPI_F32 if out_f32 else EPI_BF16)
+        y = linear_fwd(x16, w, b, epi=epi, out2=pre)
+        if need:
+            ctx.save_for_backward(x16, w, pre)
+        ctx.meta = (tuple(x.shape), x.dtype, b is not None, gelu)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w, pre = ctx.saved_tensors
+        xshape, xdtype, has_bias, gelu = ctx.meta
+        M, K = x16.shape
+        N = w.shape[0]
+        dy = dy.contiguous()
+        dy2 = take_bf16_shadow(dy) if dy.dtype == F32 else None
+        if dy2 is None:
+            dy2 = dy.view(-1, N)
+            if dy2.dtype != BF16:
+                dy2 = rows_to_bf16(dy2, groups=1, src_rows_per_group=M, src_row_off=0, rows_per_group=M, dim=N)
+        if gelu:
+            dy2 = gelu_bwd(dy2, pre)
+        dw = linear_wgrad(dy2, x16).view(w.shape) if ctx.needs_input_grad[1] else None
+        db = colsum(dy2, N) if (has_bias and ctx.needs_input_grad[2]) else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx16 = linear_dgrad(dy2, w)
+            dx = dx16.view(xshape) if xdtype == BF16 else cast_f32(dx16).view(xshape)
+        return dx, dw, db, None, None
+
+
+def gelu_bwd(dy16: torch.Tensor, pre16: torch.Tensor) -> torch.Tensor:
+    """dy * gelu_erf'(pre), bf16 elementwise (only the small DINO-head MLP uses this; transformer blocks fuse
+    the same product into the linear2 dgrad GEMM epilogue)."""
+    out = torch.empty_like(dy16)
+    call("hct_gelu_bwd", dy16.data_ptr(), pre16.data_ptr(), out.data_ptr(), dy16.numel(), stream_ptr(dy16.device))
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# a7: decoder input assembly (mae.py:257-265)
+# --------------------------------------------------------------------------------------------
+class DecoderAssembleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y16, ids_restore, mask_token, dec_cls, dec_pos):
+        N, Sk, D = y16.shape
+        L = ids_restore.shape[1]
+        keep = Sk - 1
+        y16 = y16.contiguous()
+        out = torch.empty((N, L + 1, D), dtype=F32, device=y16.device)
+        call("hct_decoder_assemble", y16.data_ptr(), ids_restore.data_ptr(), mask_token.data_ptr(), dec_cls.data_ptr(),
+             dec_pos.data_ptr(), out.data_ptr(), N, L, keep, D, stream_ptr(y16.device))
+        ctx.save_for_backward(ids_restore)
+        ctx.dims = (N, L, keep, D, tuple(mask_token.shape), tuple(dec_cls.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids_restore,) = ctx.saved_tensors
+        N, L, keep, D, mshape, cshape = ctx.dims
+        dout = dout.contiguous()
+        take_bf16_shadow(dout)
+        dev = dout.device
+        dy = torch.empty((N, keep + 1, D), dtype=BF16, device=dev)
+        dmask = torch.zeros(mshape, dtype=F32, device=dev)
+        dcls = torch.zeros(cshape, dtype=F32, device=dev)
+        call("hct_decoder_assemble_bwd", dout.data_ptr(), ids_restore.data_ptr(), dy.data_ptr(), dmask.data_ptr(),
+             dcls.data_ptr(), N, L, keep, D, stream_ptr(dev))
+        return dy, None, dmask, dcls, None   # decoder_pos_embed is frozen (mae.py:92)
+
+
+# --------------------------------------------------------------------------------------------
+# a8: masked-MSE loss (mae.py:277-301)
+# --------------------------------------------------------------------------------------------
+class MaeLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, imgs, mask, patch, norm_pix, inplace_grad, prefix):
+        """pred: [N, prefix + L, P] (bf16 on the fast path); `prefix` leading rows per sample are ignored."""
+        _require_cuda(pred, "pred")
+        imgs = imgs.contiguous()
+        if imgs.dtype != F32:
+            imgs = imgs.float()
+        mask = mask.contiguous().float()
+        pred16 = pred.contiguous() if pred.dtype == BF16 else cast_bf16(pred.float())
+        N, C, H, W, D = imgs.shape
+        L = mask.numel() // N
+        ws = torch.empty((4 + N * L,), dtype=F32, device=pred.device)
+        call("hct_mae_loss_fwd", pred16.data_ptr(), int(prefix), imgs.data_ptr(), mask.data_ptr(), ws.data_ptr(), N, C,
+             H, W, D, patch, int(norm_pix), stream_ptr(pred.device))
+        ctx.save_for_backward(pred16, imgs, mask, ws)
+        ctx.meta = (patch, int(norm_pix), bool(inplace_grad) and pred.dtype == BF16, pred.dtype, tuple(pred.shape),
+                    int(prefix))
+        return ws[2]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred16, imgs, mask, ws = ctx.saved_tensors
+        patch, norm_pix, inplace, pdtype, pshape, prefix = ctx.meta
+        N, C, H, W, D = imgs.shape
+        dloss = dloss.contiguous().float()
+        dpred = pred16 if inplace else torch.empty_like(pred16)
+        call("hct_mae_loss_bwd", pred16.data_ptr(), prefix, imgs.data_ptr(), mask.data_ptr(), dloss.data_ptr(),
+             ws[1:2].data_ptr(), dpred.data_ptr(), N, C, H, W, D, patch, norm_pix, stream_ptr(pred16.device))
+        if pdtype != BF16:
+            dpred = cast_f32(dpred)
+        return dpred.view(pshape), None, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# DINO pieces (dino_head.py:37-41, losses.py:63-102, misc.py:386-397)
+# --------------------------------------------------------------------------------------------
+class L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        rows, dim = x.numel() // x.shape[-1], x.shape[-1]
+        y = torch.empty(x.shape, dtype=BF16, device=x.device)
+        inv = torch.empty((rows,), dtype=F32, device=x.device)
+        call("hct_l2norm_fwd", x.data_ptr(), int(x.dtype == BF16), y.data_ptr(), inv.data_ptr(), rows, dim,
+             stream_ptr(x.device))
+        ctx.save_for_backward(y, inv)
+        ctx.xdtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != BF16:
+            dy = cast_bf16(dy)
+        dx = torch.empty_like(y)
+        call("hct_l2norm_bwd", dy.data_ptr(), y.data_ptr(), inv.data_ptr(), dx.data_ptr(), inv.numel(), y.shape[-1],
+             stream_ptr(y.device))
+        return dx if ctx.xdtype == BF16 else cast_f32(dx)
+
+
+class WeightNormLinearFn(torch.autograd.Function):
+    """logits fp32 [n, K] = x16 @ (g * v / ||v||)^T   (weight_norm(Linear(bias=False)), dino_head.py:26-41)."""
+
+    @staticmethod
+    def forward(ctx, x16, weight_g, weight_v):
+        x16 = x16.contiguous()
+        n, dim = x16.shape
+        K = weight_v.shape[0]
+        dev = x16.device
+        w = torch.empty((K, dim), dtype=BF16, device=dev)
+        inv = torch.empty((K,), dtype=F32, device=dev)
+        call("hct_weightnorm_fwd", weight_v.data_ptr(), weight_g.data_ptr(), w.data_ptr(), inv.data_ptr(), K, dim,
+             stream_ptr(dev))
+        out = torch.empty((n, K), dtype=F32, device=dev)
+        gemm(x16, w, M=n, N=K, K=dim, lda=dim, ldb=dim, out=out, ldo=K, epi=EPI_F32)
+        ctx.save_for_backward(x16, w, inv, weight_v, weight_g)
+        return out
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x16, w, inv, weight_v, weight_g = ctx.saved_tensors
+        n, dim = x16.shape
+        K = w.shape[0]
+        dev = x16.device
+        d16 = take_grad16(dlogits)
+        if d16 is None:
+            d16 = cast_bf16(dlogits.contiguous())
+        dx = torch.empty((n, dim), dtype=BF16, device=dev)
+        gemm(d16, w, M=n, N=dim, K=K, lda=K, ldb=dim, b_mn=True, out=dx, ldo=dim, epi=EPI_BF16)
+        dv = None
+        if ctx.needs_input_grad[2]:
+            dw = linear_wgrad(d16, x16)                                                 # [K, dim] fp32
+            dv = torch.empty_like(weight_v)
+            call("hct_weightnorm_bwd", dw.data_ptr(), weight_v.data_ptr(), weight_g.data_ptr(), inv.data_ptr(),
+                 dv.data_ptr(), K, dim, stream_ptr(dev))
+        return dx, None, dv     # weight_g is frozen (norm_last_layer=True, dino_head.py:28-29)
+
+
+_GRAD16: Dict[int, torch.Tensor] = {}
+
+
+def take_grad16(t32: torch.Tensor) -> Optional[torch.Tensor]:
+    hit = _GRAD16.pop(t32.data_ptr(), None)
+    _GRAD16.clear()
+    return hit
+
+
+class DinoLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, student, teacher, center, ncrops, student_temp, teacher_temp):
+        _require_cuda(student, "student_output")
+        student = student.contiguous().float()
+        teacher = teacher.contiguous().float()
+        K = student.shape[1]
+        B = teacher.shape[0] // 2
+        dev = student.device
+        loss = torch.zeros((1,), dtype=F32, device=dev)
+        stats = torch.empty((2 * (ncrops + 2) * B,), dtype=F32, device=dev)
+        call("hct_dino_loss", student.data_ptr(), teacher.data_ptr(), center.data_ptr(), loss.data_ptr(),
+             stats.data_ptr(), None, None, B, ncrops, K, float(student_temp), float(teacher_temp), stream_ptr(dev))
+        ctx.save_for_backward(student, teacher, center.clone())
+        ctx.meta = (B, ncrops, K, float(student_temp), float(teacher_temp))
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        student, teacher, center = ctx.saved_tensors
+        B, ncrops, K, ts, tt = ctx.meta
+        dev = student.device
+        dloss = dloss.contiguous().float()
+        stats = torch.empty((2 * (ncrops + 2) * B,), dtype=F32, device=dev)
+        d16 = torch.empty(student.shape, dtype=BF16, device=dev)
+        call("hct_dino_loss", student.data_ptr(), teacher.data_ptr(), center.data_ptr(), None, stats.data_ptr(),
+             d16.data_ptr(), dloss.data_ptr(), B, ncrops, K, ts, tt, stream_ptr(dev))
+        d32 = cast_f32(d16)
+        _GRAD16.clear()
+        _GRAD16[d32.data_ptr()] = d16       # the prototype layer's backward consumes the bf16 copy directly
+        return d32, None, None, None, None, None
+
+
+def center_update(center: torch.Tensor, teacher: torch.Tensor, momentum: float) -> None:
+    """DINOLoss.update_center (losses.py:91-102): column sum -> all-reduce -> EMA, in place on `center`."""
+    import torch.distributed as dist
+    teacher = teacher.contiguous().float()
+    K = teacher.shape[1]
+    bc = colsum(teacher, K)
+    world = 1
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(bc)
+        world = dist.get_world_size()
+    call("hct_center_ema", center.data_ptr(), bc.data_ptr(), float(teacher.shape[0] * world), float(momentum), K,
+         stream_ptr(center.device))
+
+
+_EMA_TABLES: Dict[Tuple[int, int], Tuple[Tuple[int, ...], torch.Tensor]] = {}
+
+
+def ema_update(student_params: Sequence[torch.Tensor], teacher_params: Sequence[torch.Tensor], m: float) -> None:
+    """_update_momentum_encoder (misc.py:386-397) as ONE launch over all parameter tensors."""
+    ptrs: List[int] = []
+    for pq, pk in zip(student_params, teacher_params):
+        _require_cuda(pk, "teacher parameter")
+        if pq.dtype != F32 or pk.dtype != F32 or not pq.is_contiguous() or not pk.is_contiguous():
+            raise RuntimeError("ema_update expects contiguous fp32 parameters")
+        ptrs += [pk.data_ptr(), pq.data_ptr(), pk.numel()]
+    if not ptrs:
+        return
+    dev = teacher_params[0].device
+    key = (id(teacher_params[0]), len(ptrs))
+    sig = tuple(ptrs)
+    hit = _EMA_TABLES.get(key)
+    if hit is None or hit[0] != sig:
+        table = torch.tensor(ptrs, dtype=torch.int64).view(-1, 3).to(dev)
+        _EMA_TABLES[key] = (sig, table)
+    else:
+        table = hit[1]
+    call("hct_ema_multi", table.data_ptr(), table.shape[0], float(m), stream_ptr(dev))
+
+
+def window_scale_stack(hu: torch.Tensor, windows=((40, 80), (80, 200), (600, 2800)), out_dtype=F32) -> torch.Tensor:
+    """GPU MultipleWindowScaleStack (transforms.py:13-36): [..., 1, D, H, W] HU -> [..., nwin, D, H, W]."""
+    _require_cuda(hu, "HU volume")
+    if hu.dtype not in (F32, torch.int16):
+        hu = hu.float()
+    hu = hu.contiguous()
+    assert hu.shape[-4] == 1, "expected a single HU channel"
+    vox = hu.shape[-1] * hu.shape[-2] * hu.shape[-3]
+    nvol = hu.numel() // vox
+    nwin = len(windows)
+    a_min = (C.c_float * nwin)(*[float(l - w // 2) for l, w in windows])
+    a_max = (C.c_float * nwin)(*[float(l + w // 2) for l, w in windows])
+    out = torch.empty((*hu.shape[:-4], nwin, *hu.shape[-3:]), dtype=out_dtype, device=hu.device)
+    call("hct_window_scale_stack", hu.data_ptr(), int(hu.dtype == torch.int16), out.data_ptr(), int(out_dtype == BF16),
+         nvol, vox, nwin, a_min, a_max, stream_ptr(hu.device))
+    return out

@@ -1,0 +1,153 @@
+"""3-D Masked Autoencoder on B200 kernels.  Drop-in for `src/models/mae.py:20-317`."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .. import functional as HF
+from ..utils.patch_embedding import PatchEmbeddingBlock
+from ..utils.pos_embed import build_sincos_position_embedding
+from .attentionblock import AttentionBlock
+
+
+def _to_3tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
+
+
+class MaskedAutoencoderViT(nn.Module):
+    """Masked Autoencoder with a ViT backbone; same constructor, methods and state_dict as the reference."""
+
+    def __init__(self, input_size: int, patch_size: int, mask_ratio: float, in_chans: int = 1,
+                 dropout_rate: float = 0., spatial_dims: int = 3, patch_embed: str = "conv",
+                 pos_embed: str = "learnable", encoder_depth: int = 12, encoder_embed_dim: int = 768,
+                 encoder_mlp_dim: int = 3072, encoder_num_heads: int = 12, decoder_depth: int = 8,
+                 decoder_embed_dim: int = 768, decoder_mlp_dim: int = 3072, decoder_num_heads: int = 16,
+                 norm_pix_loss: bool = False, use_bias: bool = False, norm_layer=nn.LayerNorm):
+        super().__init__()
+        input_size, patch_size = _to_3tuple(input_size), _to_3tuple(patch_size)
+        self.input_size, self.patch_size = input_size, patch_size
+        self.mask_ratio, self.spatial_dims, self.pos_embed = mask_ratio, spatial_dims, pos_embed
+        self.norm_pix_loss = norm_pix_loss
+        self.encoder_embed_dim, self.decoder_embed_dim = encoder_embed_dim, decoder_embed_dim
+        self.encoder_num_heads, self.decoder_num_heads = encoder_num_heads, decoder_num_heads
+        self.out_chans = in_chans * np.prod(patch_size)
+        self.grid_size = [i // p for i, p in zip(input_size, patch_size)]
+        num_patches = int(np.prod(self.grid_size))
+        patch_dim = int(np.prod(patch_size))
+
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, encoder_embed_dim))
+        self.decoder_cls_token = nn.Parameter(torch.zeros(1, 1, decoder_embed_dim))
+        self.decoder_pos_embed = nn.Parameter(torch.zeros(1, num_patches, decoder_embed_dim), requires_grad=False)
+        self.patch_embedding = PatchEmbeddingBlock(img_size=input_size, patch_size=patch_size, in_channels=in_chans,
+                                                   hidden_size=encoder_embed_dim, num_heads=encoder_num_heads,
+                                                   patch_embed=patch_embed, pos_embed=pos_embed,
+                                                   dropout_rate=dropout_rate, spatial_dims=spatial_dims)
+        self.blocks = nn.ModuleList([
+            AttentionBlock(encoder_embed_dim, encoder_mlp_dim, encoder_num_heads, dropout_rate, qkv_bias=use_bias,
+                           save_attn=False, norm_layer=norm_layer) for _ in range(encoder_depth)])
+        self.decoder_blocks = nn.ModuleList([
+            AttentionBlock(decoder_embed_dim, decoder_mlp_dim, decoder_num_heads, dropout_rate, qkv_bias=use_bias,
+                           save_attn=False, norm_layer=norm_layer) for _ in range(decoder_depth)])
+        self.norm = norm_layer(encoder_embed_dim)
+        self.decoder_norm = norm_layer(decoder_embed_dim)
+        self.decoder_embed = nn.Linear(encoder_embed_dim, decoder_embed_dim, bias=use_bias)
+        self.decoder_pred = nn.Linear(decoder_embed_dim, patch_dim * in_chans, bias=use_bias)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, decoder_embed_dim))
+        self.initialize_weights()
+
+    # ---- init (mae.py:125-148)
+    def initialize_weights(self) -> None:
+        if self.pos_embed == "sincos":
+            with torch.no_grad():
+                self.decoder_pos_embed.data.copy_(
+                    build_sincos_position_embedding(self.grid_size, self.decoder_embed_dim, self.spatial_dims).float())
+        else:
+            nn.init.trunc_normal_(self.decoder_pos_embed, std=.02)
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        nn.init.trunc_normal_(self.decoder_cls_token, std=.02)
+        nn.init.trunc_normal_(self.mask_token, std=.02)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m: nn.Module) -> None:
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    # ---- layout helpers (mae.py:150-192); pure index shuffles, used outside the training step only
+    def patchify(self, x: Tensor) -> Tensor:
+        B, C, H, W, D = x.shape
+        ph, pw, pd = self.patch_size
+        gh, gw, gd = H // ph, W // pw, D // pd
+        x = x.reshape(B, C, gh, ph, gw, pw, gd, pd).permute(0, 2, 4, 6, 3, 5, 7, 1)
+        return x.reshape(B, gh * gw * gd, ph * pw * pd * C)
+
+    def unpatchify(self, x: Tensor, x_ori: Tensor) -> Tensor:
+        B, C, H, W, D = x_ori.shape
+        ph, pw, pd = self.patch_size
+        gh, gw, gd = H // ph, W // pw, D // pd
+        x = x.reshape(B, gh, gw, gd, ph, pw, pd, C).permute(0, 7, 1, 4, 2, 5, 3, 6)
+        return x.reshape(B, C, gh * ph, gw * pw, gd * pd)
+
+    # ---- masking (mae.py:194-218)
+    def _draw_indices(self, N: int, L: int, device):
+        len_keep = int(L * (1 - self.mask_ratio))
+        noise = getattr(self, "noise_override", None)   # parity tests hand in the oracle's noise tensor
+        if noise is None:
+            noise = torch.rand(N, L, device=device)     # same generator call, same order as the reference (mae.py:206)
+        return HF.mask_indices(noise.to(device), len_keep)
+
+    def random_masking(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        N, L, D = x.shape
+        ids_restore, ids_keep, mask = self._draw_indices(N, L, x.device)
+        x_masked = HF.GatherTokensFn.apply(x, ids_keep)
+        return x_masked, mask, ids_restore, ids_keep
+
+    # ---- encoder (mae.py:220-242).  Only the kept 25 % of the patches are ever embedded: the result equals
+    # patch-embedding everything and gathering, at a quarter of the GEMM work.
+    def forward_encoder(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        with torch.autocast(device_type="cuda", enabled=False):
+            N = x.shape[0]
+            L = int(np.prod(self.grid_size))
+            ids_restore, ids_keep, mask = self._draw_indices(N, L, x.device)
+            t = self.patch_embedding.embed(x, prefix=self.cls_token, ids_keep=ids_keep)
+            residual = None
+            for blk in self.blocks:
+                t, residual = blk(t, residual)
+            t = HF.LayerNormFn.apply(t, self.norm.weight, self.norm.bias, self.norm.eps, False)
+        return t, mask, ids_restore
+
+    # ---- decoder (mae.py:244-275)
+    def _decode_full(self, x: Tensor, ids_restore: Tensor) -> Tensor:
+        """bf16 [N, 1 + L, P] including the cls row (dropped by the callers)."""
+        y = HF.LinearFn.apply(x, self.decoder_embed.weight, self.decoder_embed.bias, False, False)
+        t = HF.DecoderAssembleFn.apply(y, ids_restore, self.mask_token, self.decoder_cls_token, self.decoder_pos_embed)
+        residual = None
+        for blk in self.decoder_blocks:
+            t, residual = blk(t, residual)
+        h = HF.LayerNormFn.apply(t, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm.eps, True)
+        return HF.LinearFn.apply(h, self.decoder_pred.weight, self.decoder_pred.bias, False, False)
+
+    def forward_decoder(self, x: Tensor, ids_restore: Tensor) -> Tensor:
+        with torch.autocast(device_type="cuda", enabled=False):
+            return self._decode_full(x, ids_restore)[:, 1:, :]
+
+    # ---- loss (mae.py:277-301)
+    def forward_loss(self, imgs: Tensor, pred: Tensor, mask: Tensor) -> Tensor:
+        with torch.autocast(device_type="cuda", enabled=False):
+            return HF.MaeLossFn.apply(pred.contiguous(), imgs, mask, self.patch_size[0], self.norm_pix_loss, False, 0)
+
+    def forward(self, x: Tensor) -> Tuple[Tensor, None, None]:
+        latent, mask, ids_restore = self.forward_encoder(x)
+        with torch.autocast(device_type="cuda", enabled=False):
+            pred_full = self._decode_full(latent, ids_restore)
+            loss = HF.MaeLossFn.apply(pred_full, x, mask, self.patch_size[0], self.norm_pix_loss, True, 1)
+        return loss, None, None

@@ -1,0 +1,226 @@
+/*
+ * hct_b200.h -- C ABI of libhct_b200.so: the B200 (sm_100a) kernels behind the HeadCT-Foundation
+ * 3D-ViT hot path.
+ *
+ * The reference (nirvanesque/headCT_foundation) has NO FFI / plugin registry: every GPU
+ * instruction it executes is a stock PyTorch library kernel called from Python.  The boundary a
+ * maintainer binds is therefore "one C entry point per library call site on the hot path"; each
+ * declaration below cites the reference call site(s) it replaces (file:line relative to the
+ * reference tree).  INTEGRATION.md shows the ctypes stub the reference side would add.
+ *
+ * Conventions:
+ *   - plain pointers + sizes; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every call enqueues work on the given stream (cudaStream_t passed as void*), never
+ *     synchronises the device and holds no global mutable state besides per-process caches;
+ *   - return value: 0 = ok, 1 = invalid argument, 2 = CUDA error, 3 = unsupported shape;
+ *     hct_last_error() returns a thread-local message for the last non-zero return;
+ *   - "bf16" = __nv_bfloat16 storage, row-major with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef HCT_B200_H
+#define HCT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hct_stream_t; /* cudaStream_t */
+
+const char* hct_last_error(void);
+int hct_abi_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+long long hct_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM core (tcgen05 / TMEM / TMA):  C[M,N] = epilogue( A[M,K] * B[N,K]^T )
+ * replaces every nn.Linear / Conv3d(k=s) forward + backward on the path:
+ *   attentionblock.py:54 (qkv), :64 (proj); monai MLPBlock linear1/linear2 (attentionblock.py:98);
+ *   patch_embedding.py:149 (Conv3d as GEMM); mae.py:255 (decoder_embed), :272 (decoder_pred);
+ *   dino_head.py:38,40 (head MLP, prototype layer) -- and their autograd dgrad / wgrad.
+ * Operand storage:  K-major  : X[row * ld + k]        (row = m for A, n for B)
+ *                   MN-major : X[k * ld + row]        (the transposed storage; used by dgrad/wgrad)
+ * ------------------------------------------------------------------------------------------- */
+enum hct_epilogue {
+  HCT_EPI_BF16 = 0,       /* out_bf16 = alpha*acc + bias                                        */
+  HCT_EPI_GELU_BF16 = 1,  /* t = acc + bias; out2_bf16 = t (if out2); out_bf16 = gelu_erf(t)     */
+  HCT_EPI_RES_F32 = 2,    /* out_f32 = res_f32 + acc + bias          (out may alias res)         */
+  HCT_EPI_POS_F32 = 3,    /* out_f32[remap(r)] = acc + bias + pos[pos_idx ? pos_idx[r] : r % pos_period] */
+  HCT_EPI_DGELU_BF16 = 4, /* out_bf16 = acc * gelu_erf'(aux_bf16)                                */
+  HCT_EPI_F32 = 5,        /* out_f32 = alpha*acc + bias                                          */
+  HCT_EPI_ATOMIC_F32 = 6  /* out_f32 += alpha*acc   (split-K reduction; out pre-zeroed by caller) */
+};
+
+typedef struct hct_gemm_desc {
+  int32_t M, N, K;
+  const void* A; int64_t lda; int32_t a_mn_major;
+  const void* B; int64_t ldb; int32_t b_mn_major;
+  int32_t epilogue;
+  void* out;  int64_t ldo;
+  void* out2; int64_t ldo2;
+  const float* bias;                 /* [N] fp32 or NULL */
+  const float* res; int64_t ldres;   /* fp32 residual */
+  const void* aux;  int64_t ldaux;   /* bf16 pre-activation (DGELU) */
+  const float* pos; int64_t ldpos;   /* fp32 position table */
+  const int32_t* pos_idx;            /* per-row index into pos, or NULL */
+  int32_t pos_period;
+  /* output row remap: r -> (r / rows_in) * rows_out + (r % rows_in) + row_off; rows that fall
+   * outside [0, rows_out) within their group are skipped.  rows_in == 0 disables the remap. */
+  int32_t rows_in, rows_out, row_off;
+  float alpha;
+  int32_t splits;                    /* split-K factor for HCT_EPI_ATOMIC_F32; 0 = auto */
+} hct_gemm_desc;
+
+int hct_gemm_bf16(const hct_gemm_desc* desc, hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels (HBM-bound)
+ * ------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm forward: attentionblock.py:97-98, mae.py:240,271, vit.py:169.
+ * x fp32 [rows, dim] -> y (bf16 if y_bf16 else fp32) ; mean/rstd fp32 [rows] (may be NULL). */
+int hct_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_bf16,
+                      float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
+                      hct_stream_t stream);
+/* LayerNorm backward (autograd of the call sites above).  dy: bf16 (dy_bf16) or fp32 [rows, dim].
+ * dx_out_f32 = (dres_in ? dres_in : 0) + dLN ; optional bf16 copy dx_out_bf16 ;
+ * dgamma/dbeta fp32 [dim] are ACCUMULATED (+=) with atomics. */
+int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* gamma,
+                      const float* mean, const float* rstd, const float* dres_in,
+                      float* dx_out_f32, void* dx_out_bf16, float* dgamma, float* dbeta,
+                      int64_t rows, int32_t dim, hct_stream_t stream);
+/* fp32 -> bf16 cast of a contiguous buffer (autocast weight casts). */
+int hct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, hct_stream_t stream);
+int hct_cast_bf16_to_f32(const void* src, float* dst, int64_t n, hct_stream_t stream);
+/* out_bf16 = dy_bf16 * gelu_erf'(pre_bf16)  (nn.GELU backward in the DINO head MLP, dino_head.py:16-21) */
+int hct_gelu_bwd(const void* dy, const void* pre, void* out, int64_t n, hct_stream_t stream);
+/* out[c] += sum_r X[r, c]   (bias gradients; X bf16 or fp32, ld in elements). */
+int hct_colsum(const void* x, int x_bf16, int64_t ld, float* out, int64_t rows, int32_t cols,
+               hct_stream_t stream);
+/* dst[b, row_off + r, :] = src[r, :] for b < batch, r < nrows  (cls / register tokens:
+ * mae.py:233-234, vit.py:147-160). */
+int hct_broadcast_rows(const float* src, float* dst, int32_t batch, int32_t nrows,
+                       int64_t dst_rows_per_batch, int32_t row_off, int32_t dim, hct_stream_t stream);
+/* out[r, :] += sum_b src[b, row_off + r, :]  (gradient of the above). */
+int hct_reduce_rows(const float* src, float* out, int32_t batch, int32_t nrows,
+                    int64_t src_rows_per_batch, int32_t row_off, int32_t dim, hct_stream_t stream);
+/* fp32 rows -> bf16 rows with a per-group row window (slices the cls/register prefix off a gradient
+ * or casts a GEMM operand):  dst[g*rows_per_group + r, :] = bf16(src[(g*src_rows_per_group + src_row_off + r) * src_ld ...]) */
+int hct_copy_rows_f32_to_bf16(const float* src, int64_t src_ld, int64_t src_rows_per_group,
+                              int32_t src_row_off, void* dst, int64_t dst_ld, int64_t groups,
+                              int32_t rows_per_group, int32_t dim, hct_stream_t stream);
+/* out[idx[r], :] += src[r, :]  (fp32 atomics; gradient of the position-embedding gather for the
+ * kept patches, patch_embedding.py:156 under mae.py:211-212).  src bf16 [rows, dim]. */
+int hct_scatter_add_rows(const void* src_bf16, const int32_t* idx, float* out, int64_t rows,
+                         int32_t dim, hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MAE-specific kernels
+ * ------------------------------------------------------------------------------------------- */
+/* MultipleWindowScaleStack (src/data/transforms.py:22-36, windows :130): HU -> 3 clipped windows.
+ * hu: [nvol, 1, vox] fp32 (hu_i16 = 0) or int16 (hu_i16 = 1); out: [nvol, nwin, vox] fp32 or bf16.
+ * a_min/a_max: HOST arrays of nwin floats. */
+int hct_window_scale_stack(const void* hu, int hu_i16, void* out, int out_bf16, int64_t nvol,
+                           int64_t vox, int32_t nwin, const float* a_min, const float* a_max,
+                           hct_stream_t stream);
+/* im2col for Conv3d(k = s = patch) (patch_embedding.py:149): x fp32 [B,C,H,W,D] -> cols bf16
+ * [rows, C*p^3] in (c,ph,pw,pd) order.  patch_ids (int64 [B, rows_per_vol]) selects which patches
+ * are materialised (MAE keeps 25 %: mae.py:211-212); NULL = all patches in (gh,gw,gd) order.
+ * pos_idx_out (int32 [rows], may be NULL) receives the patch index of each row. */
+int hct_patchify(const float* x, void* cols, const int64_t* patch_ids, int32_t* pos_idx_out,
+                 int32_t B, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
+                 int32_t rows_per_vol, hct_stream_t stream);
+/* random_masking index part (mae.py:205-216): stable ascending argsort of noise rows.
+ * noise fp32 [N, L] -> ids_restore int64 [N, L], ids_keep int64 [N, len_keep], mask fp32 [N, L]. */
+int hct_mask_indices(const float* noise, int64_t* ids_restore, int64_t* ids_keep, float* mask,
+                     int32_t N, int32_t L, int32_t len_keep, hct_stream_t stream);
+/* token gather (mae.py:212): dst[n, row_off + j, :] = src[n, ids[n, j], :]   (fp32 rows). */
+int hct_gather_tokens(const float* src, const int64_t* ids, float* dst, int32_t N, int32_t L,
+                      int32_t n_ids, int64_t dst_rows_per_batch, int32_t row_off, int32_t dim,
+                      hct_stream_t stream);
+/* gradient of the gather: dsrc[n, ids[n,j], :] = ddst[n, row_off + j, :], other rows zero. */
+int hct_scatter_tokens(const float* ddst, const int64_t* ids, float* dsrc, int32_t N, int32_t L,
+                       int32_t n_ids, int64_t ddst_rows_per_batch, int32_t row_off, int32_t dim,
+                       hct_stream_t stream);
+/* decoder input assembly (mae.py:257-265): y bf16 [N, 1+keep, dim] (decoder_embed output) ->
+ * out fp32 [N, 1+L, dim]: row 0 = y[:,0] + dec_cls ; row 1+l = (ids_restore[n,l] < keep ?
+ * y[n, 1+ids_restore[n,l]] : mask_token) + dec_pos[l]. */
+int hct_decoder_assemble(const void* y, const int64_t* ids_restore, const float* mask_token,
+                         const float* dec_cls, const float* dec_pos, float* out, int32_t N,
+                         int32_t L, int32_t keep, int32_t dim, hct_stream_t stream);
+/* its gradient: dy bf16 [N, 1+keep, dim]; dmask_token / ddec_cls fp32 [dim] accumulated (+=). */
+int hct_decoder_assemble_bwd(const float* dout, const int64_t* ids_restore, void* dy,
+                             float* dmask_token, float* ddec_cls, int32_t N, int32_t L,
+                             int32_t keep, int32_t dim, hct_stream_t stream);
+/* patchify + forward_loss (mae.py:150-170, :289-299).  pred bf16 [N, prefix + L, p^3*C] in
+ * (ph,pw,pd,c) order -- `pred_prefix_rows` leading rows per sample (the cls row, dropped at
+ * mae.py:273) are skipped; imgs fp32 [N,C,H,W,D], mask fp32 [N,L].  loss_out fp32 [4 + N*L]:
+ * [0] = sum(mask*mse), [1] = sum(mask), [2] = loss = [0]/[1], [4..) = per-patch MSE workspace.
+ * The final reduction is a fixed-order tree (deterministic). */
+int hct_mae_loss_fwd(const void* pred, int32_t pred_prefix_rows, const float* imgs,
+                     const float* mask, float* loss_out, int32_t N, int32_t C, int32_t H, int32_t W,
+                     int32_t D, int32_t p, int32_t norm_pix, hct_stream_t stream);
+/* dpred bf16 (same layout as pred, may alias it) = dloss * mask * 2 (pred - target) / (P * sum(mask));
+ * rows with mask == 0 and the prefix rows are written as zeros.  dloss, mask_sum: DEVICE scalars. */
+int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, const float* imgs,
+                     const float* mask, const float* dloss, const float* mask_sum, void* dpred,
+                     int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
+                     int32_t norm_pix, hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention (F.scaled_dot_product_attention, attentionblock.py:61; no mask, no dropout)
+ * qkv bf16 [B, S, 3, H, hd] (the qkv Linear's natural output, attentionblock.py:54);
+ * out bf16 [B, S, H*hd]; lse fp32 [B, H, S].  hd in {32, 48, 64}.
+ * ------------------------------------------------------------------------------------------- */
+int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H,
+                      int32_t hd, hct_stream_t stream);
+/* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
+int hct_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                      void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd,
+                      hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DINO kernels
+ * ------------------------------------------------------------------------------------------- */
+/* F.normalize(p=2, dim=-1) (dino_head.py:39): x bf16/fp32 [rows, dim] -> y bf16, inv_norm fp32[rows] */
+int hct_l2norm_fwd(const void* x, int x_bf16, void* y_bf16, float* inv_norm, int64_t rows, int32_t dim,
+                   hct_stream_t stream);
+int hct_l2norm_bwd(const void* dy_bf16, const void* y_bf16, const float* inv_norm, void* dx_bf16,
+                   int64_t rows, int32_t dim, hct_stream_t stream);
+/* weight_norm (dino_head.py:26-29): w_bf16[r,:] = g[r] * v[r,:] / ||v[r,:]|| ; inv_norm fp32[rows] */
+int hct_weightnorm_fwd(const float* v, const float* g, void* w_bf16, float* inv_norm, int64_t rows,
+                       int32_t dim, hct_stream_t stream);
+/* dv = g*inv*(dw - (dw . vhat) vhat)  (g frozen: norm_last_layer=True, dino_head.py:28-29) */
+int hct_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm,
+                       float* dv, int64_t rows, int32_t dim, hct_stream_t stream);
+/* DINOLoss.forward (losses.py:63-89).  student fp32 [ncrops*B, K], teacher fp32 [2*B, K],
+ * center fp32 [K].  loss_out fp32[1] (may be NULL) is ACCUMULATED into (zero it first).
+ * stats_ws: fp32 [2*(ncrops+2)*B] (row max / log-sum-exp; recomputed on every call).
+ * If dstudent (bf16 [ncrops*B, K]) is non-NULL the gradient wrt student is written, scaled by
+ * *dloss (DEVICE scalar, NULL = 1). */
+int hct_dino_loss(const float* student, const float* teacher, const float* center, float* loss_out,
+                  float* stats_ws, void* dstudent_bf16, const float* dloss, int32_t B, int32_t ncrops,
+                  int32_t K, float student_temp, float teacher_temp, hct_stream_t stream);
+/* update_center (losses.py:91-102) split around the all-reduce: colsum then EMA.
+ *   hct_colsum(teacher...) -> batch_center ; [all-reduce] ; center = m*center + (1-m)*bc/denom */
+int hct_center_ema(float* center, const float* batch_center_sum, float denom, float momentum,
+                   int32_t K, hct_stream_t stream);
+/* _update_momentum_encoder (misc.py:386-397): one launch over a device table of n tensors.
+ * table: int64 [n, 3] = {teacher_ptr, student_ptr, numel}. p_k = m*p_k + (1-m)*p_q (fp32). */
+int hct_ema_multi(const int64_t* table, int32_t n, float m, hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Train-step glue: per-parameter clip (misc.py:374-383) + AdamW
+ * (optimizers.py:354-360) as one multi-tensor launch each.
+ * table: int64 [n, 5] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel}.
+ * norms_ws: fp32 [n] workspace receiving each gradient's SQUARED L2 norm.
+ * ------------------------------------------------------------------------------------------- */
+int hct_grad_norms_multi(const int64_t* table, int32_t n, float* norms_ws, hct_stream_t stream);
+int hct_adamw_multi(const int64_t* table, int32_t n, const float* norms_ws, float clip, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                    hct_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCT_B200_H */
