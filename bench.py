@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- MAE ViT-B 3-D pre-training throughput (volumes/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+A "step" is one full pre-training step of `MaskedAutoencoderViT` at the `mae_HeadCT.yaml` shape on a
+synthetic batch: forward + masked-MSE loss + backward (+ DDP gradient all-reduce for N > 1) + fused
+per-parameter-clip/AdamW update.  Workload at N = 1 is BASELINE.json configs[1] ("MAE ViT-B 3D
+pretraining bf16, mask ratio 0.75, batch 256"; DATA.BATCH_SIZE is per GPU in the reference,
+config.py:15) -- weak scaling: every rank processes `--batch` volumes per step.
+
+  value  volumes/s with the step's input volume already resident in HBM (device-timed, max over ranks)
+  e2e    same metric through the public API from HOST buffers: pinned int16 HU volumes -> H2D ->
+         on-GPU MultipleWindowScaleStack -> model step -> loss read back (D2H), copies inside the timed region
+  roofline   the tcgen05 GEMM kernel: sum(2MNK) / sum(kernel time) over every launch of the timed region,
+             measured with CUDA events on the launching stream (hct_profile_*), vs measured bf16 peak
+  cpu_baseline  the CPU oracle port of the reference path (fp32, B = 2) timed on this box's host cores
+
+`--impl reference` times only that CPU arm (the reference is a Python package that cannot travel to the
+GPU box; the oracle is its pinned restatement) and prints the same JSON shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mae_pretrain_volumes_per_sec"
+UNIT = "volumes/s"
+MAE_FWD_BWD_GFLOP = 282.133      # algorithmic GFLOP per volume, BASELINE.md section 3
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]), src="measured (MEASURED_PEAKS.json, sustained)")
+    except Exception:
+        return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def cpu_reference_arm(steps: int, warmup: int):
+    """The reference path on host cores: oracle restatement of MaskedAutoencoderViT fwd+loss+bwd, fp32, B = 2
+    (BASELINE.json configs[0] / BASELINE.md section 4)."""
+    import torch
+    from oracle import headct_oracle as O, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.MAE_FULL
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in synth.mae_state_dict(cfg, seed=4).items()}
+    torch.manual_seed(42)
+    x = torch.rand(2, 3, 96, 96, 96)
+    times = []
+    for it in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        noise = torch.rand(2, 512)
+        t0 = time.perf_counter()
+        out = O.mae_forward(sd, x, noise, patch=(12, 12, 12), mask_ratio=0.75, enc_heads=12, dec_heads=16, norm_pix=False)
+        out["loss"].backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    cpu_model = ""
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), "")
+    except Exception:
+        pass
+    return dict(value=2.0 / med, unit=UNIT, cores=cores, kind="port", cpu=cpu_model, ms_per_step=med * 1e3,
+                sample=f"oracle MaskedAutoencoderViT (mae_HeadCT.yaml shape) fwd+loss+bwd, fp32, batch 2, "
+                       f"{len(times)} timed steps after {warmup} warm-up, median")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(3, min(args.steps, 8))
+    base = cpu_reference_arm(steps, max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MAE ViT-B 3D pretraining step (mae_HeadCT.yaml shape), mask 0.75, CPU fp32, batch 2 "
+                                   "(bounded sample of the batch-256 workload)", "patch": 12, "volume": "3x96x96x96"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import headct_foundation_b200 as H
+    from headct_foundation_b200 import _cabi
+    from headct_foundation_b200.optim import FusedAdamW
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path); "
+                           "use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from headct_foundation_b200.configs import MAE_HEADCT
+    cfg = dict(MAE_HEADCT)
+    B = args.batch
+    torch.manual_seed(42 + rank)      # SEED + rank (main_pretrain_mae.py:213)
+    model = H.MaskedAutoencoderViT(**cfg).to(dev).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    step_model = model
+    if world > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
+                                                               gradient_as_bucket_view=True, bucket_cap_mb=64)
+    # lr scaling rule of main_pretrain_mae.py:149-152; TRAIN.* values from mae_HeadCT.yaml
+    lr = 1.5e-4 * B * world / 256
+    opt = FusedAdamW(params, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05, clip_grad=3.0)
+
+    # ---- inputs: HU volumes on the host (pinned, int16) and their windowed fp32 form resident in HBM
+    n_host = 2
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_hu = [torch.randint(-1024, 3072, (B, 1, 96, 96, 96), generator=g, dtype=torch.int16).pin_memory()
+               for _ in range(n_host)]
+    window = H.MultipleWindowScaleStack(keys=["image"])
+    resident = window({"image": host_hu[0].to(dev)})["image"]            # fp32 [B,3,96,96,96], 10.6 MB / volume
+
+    def train_step(x):
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = step_model(x)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        train_step(resident)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    lib = _cabi.lib()
+    lib.hct_profile_enable(1)
+    n0 = _cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            loss = train_step(resident)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _cabi.launch_count() - n0
+    gemm_ms, gemm_fl, gemm_n = C.c_double(), C.c_double(), C.c_longlong()
+    lib.hct_profile_collect(C.byref(gemm_ms), C.byref(gemm_fl), C.byref(gemm_n))
+    lib.hct_profile_enable(0)
+    final_loss = float(loss.item())
+
+    # ---- timed region 2: end to end from host buffers (H2D of the next batch overlaps the current step)
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_hu = [torch.empty((B, 1, 96, 96, 96), dtype=torch.int16, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dev_hu[i % 2].copy_(host_hu[i % n_host], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    e2e_steps = args.steps
+    for e in consumed:
+        e.record()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    prefetch(0)
+    losses = []
+    for i in range(e2e_steps):
+        if i + 1 < e2e_steps:
+            prefetch(i + 1)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        x = window({"image": dev_hu[i % 2]})["image"]
+        consumed[i % 2].record()
+        loss = train_step(x)
+        losses.append(float(loss.item()))          # D2H read of the step's result, every step
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        tl = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tl)
+        launches_all = int(tl.item())
+    else:
+        launches_all = launches
+
+    if rank == 0:
+        peaks = _peaks()
+        value = B * world * args.steps / (ms / 1e3)
+        e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
+        achieved = (gemm_fl.value / 1e12) / (gemm_ms.value / 1e3) if gemm_ms.value > 0 else 0.0
+        step_tflops = value / world * MAE_FWD_BWD_GFLOP / 1e3
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_arm(5, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "MAE ViT-B 3D pretraining step (mae_HeadCT.yaml: 96^3x3 volumes, patch 12, mask 0.75, "
+                                   "enc 12x768 12h, dec 8x768 16h), fwd+loss+bwd+per-param-clip+AdamW"
+                                   + (", DDP grad all-reduce" if world > 1 else ""),
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2_policy": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no explicit flush"
+                                    % (resident.numel() * 4 / 1e6),
+                       "final_loss": final_loss},
+            "roofline": {"bound": "tensor", "kernel": "hct_gemm_tcgen05_kernel (all epilogues)", "achieved": achieved,
+                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                         "peak_source": peaks["src"], "gemm_launches": int(gemm_n.value),
+                         "gemm_ms_per_step": gemm_ms.value / args.steps,
+                         "gemm_share_of_step": gemm_ms.value / ms if ms > 0 else None,
+                         "step_algorithmic_tflops_per_gpu": step_tflops,
+                         "step_frac_of_peak": step_tflops / peaks["tflops"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
+                    "h2d_bytes_per_step": int(host_hu[0].numel() * 2), "d2h_bytes_per_step": 4,
+                    "path": "pinned int16 HU -> H2D (copy stream, double buffered) -> MultipleWindowScaleStack (GPU) -> "
+                            "MaskedAutoencoderViT.forward/backward -> FusedAdamW -> loss.item()"},
+            "gpu_launches": launches_all,
+            "clocks": clocks.summary(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="volumes per GPU per step (DATA.BATCH_SIZE semantics)")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "hct_center_ema": [_P, _P, _F, _F, _I32, _P],
     "hct_ema_multi": [_P, _I32, _F, _P],
     "hct_grad_norms_multi": [_P, _I32, _P, _P],
+    "hct_profile_enable": [_I32],
+    "hct_profile_collect": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
     "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("hct_last_error", "hct_abi_version", "hct_launch_count")

@@ -12,6 +12,9 @@
 void hct_set_error(const char* fmt, ...);
 int hct_check_launch(const char* what);   // cudaGetLastError -> HCT_ERR_CUDA + message
 int hct_num_sms();
+bool hct_prof_enabled();
+void* hct_prof_begin(cudaStream_t st);
+void hct_prof_end(void* begin_event, cudaStream_t st, double flops);
 
 #define HCT_REQUIRE(cond, ...)                \
   do {                                        \

@@ -523,13 +523,16 @@ extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
 
   const int total_work = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int grid = total_work < sms ? total_work : sms;
+  void* prof = hct_prof_enabled() ? hct_prof_begin(stream) : nullptr;
   switch (d->epilogue) {
-    case HCT_EPI_BF16: return launch<HCT_EPI_BF16>(tmA, tmB, p, grid, stream);
-    case HCT_EPI_GELU_BF16: return launch<HCT_EPI_GELU_BF16>(tmA, tmB, p, grid, stream);
-    case HCT_EPI_RES_F32: return launch<HCT_EPI_RES_F32>(tmA, tmB, p, grid, stream);
-    case HCT_EPI_POS_F32: return launch<HCT_EPI_POS_F32>(tmA, tmB, p, grid, stream);
-    case HCT_EPI_DGELU_BF16: return launch<HCT_EPI_DGELU_BF16>(tmA, tmB, p, grid, stream);
-    case HCT_EPI_F32: return launch<HCT_EPI_F32>(tmA, tmB, p, grid, stream);
-    default: return launch<HCT_EPI_ATOMIC_F32>(tmA, tmB, p, grid, stream);
+    case HCT_EPI_BF16: rc = launch<HCT_EPI_BF16>(tmA, tmB, p, grid, stream); break;
+    case HCT_EPI_GELU_BF16: rc = launch<HCT_EPI_GELU_BF16>(tmA, tmB, p, grid, stream); break;
+    case HCT_EPI_RES_F32: rc = launch<HCT_EPI_RES_F32>(tmA, tmB, p, grid, stream); break;
+    case HCT_EPI_POS_F32: rc = launch<HCT_EPI_POS_F32>(tmA, tmB, p, grid, stream); break;
+    case HCT_EPI_DGELU_BF16: rc = launch<HCT_EPI_DGELU_BF16>(tmA, tmB, p, grid, stream); break;
+    case HCT_EPI_F32: rc = launch<HCT_EPI_F32>(tmA, tmB, p, grid, stream); break;
+    default: rc = launch<HCT_EPI_ATOMIC_F32>(tmA, tmB, p, grid, stream); break;
   }
+  if (prof != nullptr) hct_prof_end(prof, stream, 2.0 * d->M * d->N * static_cast<double>(d->K));
+  return rc;
 }

@@ -1,5 +1,6 @@
 // Error reporting, launch accounting and device queries shared by all libhct_b200 entry points.
 #include <atomic>
+#include <vector>
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -38,6 +39,47 @@ int hct_num_sms() {
     sms[dev] = n;
   }
   return sms[dev];
+}
+
+// ---- optional per-launch timing of the GEMM kernel (bench.py's roofline numbers) ----
+namespace {
+struct ProfRec { cudaEvent_t a, b; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+}  // namespace
+
+bool hct_prof_enabled() { return g_prof_on; }
+void* hct_prof_begin(cudaStream_t st) {
+  cudaEvent_t e = get_event();
+  cudaEventRecord(e, st);
+  return e;
+}
+void hct_prof_end(void* begin_event, cudaStream_t st, double flops) {
+  cudaEvent_t e = get_event();
+  cudaEventRecord(e, st);
+  g_prof.push_back(ProfRec{static_cast<cudaEvent_t>(begin_event), e, flops});
+}
+
+extern "C" int hct_profile_enable(int on) { g_prof_on = on != 0; return HCT_OK; }
+// Sums elapsed time / flops over all GEMM launches recorded since the last collect (synchronises on their events).
+extern "C" int hct_profile_collect(double* total_ms, double* total_flops, long long* launches) {
+  double ms = 0, fl = 0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventSynchronize(r.b);
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; fl += r.flops; }
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = static_cast<long long>(g_prof.size());
+  g_prof.clear();
+  return HCT_OK;
 }
 
 extern "C" const char* hct_last_error(void) { return g_err; }

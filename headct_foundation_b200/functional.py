@@ -8,7 +8,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -31,7 +30,7 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 # bf16 shadow copies of fp32 parameters (what autocast would cast on every call), refreshed only
 # when the parameter's version counter changes (i.e. after an optimizer step / load_state_dict).
 # --------------------------------------------------------------------------------------------
-_W16: "weakref.WeakKeyDictionary[torch.Tensor, Tuple[int, int, torch.Tensor]]" = weakref.WeakKeyDictionary()
+_W16_ATTR = "_hct_bf16_shadow"     # (data_ptr, version, bf16 tensor) stored on the parameter object itself
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -53,16 +52,12 @@ def w16(p: torch.Tensor) -> torch.Tensor:
     """bf16 copy of a (2-D viewable) fp32 weight, cached on (data_ptr, version)."""
     _require_cuda(p, "weight")
     key = (p.data_ptr(), p._version)
-    hit = _W16.get(p)
+    hit = getattr(p, _W16_ATTR, None)
     if hit is not None and hit[0] == key[0] and hit[1] == key[1]:
         return hit[2]
     t = cast_bf16(p.detach())
-    _W16[p] = (key[0], key[1], t)
+    setattr(p, _W16_ATTR, (key[0], key[1], t))
     return t
-
-
-def clear_weight_cache() -> None:
-    _W16.clear()
 
 
 # --------------------------------------------------------------------------------------------

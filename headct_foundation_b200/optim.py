@@ -1,0 +1,69 @@
+"""Train-step glue as multi-tensor kernels.
+
+`FusedAdamW` reproduces what the reference engines do between backward and the next forward --
+`clip_gradients` (per-parameter L2 clip, src/utils/misc.py:374-383) followed by `torch.optim.AdamW.step`
+(src/utils/optimizers.py:354-360) -- in two launches over all parameters, with no host sync
+(the reference pays one `.item()` per parameter tensor).  State layout (`exp_avg`, `exp_avg_sq`, `step`)
+matches torch.optim.AdamW so optimizer checkpoints interchange.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._cabi import call, stream_ptr
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, clip_grad: float = 0.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_grad=clip_grad)
+        super().__init__(params, defaults)
+        self._tables = {}
+
+    def _table(self, gi, group):
+        ps = [p for p in group["params"] if p.grad is not None]
+        rows = []
+        for p in ps:
+            if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_cuda:
+                raise RuntimeError("FusedAdamW expects fp32 CUDA parameters and gradients")
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.tensor(0.0)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            if g is not p.grad:
+                p.grad = g
+            rows.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
+        sig = tuple(rows)
+        hit = self._tables.get(gi)
+        if hit is None or hit[0] != sig:
+            dev = ps[0].device
+            table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            norms = torch.empty(len(rows), dtype=torch.float32, device=dev)
+            hit = (sig, table, norms)
+            self._tables[gi] = hit
+        return ps, hit[1], hit[2]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            if not any(p.grad is not None for p in group["params"]):
+                continue
+            ps, table, norms = self._table(gi, group)
+            step = int(self.state[ps[0]]["step"].item()) + 1
+            for p in ps:
+                self.state[p]["step"] += 1
+            st = stream_ptr(ps[0].device)
+            clip = float(group.get("clip_grad", 0.0) or 0.0)
+            if clip > 0:
+                call("hct_grad_norms_multi", table.data_ptr(), table.shape[0], norms.data_ptr(), st)
+            b1, b2 = group["betas"]
+            call("hct_adamw_multi", table.data_ptr(), table.shape[0], norms.data_ptr(), clip, float(group["lr"]),
+                 float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), step, st)
+        return loss

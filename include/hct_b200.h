@@ -32,6 +32,11 @@ const char* hct_last_error(void);
 int hct_abi_version(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 long long hct_launch_count(void);
+/* Measurement aid (bench.py roofline): when enabled every hct_gemm_bf16 launch is bracketed by CUDA
+ * events on its own stream; collect() returns the summed kernel time, 2*M*N*K flops and launch count
+ * since the previous collect (it waits for those events). */
+int hct_profile_enable(int on);
+int hct_profile_collect(double* total_ms, double* total_flops, long long* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM core (tcgen05 / TMEM / TMA):  C[M,N] = epilogue( A[M,K] * B[N,K]^T )

@@ -280,6 +280,17 @@ def main():
     dino_head_full_case(ns, "dino_head_full")
     layout["linear_classifier"] = _layout(ns.classifier.LinearClassifier(768, 2))
     misc_cases(ns)
+    # default-initialisation fingerprints: same seed -> same init as the reference constructors
+    init = {}
+    for nm, ctor, cfg in (("mae_small", ns.mae.MaskedAutoencoderViT, synth.MAE_SMALL),
+                          ("vit_small", ns.vit.ViT, synth.VIT_SMALL)):
+        torch.manual_seed(123)
+        mod = ctor(**cfg)
+        init[nm] = {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in mod.state_dict().items()}
+    torch.manual_seed(123)
+    hd = ns.dino_head.DINOHead(**synth.DINO_HEAD_SMALL)
+    init["dino_head_small"] = {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in hd.state_dict().items()}
+    layout["init_fingerprints_seed123"] = init
     with open(os.path.join(GOLD, "layout.json"), "w") as f:
         json.dump(layout, f, indent=0)
     print("golden vectors written to", GOLD)

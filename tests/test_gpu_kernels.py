@@ -153,7 +153,8 @@ def test_attention_fwd_bwd(cuda, HF, B, S, H, hd):
     d = dqkv.float().view(B, S, 3, D)
     dr = dref.view(B, S, 3, D)
     for i, name in enumerate("qkv"):
-        assert _rel(d[:, :, i], dr[:, :, i]) < 1.5e-2, name
+        err = (d[:, :, i] - dr[:, :, i]).double().norm().item()
+        assert err < 1.5e-2 * dr[:, :, i].double().norm().item() + 1e-5, name   # S = 1: dq and dk are exactly zero
 
 
 # ------------------------------------------------------------------ masking (bit exact)
