@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("rows_in", C.c_int32), ("rows_out", C.c_int32), ("row_off", C.c_int32),
         ("alpha", C.c_float),
         ("splits", C.c_int32),
+        ("colsum", C.c_void_p),
     ]
 
 
@@ -42,7 +43,7 @@ _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 _SIGNATURES = {
     "hct_gemm_bf16": [C.POINTER(GemmDesc), _P],
     "hct_layernorm_fwd": [_P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _F, _P],
-    "hct_layernorm_bwd": [_P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    "hct_layernorm_bwd": [_P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     "hct_cast_f32_to_bf16": [_P, _P, _I64, _P],
     "hct_cast_bf16_to_f32": [_P, _P, _I64, _P],
     "hct_colsum": [_P, _I32, _I64, _P, _I64, _I32, _P],
@@ -71,6 +72,7 @@ _SIGNATURES = {
     "hct_ema_multi": [_P, _I32, _F, _P],
     "hct_grad_norms_multi": [_P, _I32, _P, _P],
     "hct_profile_enable": [_I32],
+    "hct_gemm_set_cta_pair": [_I32],
     "hct_profile_collect": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
     "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
 }
@@ -98,6 +100,8 @@ def lib() -> C.CDLL:
         L.hct_last_error.argtypes = []
         L.hct_abi_version.restype = C.c_int
         L.hct_launch_count.restype = C.c_longlong
+        if os.environ.get("HCT_GEMM_CTA_PAIR", "1") == "0":      # debugging aid: single-CTA tcgen05 kernel
+            L.hct_gemm_set_cta_pair(0)
         _lib = L
     return _lib
 

@@ -3,8 +3,8 @@
 //   C[M,N] = epilogue( A[M,K] * B[N,K]^T ),  bf16 operands, fp32 accumulation in TMEM.
 //
 // One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages)
-//   warp 1      MMA issuer    (one elected lane issues tcgen05.mma 128x256x16, cta_group::1)
+//   warp 0      TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 or 6 stages)
+//   warp 1      MMA issuer    (one elected lane issues tcgen05.mma 128x256x16 / cta_group::2 256x256x16)
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulator stages)
 //   warps 4-11  epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
 // The two accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
@@ -22,16 +22,13 @@
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int MN_CHUNK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major box = 8 KiB
 constexpr int EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STG_BYTES = 32 * 128;           // per epilogue warp: 32 rows x 32 fp32
 
 struct GemmParams {
   int M, N, K;
@@ -47,6 +44,7 @@ struct GemmParams {
   const int* pos_idx; int pos_period;
   int rows_in, rows_out, row_off;
   float alpha;
+  float* colsum;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -135,22 +133,47 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, bool mn_major) {
   return d;
 }
 
-// erf with |err| < 1.5e-7 (Abramowitz-Stegun 7.1.26) -- far below bf16 output rounding; keeps the
-// epilogue off the critical path (erff() costs ~3x more issue slots).
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float r = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(r, x);
+// GELU(x) = x * Phi(x) with the normal CDF evaluated as a logistic of an odd degree-7 polynomial,
+//   Phi(x) ~= 1 / (1 + exp(-x (c0 + c1 x^2 + c2 x^4 + c3 x^6))),   |x| clamped to 6,
+// fitted (least squares on [-6, 6]) to erf-exact GELU: max |gelu error| 1.3e-5, max |gelu' error| 5.8e-5 -- an
+// order of magnitude below the bf16 rounding of the stored result, so the outputs are those of exact-erf GELU
+// (torch nn.GELU(approximate='none')) up to bf16 ties.  Cost: 9 FP32 ops + ex2 + rcp per element instead of
+// ~20 for erff-based code; the GELU epilogues were ALU-bound before (0.39-0.51 of tensor peak).
+// Coefficients below are pre-multiplied by -log2(e) so that the exponential is a bare ex2.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kG0 = -1.59534958f * 1.4426950408889634f, kG1 = -7.34984774e-02f * 1.4426950408889634f,
+                kG2 = 5.20865699e-04f * 1.4426950408889634f, kG3 = 1.64242936e-05f * 1.4426950408889634f;
+__device__ __forceinline__ float phi_cdf_fast(float x, float& x2_out) {
+  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+  const float x2 = xc * xc;
+  float q = fmaf(kG3, x2, kG2);
+  q = fmaf(q, x2, kG1);
+  q = fmaf(q, x2, kG0);
+  x2_out = x2;
+  return rcp_approx(1.0f + ex2_approx(xc * q));
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float x2;
+  return x * phi_cdf_fast(x, x2);
+}
 __device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f));
-  return fmaf(x * 0.39894228040143268f, __expf(-0.5f * x * x), cdf);
+  float x2;
+  const float s = phi_cdf_fast(x, x2);
+  // d/dx [x s(p(x))] = s + x s (1 - s) p'(x),  p'(x) = c0 + 3 c1 x^2 + 5 c2 x^4 + 7 c3 x^6  (natural-log units)
+  float pd = fmaf(7.0f * 1.64242936e-05f * -1.0f, x2, 5.0f * -5.20865699e-04f);
+  pd = fmaf(pd, x2, 3.0f * 7.34984774e-02f);
+  pd = fmaf(pd, x2, 1.59534958f);
+  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
+  return fmaf(xc * s * (1.0f - s), pd, s);
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -158,121 +181,186 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-// ------------------------------------------------------------------ epilogue for one 32-column chunk of one row
+// ------------------------------------------------------------------ epilogue (coalesced domain)
+// After the TMEM load each thread owns one accumulator ROW (32 fp32 columns).  Storing that way would touch 32
+// different cache lines per instruction, so every epilogue warp transposes its 32x32 fp32 unit through a private
+// 4 KiB XOR-swizzled smem buffer; afterwards lane l owns columns (l%8)*4..+3 of rows (l/8)+4i: one 16-byte
+// vector per row, eight lanes = one full 128-byte line.  Bias lives in four registers; residual / aux / pos
+// operands are fetched with the same coalesced mapping, all eight rows in flight before the math starts.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, long long orow, int row, int col0,
-                                               const uint32_t (&acc)[32]) {
-  float v[32];
+__device__ __forceinline__ void epilogue_unit(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0,
+                                              const uint32_t (&acc)[32]) {
+  // ---- phase 1: thread = row, write 8 x 16 B with chunk index XOR (row & 7)  (conflict-free)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  const int ncols = min(32, p.N - col0);   // multiple of 8 (N % 8 == 0)
-
-  if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_F32 || EPI == HCT_EPI_ATOMIC_F32) {
-    if (p.alpha != 1.0f) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-    }
-  }
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  __syncwarp();
+  // ---- phase 2: lane = (row sub-index, column group)
+  const int jj = lane & 7, rsub = lane >> 3;
+  const int col = col0 + jj * 4;
+  const bool col_ok = col < p.N;                       // N % 8 == 0 -> a group of 4 is all-in or all-out
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (EPI != HCT_EPI_DGELU_BF16 && EPI != HCT_EPI_ATOMIC_F32) {
-    if (p.bias != nullptr) {
+    if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  }
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long orow[8];
+  bool ok[8];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-        }
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + i * 4 + rsub;
+    ok[i] = col_ok && row < p.M;
+    orow[i] = row;
+    if (p.rows_in > 0) {
+      const int g = row / p.rows_in, r = row % p.rows_in + p.row_off;
+      ok[i] = ok[i] && r >= 0 && r < p.rows_out;
+      orow[i] = static_cast<long long>(g) * p.rows_out + r;
+    }
+  }
+  // operands that do not depend on the accumulator: issue all loads first
+  float4 extra[8];
+  uint2 aux[8];
+  if (EPI == HCT_EPI_RES_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (ok[i]) extra[i] = *reinterpret_cast<const float4*>(p.res + static_cast<long long>(row_base + i * 4 + rsub) * p.ldres + col);
+  }
+  if (EPI == HCT_EPI_POS_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (ok[i]) {
+        const int row = row_base + i * 4 + rsub;
+        const int pr = p.pos_idx != nullptr ? p.pos_idx[row] : (row % p.pos_period);
+        extra[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(pr) * p.ldpos + col));
       }
     }
   }
-
-  if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) {
-    if (EPI == HCT_EPI_GELU_BF16) {
-      if (p.out2 != nullptr) {
-        bf16* o2 = reinterpret_cast<bf16*>(p.out2) + orow * p.ldo2 + col0;
+  if (EPI == HCT_EPI_DGELU_BF16) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (j < ncols) {
-            uint4 u;
-            u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(o2 + j) = u;
-          }
+    for (int i = 0; i < 8; ++i)
+      if (ok[i]) aux[i] = *reinterpret_cast<const uint2*>(p.aux + static_cast<long long>(row_base + i * 4 + rsub) * p.ldaux + col);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+    if (!ok[i]) continue;
+    if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_F32 || EPI == HCT_EPI_ATOMIC_F32) {
+      v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+    }
+    v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+    if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) {
+      if (EPI == HCT_EPI_GELU_BF16) {
+        if (p.out2 != nullptr) {
+          uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + orow[i] * p.ldo2 + col) = u;
         }
+        v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
       }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-    }
-    if (EPI == HCT_EPI_DGELU_BF16) {
-      const bf16* a = p.aux + static_cast<long long>(row) * p.ldaux + col0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        if (j < ncols) {
-          const uint4 u = *reinterpret_cast<const uint4*>(a + j);
-          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z),
-                       a3 = unpack_bf16x2(u.w);
-          v[j] *= gelu_grad_fast(a0.x); v[j + 1] *= gelu_grad_fast(a0.y);
-          v[j + 2] *= gelu_grad_fast(a1.x); v[j + 3] *= gelu_grad_fast(a1.y);
-          v[j + 4] *= gelu_grad_fast(a2.x); v[j + 5] *= gelu_grad_fast(a2.y);
-          v[j + 6] *= gelu_grad_fast(a3.x); v[j + 7] *= gelu_grad_fast(a3.y);
-        }
+      if (EPI == HCT_EPI_DGELU_BF16) {
+        const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
+        v.x *= gelu_grad_fast(a0.x); v.y *= gelu_grad_fast(a0.y); v.z *= gelu_grad_fast(a1.x); v.w *= gelu_grad_fast(a1.y);
       }
-    }
-    bf16* o = reinterpret_cast<bf16*>(p.out) + orow * p.ldo + col0;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      if (j < ncols) {
-        uint4 u;
-        u.x = pack_bf16x2(v[j], v[j + 1]); u.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        u.z = pack_bf16x2(v[j + 4], v[j + 5]); u.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        *reinterpret_cast<uint4*>(o + j) = u;
+      uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow[i] * p.ldo + col) = u;
+      if (p.colsum != nullptr) {   // column sums of the values as the consumer will read them (bf16-rounded)
+        const float2 r0 = unpack_bf16x2(u.x), r1 = unpack_bf16x2(u.y);
+        csum.x += r0.x; csum.y += r0.y; csum.z += r1.x; csum.w += r1.y;
       }
-    }
-  } else {
-    float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
-    if (EPI == HCT_EPI_RES_F32) {
-      const float* r = p.res + static_cast<long long>(row) * p.ldres + col0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) {
-          const float4 t = *reinterpret_cast<const float4*>(r + j);
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-        }
-      }
-    }
-    if (EPI == HCT_EPI_POS_F32) {
-      const int pr = p.pos_idx != nullptr ? p.pos_idx[row] : (row % p.pos_period);
-      const float* r = p.pos + static_cast<long long>(pr) * p.ldpos + col0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        if (j < ncols) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(r + j));
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-        }
-      }
-    }
-    if (EPI == HCT_EPI_ATOMIC_F32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (j < ncols) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      float* o = reinterpret_cast<float*>(p.out) + orow[i] * p.ldo + col;
+      if (EPI == HCT_EPI_RES_F32 || EPI == HCT_EPI_POS_F32) {
+        v.x += extra[i].x; v.y += extra[i].y; v.z += extra[i].z; v.w += extra[i].w;
+      }
+      if (EPI == HCT_EPI_ATOMIC_F32) red_add_v4(o, v.x, v.y, v.z, v.w);
+      else *reinterpret_cast<float4*>(o) = v;
     }
   }
+  if ((EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) && p.colsum != nullptr) {
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
+      csum.z += __shfl_xor_sync(0xffffffffu, csum.z, o); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, o);
+    }
+    if (rsub == 0 && col_ok) red_add_v4(p.colsum + col, csum.x, csum.y, csum.z, csum.w);
+  }
+  __syncwarp();   // staging buffer is reused by the next unit
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int EPI>
+// CTAS = 1: one CTA per tile of 128 x 256, 4-stage ring (48 KiB / stage).
+// CTAS = 2: a CTA pair (cluster of 2 on one TPC) per tile of 256 x 256 with tcgen05.mma.cta_group::2: each CTA
+//           stages its own 128 rows of A and HALF of B (128 of the 256 N rows), so a stage is 32 KiB per SM
+//           (6-stage ring) and L2->SM operand traffic per flop drops by a third.  Only the leader (rank 0)
+//           issues MMAs; TMA loads of both CTAs complete on the leader's `full` barrier; tcgen05.commit
+//           multicasts to both CTAs' `empty` / `tmem full` barriers; both epilogues report to the leader's
+//           `tmem empty` barrier.
+template <int CTAS>
+struct Cfg {
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int B_ROWS = BN / CTAS;                     // B rows staged by each CTA
+  static constexpr int B_STAGE = B_ROWS * BK * 2;
+  static constexpr int STAGE = A_STAGE_BYTES + B_STAGE;
+  static constexpr int SMEM = STAGES * STAGE + EPI_WARPS * STG_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> rank 0
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // remote arrive on rank 0's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
+template <int EPI, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const GemmParams p) {
+  using C = Cfg<CTAS>;
+  constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* sStage = smem + STAGES * C::STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -280,8 +368,11 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int unit = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int total_work = tiles * p.splits;
+  constexpr int TILE_M = BM * CTAS;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -289,58 +380,73 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS * CTAS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = unit; w < total_work; w += num_units) {
       const int tile = w % tiles, split = w / tiles;
-      const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * BM;
+      const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * TILE_M;
       const int kb0 = split * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.total_kb);
-      const int a_chunks = p.a_mn ? min(BM / 64, (p.M - m0 + 63) / 64) : 0;
-      const int b_chunks = p.b_mn ? min(BN / 64, (p.N - n0 + 63) / 64) : 0;
-      const uint32_t bytes = (p.a_mn ? a_chunks * MN_CHUNK_BYTES : A_STAGE_BYTES) +
-                             (p.b_mn ? b_chunks * MN_CHUNK_BYTES : B_STAGE_BYTES);
+      const int my_m0 = m0 + rank * BM, my_n0 = n0 + rank * C::B_ROWS;
+      // MN-major operands are staged in 64-column chunks; chunks entirely outside the matrix are skipped
+      uint32_t bytes = 0;       // bytes that will land on the (leader's) full barrier per stage, all CTAs
+      int a_chunks = 0, b_chunks = 0;
+#pragma unroll
+      for (int r = 0; r < CTAS; ++r) {
+        const int ac = p.a_mn ? max(0, min(BM / 64, (p.M - (m0 + r * BM) + 63) / 64)) : 0;
+        const int bc = p.b_mn ? max(0, min(C::B_ROWS / 64, (p.N - (n0 + r * C::B_ROWS) + 63) / 64)) : 0;
+        bytes += (p.a_mn ? ac * MN_CHUNK_BYTES : A_STAGE_BYTES) + (p.b_mn ? bc * MN_CHUNK_BYTES : C::B_STAGE);
+        if (r == rank) { a_chunks = ac; b_chunks = bc; }
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_expect_tx(&full_bar[stage], bytes);
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], bytes);
         const uint32_t a_dst = smem_u32(sA + stage * A_STAGE_BYTES);
-        const uint32_t b_dst = smem_u32(sB + stage * B_STAGE_BYTES);
-        if (!p.a_mn) {
-          tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, m0);
+        const uint32_t b_dst = smem_u32(sB + stage * C::B_STAGE);
+        if (CTAS == 2) {
+          if (!p.a_mn) tma_load_2d_2sm(a_dst, &tmA, &full_bar[stage], kb * BK, my_m0);
+          else for (int i = 0; i < a_chunks; ++i)
+            tma_load_2d_2sm(a_dst + i * MN_CHUNK_BYTES, &tmA, &full_bar[stage], my_m0 + i * 64, kb * BK);
+          if (!p.b_mn) tma_load_2d_2sm(b_dst, &tmB, &full_bar[stage], kb * BK, my_n0);
+          else for (int i = 0; i < b_chunks; ++i)
+            tma_load_2d_2sm(b_dst + i * MN_CHUNK_BYTES, &tmB, &full_bar[stage], my_n0 + i * 64, kb * BK);
         } else {
-          for (int i = 0; i < a_chunks; ++i)
-            tma_load_2d(a_dst + i * MN_CHUNK_BYTES, &tmA, &full_bar[stage], m0 + i * 64, kb * BK);
-        }
-        if (!p.b_mn) {
-          tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n0);
-        } else {
-          for (int i = 0; i < b_chunks; ++i)
-            tma_load_2d(b_dst + i * MN_CHUNK_BYTES, &tmB, &full_bar[stage], n0 + i * 64, kb * BK);
+          if (!p.a_mn) tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, my_m0);
+          else for (int i = 0; i < a_chunks; ++i)
+            tma_load_2d(a_dst + i * MN_CHUNK_BYTES, &tmA, &full_bar[stage], my_m0 + i * 64, kb * BK);
+          if (!p.b_mn) tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, my_n0);
+          else for (int i = 0; i < b_chunks; ++i)
+            tma_load_2d(b_dst + i * MN_CHUNK_BYTES, &tmB, &full_bar[stage], my_n0 + i * 64, kb * BK);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t a_kstep = p.a_mn ? (16 * 128) >> 4 : 32 >> 4;   // descriptor units of 16 B per UMMA_K=16
     const uint32_t b_kstep = p.b_mn ? (16 * 128) >> 4 : 32 >> 4;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = unit; w < total_work; w += num_units) {
       const int split = w / tiles;
       const int kb0 = split * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.total_kb);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -350,55 +456,55 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t adesc = make_sdesc(smem_u32(sA + stage * A_STAGE_BYTES), p.a_mn);
-        const uint64_t bdesc = make_sdesc(smem_u32(sB + stage * B_STAGE_BYTES), p.b_mn);
+        const uint64_t bdesc = make_sdesc(smem_u32(sB + stage * C::B_STAGE), p.b_mn);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          tc_mma(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-        tc_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+        for (int k = 0; k < BK / 16; ++k) {
+          if (CTAS == 2) tc_mma_2sm(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          else tc_mma(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        if (CTAS == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      tc_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+      if (CTAS == 2) tc_commit_2sm(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may touch
     const int half = (warp - FIRST_EPI_WARP) >> 2;        // which 128-column half
+    const uint32_t stg = smem_u32(sStage + (warp - FIRST_EPI_WARP) * STG_BYTES);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int w = unit; w < total_work; w += num_units) {
       const int tile = w % tiles;
-      const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * BM;
+      const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * TILE_M + rank * BM;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      bool row_ok = row < p.M;
-      long long orow = row;
-      if (p.rows_in > 0) {
-        const int g = row / p.rows_in, r = row % p.rows_in + p.row_off;
-        row_ok = row_ok && r >= 0 && r < p.rows_out;
-        orow = static_cast<long long>(g) * p.rows_out + r;
-      }
 #pragma unroll 1
       for (int c = 0; c < (BN / 2) / 32; ++c) {
         const int col0 = n0 + half * (BN / 2) + c * 32;
-        if (col0 < p.N) {   // warp-uniform
+        if (col0 < p.N && m0 < p.M) {   // warp-uniform
           uint32_t v[32];
           tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, v);
-          if (row_ok) epilogue_chunk<EPI>(p, orow, row, col0, v);
+          epilogue_unit<EPI>(p, stg, lane, m0 + q * 32, col0, v);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (CTAS == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -439,20 +545,48 @@ int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long oute
   return HCT_OK;
 }
 
-template <int EPI>
+template <int EPI, int CTAS>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;
+  auto kernel = hct_gemm_tcgen05_kernel<EPI, CTAS>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(hct_gemm_tcgen05_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CTAS>::SMEM);
     if (e != cudaSuccess) { hct_set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
     configured = true;
   }
-  hct_gemm_tcgen05_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p);
+  if (e != cudaSuccess) { hct_set_error("cudaLaunchKernelEx(gemm): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return HCT_ERR_CUDA; }
   return hct_check_launch("hct_gemm_tcgen05_kernel");
 }
 
+template <int CTAS>
+int dispatch(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+  switch (epi) {
+    case HCT_EPI_BF16: return launch<HCT_EPI_BF16, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_GELU_BF16: return launch<HCT_EPI_GELU_BF16, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_RES_F32: return launch<HCT_EPI_RES_F32, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_POS_F32: return launch<HCT_EPI_POS_F32, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_DGELU_BF16: return launch<HCT_EPI_DGELU_BF16, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_F32: return launch<HCT_EPI_F32, CTAS>(tmA, tmB, p, grid, st);
+    default: return launch<HCT_EPI_ATOMIC_F32, CTAS>(tmA, tmB, p, grid, st);
+  }
+}
+
+int g_gemm_ctas = 2;   // CTA-pair mode by default; hct_gemm_set_cta_pair(0) selects the single-CTA kernel
+
 }  // namespace
+
+extern "C" int hct_gemm_set_cta_pair(int enable) { g_gemm_ctas = enable ? 2 : 1; return HCT_OK; }
 
 extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -476,63 +610,69 @@ extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
     HCT_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "hct_gemm_bf16: DGELU epilogue needs aux");
   if (d->epilogue == HCT_EPI_GELU_BF16 && d->out2 != nullptr)
     HCT_REQUIRE(d->ldo2 % 8 == 0, "hct_gemm_bf16: ldo2 misaligned");
+  HCT_REQUIRE(d->colsum == nullptr || !f32_out, "hct_gemm_bf16: colsum is only available with bf16-output epilogues");
   if (d->a_mn_major) HCT_REQUIRE(d->M % 8 == 0, "hct_gemm_bf16: MN-major A needs M %% 8 == 0");
   else HCT_REQUIRE(d->K % 8 == 0, "hct_gemm_bf16: K-major A needs K %% 8 == 0");
   if (!d->b_mn_major) HCT_REQUIRE(d->K % 8 == 0, "hct_gemm_bf16: K-major B needs K %% 8 == 0");
 
+  const int ctas = g_gemm_ctas;
   GemmParams p{};
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.a_mn = d->a_mn_major ? 1 : 0; p.b_mn = d->b_mn_major ? 1 : 0;
-  p.num_m_tiles = (d->M + BM - 1) / BM;
+  p.num_m_tiles = (d->M + BM * ctas - 1) / (BM * ctas);
   p.num_n_tiles = (d->N + BN - 1) / BN;
   p.total_kb = (d->K + BK - 1) / BK;
   const int sms = hct_num_sms();
+  const int units = sms / ctas;
   int splits = 1;
   if (d->epilogue == HCT_EPI_ATOMIC_F32) {
     splits = d->splits;
     if (splits <= 0) {
+      // pick the split factor whose work-item count fills whole waves of CTA (pairs): fewest splits with >= 95 %
+      // wave efficiency, else the most efficient one; keep >= 8 k-blocks per split.
       const int tiles = p.num_m_tiles * p.num_n_tiles;
-      splits = (2 * sms + tiles - 1) / tiles;            // ~2 work items per SM
-      const int max_splits = (p.total_kb + 7) / 8;       // keep >= 8 k-blocks per split
-      if (splits > max_splits) splits = max_splits;
-      if (splits < 1) splits = 1;
+      int max_splits = (p.total_kb + 7) / 8;
+      if (max_splits > 64) max_splits = 64;
+      if (max_splits < 1) max_splits = 1;
+      double best_eff = -1.0;
+      splits = 1;
+      for (int sp = 1; sp <= max_splits; ++sp) {
+        const long long items = static_cast<long long>(tiles) * sp;
+        const long long waves = (items + units - 1) / units;
+        const double eff = static_cast<double>(items) / static_cast<double>(waves * units);
+        if (eff > best_eff + 1e-9) { best_eff = eff; splits = sp; }
+        if (eff >= 0.95) { splits = sp; break; }
+      }
     }
     if (splits > p.total_kb) splits = p.total_kb;
   }
   p.kb_per_split = (p.total_kb + splits - 1) / splits;
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;   // no empty split
-  // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4
+  // instruction descriptor: D=f32, A=B=bf16, majorness, N>>3, M>>4 (M = 256 for the CTA pair)
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn) << 15) |
             (static_cast<uint32_t>(p.b_mn) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
-            (static_cast<uint32_t>(BM >> 4) << 24);
+            (static_cast<uint32_t>((BM * ctas) >> 4) << 24);
   p.out = d->out; p.ldo = d->ldo; p.out2 = d->out2; p.ldo2 = d->ldo2;
   p.bias = d->bias; p.res = d->res; p.ldres = d->ldres;
   p.aux = static_cast<const bf16*>(d->aux); p.ldaux = d->ldaux;
   p.pos = d->pos; p.ldpos = d->ldpos; p.pos_idx = d->pos_idx; p.pos_period = d->pos_period;
   p.rows_in = d->rows_in; p.rows_out = d->rows_out; p.row_off = d->row_off;
   p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+  p.colsum = d->colsum;
 
   CUtensorMap tmA, tmB;
   int rc;
   if (!p.a_mn) rc = make_tmap(&tmA, d->A, d->K, d->M, d->lda, BK, BM);
   else rc = make_tmap(&tmA, d->A, d->M, d->K, d->lda, 64, BK);
   if (rc != HCT_OK) return rc;
-  if (!p.b_mn) rc = make_tmap(&tmB, d->B, d->K, d->N, d->ldb, BK, BN);
+  if (!p.b_mn) rc = make_tmap(&tmB, d->B, d->K, d->N, d->ldb, BK, BN / ctas);
   else rc = make_tmap(&tmB, d->B, d->N, d->K, d->ldb, 64, BK);
   if (rc != HCT_OK) return rc;
 
   const int total_work = p.num_m_tiles * p.num_n_tiles * p.splits;
-  const int grid = total_work < sms ? total_work : sms;
+  const int grid = (total_work < units ? total_work : units) * ctas;
   void* prof = hct_prof_enabled() ? hct_prof_begin(stream) : nullptr;
-  switch (d->epilogue) {
-    case HCT_EPI_BF16: rc = launch<HCT_EPI_BF16>(tmA, tmB, p, grid, stream); break;
-    case HCT_EPI_GELU_BF16: rc = launch<HCT_EPI_GELU_BF16>(tmA, tmB, p, grid, stream); break;
-    case HCT_EPI_RES_F32: rc = launch<HCT_EPI_RES_F32>(tmA, tmB, p, grid, stream); break;
-    case HCT_EPI_POS_F32: rc = launch<HCT_EPI_POS_F32>(tmA, tmB, p, grid, stream); break;
-    case HCT_EPI_DGELU_BF16: rc = launch<HCT_EPI_DGELU_BF16>(tmA, tmB, p, grid, stream); break;
-    case HCT_EPI_F32: rc = launch<HCT_EPI_F32>(tmA, tmB, p, grid, stream); break;
-    default: rc = launch<HCT_EPI_ATOMIC_F32>(tmA, tmB, p, grid, stream); break;
-  }
+  rc = ctas == 2 ? dispatch<2>(d->epilogue, tmA, tmB, p, grid, stream) : dispatch<1>(d->epilogue, tmA, tmB, p, grid, stream);
   if (prof != nullptr) hct_prof_end(prof, stream, 2.0 * d->M * d->N * static_cast<double>(d->K));
   return rc;
 }

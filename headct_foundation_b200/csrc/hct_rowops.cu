@@ -61,37 +61,82 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // ------------------------------------------------------------------ LayerNorm backward
-template <int NV>
+// One warp per row, rows software-pipelined through shared memory with cp.async (next row's x / dy / dres land
+// while the current row is reduced), so the kernel keeps ~8 KB per warp in flight without register cost.
+// dgamma, dbeta and (optionally) the column sums of the bf16-rounded dx output -- the bias gradient of the
+// Linear that consumes dx -- are accumulated in registers and flushed once per CTA.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc) : "memory");
+}
+
+template <int NV, bool DY_BF16>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-ln_bwd_kernel(const void* __restrict__ dy, int dy_bf16, const float* __restrict__ x, const float* __restrict__ gamma,
+ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres_in,
               float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-              float* __restrict__ dbeta, long long rows, int dim) {
-  extern __shared__ float sred[];   // [LN_WARPS][2*dim]
+              float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int dim) {
+  extern __shared__ __align__(16) float sbuf[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = dim >> 2;
-  float4 dg[NV], db[NV];
+  // per warp, per stage: x [dim] f32 | dres [dim] f32 | dy [dim] (f32 or bf16, sized for f32)
+  const int stage_floats = 3 * dim;
+  float* wbuf = sbuf + static_cast<size_t>(warp) * 2 * stage_floats;
+  float4 dg[NV], db[NV], ds[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = dg[i]; ds[i] = dg[i]; }
 
-  for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < rows;
-       row += static_cast<long long>(gridDim.x) * LN_WARPS) {
+  const long long row0 = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
+  const long long rstride = static_cast<long long>(gridDim.x) * LN_WARPS;
+  auto prefetch = [&](long long row, int stage) {
+    float* sx = wbuf + stage * stage_floats;
+    float* sr = sx + dim;
+    float* sd = sr + dim;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nv) {
+        cp_async_16(sx + 4 * c, x + row * dim + 4 * c);
+        if (dres_in) cp_async_16(sr + 4 * c, dres_in + row * dim + 4 * c);
+        if (DY_BF16) cp_async_8(reinterpret_cast<bf16*>(sd) + 4 * c, reinterpret_cast<const bf16*>(dy) + row * dim + 4 * c);
+        else cp_async_16(sd + 4 * c, reinterpret_cast<const float*>(dy) + row * dim + 4 * c);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (row0 < rows) prefetch(row0, 0);
+  int stage = 0;
+  for (long long row = row0; row < rows; row += rstride, stage ^= 1) {
+    if (row + rstride < rows) {
+      prefetch(row + rstride, stage ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
     const float mu = mean[row], rs = rstd[row];
-    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    const float* sx = wbuf + stage * stage_floats;
+    const float* sr = sx + dim;
+    const float* sd = sr + dim;
     float4 xh[NV], g[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 32 + lane;
       if (c < nv) {
-        const float4 xv = xr[c];
+        const float4 xv = reinterpret_cast<const float4*>(sx)[c];
         float4 d;
-        if (dy_bf16) {
-          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy) + row * dim)[c];
+        if (DY_BF16) {
+          const uint2 u = reinterpret_cast<const uint2*>(sd)[c];
           const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
           d = make_float4(a.x, a.y, b.x, b.y);
         } else {
-          d = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * dim)[c];
+          d = reinterpret_cast<const float4*>(sd)[c];
         }
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
@@ -110,35 +155,43 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_bf16, const float* __restrict_
         float4 o = make_float4(rs * (g[i].x - c1 - xh[i].x * c2), rs * (g[i].y - c1 - xh[i].y * c2),
                                rs * (g[i].z - c1 - xh[i].z * c2), rs * (g[i].w - c1 - xh[i].w * c2));
         if (dres_in) {
-          const float4 r = reinterpret_cast<const float4*>(dres_in + row * dim)[c];
+          const float4 r = reinterpret_cast<const float4*>(sr)[c];
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
         if (dx_f32) reinterpret_cast<float4*>(dx_f32 + row * dim)[c] = o;
         if (dx_bf16) {
           uint2 u; u.x = pack_bf16x2(o.x, o.y); u.y = pack_bf16x2(o.z, o.w);
           reinterpret_cast<uint2*>(dx_bf16 + row * dim)[c] = u;
+          if (dxsum) {
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+            ds[i].x += a.x; ds[i].y += a.y; ds[i].z += b.x; ds[i].w += b.y;
+          }
         }
       }
     }
+    __syncwarp();   // everyone done reading this stage before it is refilled two iterations later
   }
-  // cross-warp reduction of dgamma / dbeta partials, then one atomic per column per CTA
-  if (dgamma != nullptr) {
-    float* my = sred + static_cast<size_t>(warp) * 2 * dim;
+  // cross-warp reduction of the column accumulators (reuses the staging memory), one atomic per column per CTA
+  __syncthreads();
+  if (dgamma != nullptr || dxsum != nullptr) {
+    float* my = sbuf + static_cast<size_t>(warp) * 3 * dim;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 32 + lane;
       if (c < nv) {
         reinterpret_cast<float4*>(my)[c] = dg[i];
         reinterpret_cast<float4*>(my + dim)[c] = db[i];
+        reinterpret_cast<float4*>(my + 2 * dim)[c] = ds[i];
       }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * dim; c += blockDim.x) {
+    for (int c = threadIdx.x; c < 3 * dim; c += blockDim.x) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += sred[static_cast<size_t>(w) * 2 * dim + c];
-      if (c < dim) atomicAdd(dgamma + c, s);
-      else atomicAdd(dbeta + (c - dim), s);
+      for (int w = 0; w < LN_WARPS; ++w) s += sbuf[static_cast<size_t>(w) * 3 * dim + c];
+      if (c < dim) { if (dgamma) atomicAdd(dgamma + c, s); }
+      else if (c < 2 * dim) { if (dbeta) atomicAdd(dbeta + (c - dim), s); }
+      else if (dxsum) atomicAdd(dxsum + (c - 2 * dim), s);
     }
   }
 }
@@ -300,23 +353,33 @@ extern "C" int hct_layernorm_fwd(const float* x, const float* gamma, const float
 
 extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* gamma, const float* mean,
                                  const float* rstd, const float* dres_in, float* dx_out_f32, void* dx_out_bf16,
-                                 float* dgamma, float* dbeta, int64_t rows, int32_t dim, hct_stream_t s) {
+                                 float* dgamma, float* dbeta, float* dxsum, int64_t rows, int32_t dim, hct_stream_t s) {
   HCT_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAXV * 128, "layernorm_bwd: dim=%d unsupported", dim);
   HCT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be set or both NULL");
+  HCT_REQUIRE(dxsum == nullptr || dx_out_bf16 != nullptr, "layernorm_bwd: dxsum needs the bf16 output");
   if (rows == 0) return HCT_OK;
-  const int grid = grid_for(rows, LN_WARPS, hct_num_sms() * 2);
-  const size_t smem = static_cast<size_t>(LN_WARPS) * 2 * dim * sizeof(float);
-#define HCT_LN_BWD(NV)                                                                                         \
+  const int grid = grid_for(rows, LN_WARPS, hct_num_sms());
+  const size_t smem = static_cast<size_t>(LN_WARPS) * 2 * 3 * dim * sizeof(float);
+  HCT_REQUIRE(smem <= 200 * 1024, "layernorm_bwd: dim=%d needs %zu bytes of shared memory", dim, smem);
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  bf16* dx16 = static_cast<bf16*>(dx_out_bf16);
+#define HCT_LN_BWD(NV, BF)                                                                                     \
   do {                                                                                                         \
     static bool configured = false;                                                                            \
     if (!configured) {                                                                                         \
-      cudaFuncSetAttribute(ln_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_WARPS * 2 * NV * 128 * 4); \
+      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
       configured = true;                                                                                       \
     }                                                                                                          \
-    ln_bwd_kernel<NV><<<grid, LN_WARPS * 32, smem, static_cast<cudaStream_t>(s)>>>(                             \
-        dy, dy_bf16, x, gamma, mean, rstd, dres_in, dx_out_f32, static_cast<bf16*>(dx_out_bf16), dgamma, dbeta, rows, dim); \
+    ln_bwd_kernel<NV, BF><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32, dx16, \
+                                                             dgamma, dbeta, dxsum, rows, dim);                 \
   } while (0)
-  if (dim <= 256) HCT_LN_BWD(2); else if (dim <= 768) HCT_LN_BWD(6); else if (dim <= 1024) HCT_LN_BWD(8); else HCT_LN_BWD(16);
+#define HCT_LN_BWD_D(BF)                                                                                        \
+  do {                                                                                                         \
+    if (dim <= 256) HCT_LN_BWD(2, BF); else if (dim <= 768) HCT_LN_BWD(6, BF);                                  \
+    else if (dim <= 1024) HCT_LN_BWD(8, BF); else HCT_LN_BWD(16, BF);                                           \
+  } while (0)
+  if (dy_bf16) HCT_LN_BWD_D(true); else HCT_LN_BWD_D(false);
+#undef HCT_LN_BWD_D
 #undef HCT_LN_BWD
   return hct_check_launch("ln_bwd_kernel");
 }

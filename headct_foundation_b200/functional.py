@@ -68,7 +68,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, lda: int, 
          ldo2: int = 0, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, ldres: int = 0,
          aux: Optional[torch.Tensor] = None, ldaux: int = 0, pos: Optional[torch.Tensor] = None, ldpos: int = 0,
          pos_idx: Optional[torch.Tensor] = None, pos_period: int = 0, rows_in: int = 0, rows_out: int = 0,
-         row_off: int = 0, alpha: float = 1.0, splits: int = 0) -> None:
+         row_off: int = 0, alpha: float = 1.0, splits: int = 0, colsum: Optional[torch.Tensor] = None) -> None:
     d = GemmDesc()
     d.M, d.N, d.K = M, N, K
     d.A, d.lda, d.a_mn_major = A.data_ptr(), lda, int(a_mn)
@@ -83,6 +83,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, lda: int, 
     d.pos_idx, d.pos_period = ptr(pos_idx), pos_period
     d.rows_in, d.rows_out, d.row_off = rows_in, rows_out, row_off
     d.alpha, d.splits = alpha, splits
+    d.colsum = ptr(colsum)
     call("hct_gemm_bf16", C.byref(d), stream_ptr(A.device))
 
 
@@ -105,14 +106,14 @@ def linear_fwd(x16: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
 
 
 def linear_dgrad(dy16: torch.Tensor, w: torch.Tensor, *, epi: int = EPI_BF16, aux: Optional[torch.Tensor] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx[M,K] = dy16[M,N] @ w16[N,K]   (B operand MN-major: the weight exactly as stored)."""
     M, N = dy16.shape
     wb = w16(w).view(N, -1)
     K = wb.shape[1]
     if out is None:
         out = torch.empty((M, K), dtype=BF16, device=dy16.device)
-    gemm(dy16, wb, M=M, N=K, K=N, lda=N, ldb=K, b_mn=True, out=out, ldo=K, epi=epi, aux=aux, ldaux=K)
+    gemm(dy16, wb, M=M, N=K, K=N, lda=N, ldb=K, b_mn=True, out=out, ldo=K, epi=epi, aux=aux, ldaux=K, colsum=colsum)
     return out
 
 
@@ -154,15 +155,19 @@ def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd, dres: Optional[torch.Tensor],
-                  want_bf16: bool, want_param_grads: bool = True):
+                  want_bf16: bool, want_param_grads: bool = True, want_colsum: bool = False):
     D = x.shape[-1]
     rows = x.numel() // D
     dx = torch.empty(x.shape, dtype=F32, device=x.device)
     dx16 = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
     dg = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
     db = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
+    dsum = torch.zeros((D,), dtype=F32, device=x.device) if (want_colsum and want_bf16) else None
     call("hct_layernorm_bwd", dy.data_ptr(), int(dy.dtype == BF16), x.data_ptr(), w.data_ptr(), mean.data_ptr(),
-         rstd.data_ptr(), ptr(dres), dx.data_ptr(), ptr(dx16), ptr(dg), ptr(db), rows, D, stream_ptr(x.device))
+         rstd.data_ptr(), ptr(dres), dx.data_ptr(), ptr(dx16), ptr(dg), ptr(db), ptr(dsum), rows, D,
+         stream_ptr(x.device))
+    if want_colsum:
+        return dx, dx16, dg, db, dsum
     return dx, dx16, dg, db
 
 
@@ -216,24 +221,24 @@ class BlockFn(torch.autograd.Function):
         dev = x.device
         st = stream_ptr(dev)
         dout = dout.contiguous()
-        d3 = take_bf16_shadow(dout)
+        d3, dfc2_b = take_bf16_shadow(dout, with_colsum=True)
         if d3 is None:
             d3 = rows_to_bf16(dout, groups=1, src_rows_per_group=M, src_row_off=0, rows_per_group=M, dim=D)
+        if dfc2_b is None:
+            dfc2_b = colsum(d3, D)
         # ---- MLP branch
         dfc2_w = linear_wgrad(d3, g)
-        dfc2_b = colsum(d3, D)
-        da = linear_dgrad(d3, fc2_w, epi=EPI_DGELU_BF16, aux=a)                         # [M, F] bf16
+        dfc1_b = torch.zeros((a.shape[1],), dtype=F32, device=dev)
+        da = linear_dgrad(d3, fc2_w, epi=EPI_DGELU_BF16, aux=a, colsum=dfc1_b)          # [M, F] bf16 (+ column sums)
         del d3
         dfc1_w = linear_wgrad(da, h2.view(M, D))
-        dfc1_b = colsum(da, da.shape[1])
         dh2 = linear_dgrad(da, fc1_w)                                                   # [M, D] bf16
         del da
-        dx2, dx2_16, dn2w, dn2b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, True)
+        dx2, dx2_16, dn2w, dn2b, dproj_b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, True, want_colsum=True)
         del dh2
         # ---- attention branch
         dx2_16 = dx2_16.view(M, D)
         dproj_w = linear_wgrad(dx2_16, att)
-        dproj_b = colsum(dx2_16, D)
         datt = linear_dgrad(dx2_16, proj_w)                                             # [M, D] bf16
         del dx2_16
         dqkv = torch.empty_like(qkv)
@@ -245,8 +250,8 @@ class BlockFn(torch.autograd.Function):
         dqkv_b = colsum(dqkv, 3 * D) if ctx.has_qkv_bias else None
         dh1 = linear_dgrad(dqkv, qkv_w)
         del dqkv
-        dx, dx16, dn1w, dn1b = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True)
-        put_bf16_shadow(dx, dx16)
+        dx, dx16, dn1w, dn1b, dxs = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True, want_colsum=True)
+        put_bf16_shadow(dx, dx16, dxs)
         return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, None,
                 None)
 
@@ -288,21 +293,23 @@ class AttentionFn(torch.autograd.Function):
 # A block's backward produces both the fp32 residual-stream gradient and its bf16 copy (the next GEMM
 # operand).  autograd only carries the fp32 tensor between nodes, so the bf16 copy rides in this
 # side table keyed by the fp32 tensor's storage; the consumer pops it (and falls back to a cast).
-_SHADOW: Dict[int, Tuple[Tuple[int, ...], torch.Tensor]] = {}
+_SHADOW: Dict[int, Tuple[Tuple[int, ...], torch.Tensor, Optional[torch.Tensor]]] = {}
 
 
-def put_bf16_shadow(t32: torch.Tensor, t16: Optional[torch.Tensor]) -> None:
+def put_bf16_shadow(t32: torch.Tensor, t16: Optional[torch.Tensor], colsum16: Optional[torch.Tensor] = None) -> None:
+    """Register the bf16 copy (and optionally its column sums) of an fp32 gradient about to be handed to autograd."""
     _SHADOW.clear()
     if t16 is not None:
-        _SHADOW[t32.data_ptr()] = (tuple(t32.shape), t16)
+        _SHADOW[t32.data_ptr()] = (tuple(t32.shape), t16, colsum16)
 
 
-def take_bf16_shadow(t32: torch.Tensor) -> Optional[torch.Tensor]:
+def take_bf16_shadow(t32: torch.Tensor, with_colsum: bool = False):
     hit = _SHADOW.pop(t32.data_ptr(), None)
     _SHADOW.clear()
     if hit is None or hit[0] != tuple(t32.shape):
-        return None
-    return hit[1].view(-1, t32.shape[-1])
+        return (None, None) if with_colsum else None
+    t16 = hit[1].view(-1, t32.shape[-1])
+    return (t16, hit[2]) if with_colsum else t16
 
 
 # --------------------------------------------------------------------------------------------

@@ -75,9 +75,13 @@ typedef struct hct_gemm_desc {
   int32_t rows_in, rows_out, row_off;
   float alpha;
   int32_t splits;                    /* split-K factor for HCT_EPI_ATOMIC_F32; 0 = auto */
+  float* colsum;                     /* optional fp32 [N], += column sums of the bf16 output (bias gradient
+                                        of the Linear that consumes it); bf16-output epilogues only */
 } hct_gemm_desc;
 
 int hct_gemm_bf16(const hct_gemm_desc* desc, hct_stream_t stream);
+/* 1 (default): CTA-pair kernel (tcgen05 cta_group::2, 256x256 tiles); 0: single-CTA kernel (128x256 tiles). */
+int hct_gemm_set_cta_pair(int enable);
 
 /* ---------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound)
@@ -89,10 +93,11 @@ int hct_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
                       hct_stream_t stream);
 /* LayerNorm backward (autograd of the call sites above).  dy: bf16 (dy_bf16) or fp32 [rows, dim].
  * dx_out_f32 = (dres_in ? dres_in : 0) + dLN ; optional bf16 copy dx_out_bf16 ;
- * dgamma/dbeta fp32 [dim] are ACCUMULATED (+=) with atomics. */
+ * dgamma/dbeta fp32 [dim] are ACCUMULATED (+=) with atomics; dxsum (optional, fp32 [dim], +=) receives
+ * the column sums of the bf16 dx output = the bias gradient of the Linear that consumes it. */
 int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dres_in,
-                      float* dx_out_f32, void* dx_out_bf16, float* dgamma, float* dbeta,
+                      float* dx_out_f32, void* dx_out_bf16, float* dgamma, float* dbeta, float* dxsum,
                       int64_t rows, int32_t dim, hct_stream_t stream);
 /* fp32 -> bf16 cast of a contiguous buffer (autocast weight casts). */
 int hct_cast_f32_to_bf16(const float* src, void* dst, int64_t n, hct_stream_t stream);

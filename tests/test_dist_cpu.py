@@ -1,0 +1,75 @@
+"""world_size-2 gloo tests (CPU) of the host-side data-parallel logic and of bench.py's multi-rank contract."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from headct_foundation_b200 import parallel as P
+    res = {}
+    assert P.world() == (rank, world)
+    res["seed"] = P.rank_seed(42, rank)
+    res["max"] = P.max_over_ranks([10.0 + rank, 5.0 - rank])
+    # DINO center: sum of per-rank column sums, divided by (rows * world)  (losses.py:96-98)
+    bc = torch.full((1, 8), float(rank + 1))
+    P.allreduce_sum_(bc)
+    res["center"] = (bc / (4 * world)).tolist()
+    # gradient mean over ranks, bucketed
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    res["buckets"] = P.mean_gradients_(params, bucket_bytes=64)
+    res["grads"] = [float(p.grad.flatten()[0]) for p in params]
+    lo, hi = P.shard_bounds(11, rank, world)
+    res["shard"] = [lo, hi]
+    out[rank] = res
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_helpers():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29611, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert (r0["seed"], r1["seed"]) == (42, 43)
+    assert r0["max"] == [11.0, 5.0] == r1["max"]
+    assert r0["center"] == r1["center"] == [[3.0 / 8] * 8]
+    assert r0["grads"] == r1["grads"] == [1.5, 3.0, 4.5]          # mean over ranks of (rank+1)*(i+1)
+    assert r0["buckets"] == r1["buckets"] >= 2
+    assert r0["shard"] == [0, 6] and r1["shard"] == [6, 11]
+
+
+def test_scaled_lr_rule():
+    from headct_foundation_b200 import parallel as P
+    assert P.scaled_lr(1.5e-4, 256, 8) == pytest.approx(1.5e-4 * 8)
+    assert P.shard_bounds(10, 0, 1) == (0, 10)
+
+
+@pytest.mark.timeout(600)
+def test_bench_reference_arm_under_torchrun_two_ranks():
+    """`bench.py --impl reference` under torchrun: rank 0 alone prints ONE JSON line, rank 1 exits 0 without work."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "3", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=580, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "volumes/s" and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0

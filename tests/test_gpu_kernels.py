@@ -100,8 +100,20 @@ def test_gemm_epilogues(cuda, HF):
     assert _rel(o2, acc + bias + pos[idx.long()]) < 2e-3
 
 
+def test_gemm_fused_colsum(cuda, HF):
+    M, N, K = 1000, 768, 256
+    g = torch.Generator(device="cuda").manual_seed(9)
+    A = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    B = (torch.randn(N, K, device=cuda, generator=g) / math.sqrt(K)).bfloat16()
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=cuda)
+    HF.gemm(A, B, M=M, N=N, K=K, lda=K, ldb=K, out=out, ldo=N, epi=HF.EPI_BF16, colsum=cs)
+    assert _rel(cs, out.float().sum(0)) < 1e-5
+
+
 # ------------------------------------------------------------------ LayerNorm
-@pytest.mark.parametrize("rows,dim,eps", [(1000, 768, 1e-5), (333, 96, 1e-6), (64, 192, 1e-5), (50, 2048, 1e-5)])
+@pytest.mark.parametrize("rows,dim,eps", [(1000, 768, 1e-5), (333, 96, 1e-6), (64, 192, 1e-5), (50, 1024, 1e-5),
+                                          (5000, 768, 1e-5)])
 def test_layernorm_fwd_bwd(cuda, HF, rows, dim, eps):
     g = torch.Generator(device="cuda").manual_seed(rows)
     x = torch.randn(rows, dim, device=cuda, generator=g) * 2 + 0.5
@@ -120,6 +132,8 @@ def test_layernorm_fwd_bwd(cuda, HF, rows, dim, eps):
     assert _rel(dx, xr.grad + dres) < 1e-5
     assert _rel(dx16.float(), xr.grad + dres) < 5e-3
     assert _rel(dg, wr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    _, d16, _, _, dsum = HF.layernorm_bwd(dy, x, w, mean, rstd, dres, True, want_colsum=True)
+    assert _rel(dsum, d16.float().sum(0)) < 1e-5
     dx_b, _, _, _ = HF.layernorm_bwd(dy.bfloat16(), x, w, mean, rstd, None, False)
     xr.grad = None
     torch.nn.functional.layer_norm(xr, (dim,), wr, br, eps).backward(dy.bfloat16().float())
