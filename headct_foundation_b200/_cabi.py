@@ -73,6 +73,7 @@ _SIGNATURES = {
     "hct_grad_norms_multi": [_P, _I32, _P, _P],
     "hct_profile_enable": [_I32],
     "hct_gemm_set_cta_pair": [_I32],
+    "hct_attention_set_tcgen05": [_I32],
     "hct_profile_collect": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
     "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
 }
@@ -102,6 +103,8 @@ def lib() -> C.CDLL:
         L.hct_launch_count.restype = C.c_longlong
         if os.environ.get("HCT_GEMM_CTA_PAIR", "1") == "0":      # debugging aid: single-CTA tcgen05 kernel
             L.hct_gemm_set_cta_pair(0)
+        if os.environ.get("HCT_ATTN_TCGEN05", "1") == "0":       # debugging aid: mma.sync attention only
+            L.hct_attention_set_tcgen05(0)
         _lib = L
     return _lib
 

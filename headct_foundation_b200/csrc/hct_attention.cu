@@ -81,7 +81,7 @@ __device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], const bf16* tile, in
 template <int HD>
 __global__ void __launch_bounds__(NTHREADS)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int S, int H,
-                float scale) {
+                float scale, int q_start) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sK = sQ + BLK * Tile<HD>::PITCH;                 // 2 stages
@@ -96,7 +96,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
   const int nkb = (S + BLK - 1) / BLK;
   const float sl2 = scale * LOG2E;
 
-  load_tile<HD>(sQ, qg, rs, qb * BLK, S);
+  const int q_base = q_start + qb * BLK;
+  load_tile<HD>(sQ, qg, rs, q_base, S);
   load_tile<HD>(sK, kg, rs, 0, S);
   load_tile<HD>(sV, vg, rs, 0, S);
   cp_async_commit();
@@ -200,7 +201,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __r
     l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 1);
     l_i[r] += __shfl_xor_sync(0xffffffffu, l_i[r], 2);
   }
-  const int row0 = qb * BLK + warp * 16 + (lane >> 2);
+  const int row0 = q_base + warp * 16 + (lane >> 2);
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = row0 + r * 8;
@@ -509,12 +510,12 @@ int set_smem(K kernel, int bytes) {
 }
 
 template <int HD>
-int launch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, cudaStream_t st) {
+int launch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, int q_start, cudaStream_t st) {
   const int smem = 5 * Tile<HD>::BYTES;
   static bool configured = false;
   if (!configured) { int rc = set_smem(attn_fwd_kernel<HD>, smem); if (rc) return rc; configured = true; }
-  dim3 grid((S + BLK - 1) / BLK, H, B);
-  attn_fwd_kernel<HD><<<grid, NTHREADS, smem, st>>>(qkv, out, lse, S, H, 1.0f / sqrtf(static_cast<float>(HD)));
+  dim3 grid((S - q_start + BLK - 1) / BLK, H, B);
+  attn_fwd_kernel<HD><<<grid, NTHREADS, smem, st>>>(qkv, out, lse, S, H, 1.0f / sqrtf(static_cast<float>(HD)), q_start);
   return hct_check_launch("attn_fwd_kernel");
 }
 
@@ -540,16 +541,33 @@ int launch_bwd(const bf16* qkv, const bf16* dout, const float* lse, const float*
 
 }  // namespace
 
+// tcgen05 kernels (hct_attention_sm100.cu)
+int hct_attn_tc_tiles(int S);
+int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles, cudaStream_t st);
+int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
+                         int H, int hd, cudaStream_t st);
+static bool g_attn_tc = true;
+extern "C" int hct_attention_set_tcgen05(int enable) { g_attn_tc = enable != 0; return HCT_OK; }
+
 extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H, int32_t hd,
                                  hct_stream_t s) {
   HCT_REQUIRE(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attention_fwd: bad B=%d S=%d H=%d", B, S, H);
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const bf16* q = static_cast<const bf16*>(qkv);
   bf16* o = static_cast<bf16*>(out);
+  int q_start = 0;
+  if (g_attn_tc && (hd == 64 || hd == 48)) {
+    // full 128-row query tiles on tcgen05; the few rows behind them (the cls token makes S = 128 k + 1) on mma.sync
+    const int n_tiles = hct_attn_tc_tiles(S);
+    int rc = hct_attention_fwd_tc(qkv, out, lse, B, S, H, hd, n_tiles, st);
+    if (rc != HCT_OK) return rc;
+    q_start = n_tiles * 128;
+    if (q_start >= S) return HCT_OK;
+  }
   switch (hd) {
-    case 64: return launch_fwd<64>(q, o, lse, B, S, H, st);
-    case 48: return launch_fwd<48>(q, o, lse, B, S, H, st);
-    case 32: return launch_fwd<32>(q, o, lse, B, S, H, st);
+    case 64: return launch_fwd<64>(q, o, lse, B, S, H, q_start, st);
+    case 48: return launch_fwd<48>(q, o, lse, B, S, H, q_start, st);
+    case 32: return launch_fwd<32>(q, o, lse, B, S, H, q_start, st);
     default: hct_set_error("attention_fwd: head dim %d unsupported (32/48/64)", hd); return HCT_ERR_UNSUPPORTED;
   }
 }
@@ -564,6 +582,7 @@ extern "C" int hct_attention_bwd(const void* qkv, const void* out, const void* d
       static_cast<const bf16*>(out), static_cast<const bf16*>(dout), delta_ws, S, H, hd, total);
   int rc = hct_check_launch("attn_delta_kernel");
   if (rc) return rc;
+  if (g_attn_tc && (hd == 64 || hd == 48)) return hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, st);
   const bf16* q = static_cast<const bf16*>(qkv);
   const bf16* d = static_cast<const bf16*>(dout);
   bf16* dq = static_cast<bf16*>(dqkv);

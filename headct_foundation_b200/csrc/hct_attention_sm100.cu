@@ -1,0 +1,688 @@
+// Flash attention on tcgen05 / TMEM for sm_100a (F.scaled_dot_product_attention, attentionblock.py:61).
+//
+// Forward: one CTA per (batch, head, 128-query tile), two CTAs per SM.
+//   warp 0   TMA producer: Q once, then K_j / V_j tiles (128 keys) straight out of the qkv GEMM output
+//            ([B,S,3,H,hd], 128B-swizzled boxes of 64 columns; hd = 48 uses the first 48 of them)
+//   warp 1   MMA issuer:   S = Q K_j^T (128x128, K = hd) into TMEM, then O += P_j V_j (128 x hd, K = 128)
+//   warps 2-5 softmax:     one query row per thread (TMEM lane = row): tcgen05.ld S, online max / exp2 / sum,
+//            P_j written as bf16 into a 128B-swizzled K-major smem tile (the A operand of the PV MMA),
+//            O rescaled in TMEM when the running max moves, final O / l and log-sum-exp written out.
+// Everything between the roles is mbarrier-synchronised; S and O never leave the SM.
+#include "../../include/hct_b200.h"
+#include "hct_tcgen05.cuh"
+
+namespace {
+using namespace hct_tc;
+
+constexpr int TILE = 128;                  // query rows per CTA, keys per inner block
+constexpr int TILE_BYTES = TILE * 128;     // 128 rows x 64 bf16
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2f(float x) {   // bare MUFU.EX2 (ftz); ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// bf16 P/dS tile [128 rows][128 cols] as two 64-column K-major SW128 halves: address of 16-byte chunk `ch` (0..15)
+__device__ __forceinline__ uint32_t ptile_addr(uint32_t base, int row, int ch) {
+  return base + (ch >> 3) * TILE_BYTES + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+constexpr int FWD_THREADS = 192;
+constexpr int FWD_TMEM_COLS = 256;         // S: cols [0,128), O: cols [128, 128+hd)
+constexpr int FWD_SMEM = 5 * TILE_BYTES + 1024 + 128;   // Q, K, V, P(2 halves) + align slack + barriers
+
+template <int HD>
+__global__ void __launch_bounds__(FWD_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse, int S,
+                   int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
+           *s_full = bars + 5, *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * HD;
+  const int nkb = (S + TILE - 1) / TILE;
+  const float sl2 = scale * LOG2E;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQKV)) : "memory");
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, FWD_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(q_full, TILE_BYTES);
+    tma_load_2d(smem_u32(sQ), &tmQKV, q_full, h * HD, b * S + qt * TILE);
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(k_empty, (j & 1) ^ 1u);
+      mbar_expect_tx(k_full, TILE_BYTES);
+      tma_load_2d(smem_u32(sK), &tmQKV, k_full, D + h * HD, b * S + j * TILE);
+      mbar_wait(v_empty, (j & 1) ^ 1u);
+      mbar_expect_tx(v_full, TILE_BYTES);
+      tma_load_2d(smem_u32(sV), &tmQKV, v_full, 2 * D + h * HD, b * S + j * TILE);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = make_idesc_bf16(TILE, TILE, false, false);
+    const uint32_t idesc_o = make_idesc_bf16(TILE, HD, false, true);
+    const uint64_t dQ = make_sdesc_sw128(smem_u32(sQ), false, 0);
+    const uint64_t dK = make_sdesc_sw128(smem_u32(sK), false, 0);
+    const uint64_t dV = make_sdesc_sw128(smem_u32(sV), true, TILE_BYTES);
+    const uint64_t dP0 = make_sdesc_sw128(smem_u32(sP), false, 0);
+    const uint64_t dP1 = make_sdesc_sw128(smem_u32(sP + TILE_BYTES), false, 0);
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(k_full, j & 1);
+      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dQ + ks * 2, dK + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+      tc_commit(s_full);
+      tc_commit(k_empty);
+      mbar_wait(p_full, j & 1);
+      mbar_wait(v_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < TILE / 16; ++ks)
+        tc_mma(tmem_O, (ks < 4 ? dP0 : dP1) + (ks & 3) * 2, dV + ks * 128, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+      tc_commit(pv_done);
+      tc_commit(v_empty);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax / correction / epilogue: one query row per thread =====================
+    const int q = warp & 3;
+    const int row_local = q * 32 + lane;
+    const int row = qt * TILE + row_local;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t sP_addr = smem_u32(sP);
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int col_base = j * TILE;
+      const bool partial = col_base + TILE > S;
+      float mb = -INFINITY;
+      const int nvalid = partial ? S - col_base : TILE;       // valid key columns in this block (>= 1)
+      const int nchunks = (nvalid + 31) >> 5;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        if (!partial || (c + 1) * 32 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mb = fmaxf(mb, __uint_as_float(v[i]));
+        } else {
+          const int lim = nvalid - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mb = fmaxf(mb, i < lim ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m, mb);
+      const float alpha = ex2f((m - m_new) * sl2);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {      // running max moved: rescale the O accumulator in TMEM
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_off, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_O + lane_off, o);
+          if (HD > 32) {
+            if (HD == 64) {
+              tmem_ld32(tmem_O + lane_off + 32, o);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tmem_O + lane_off + 32, o);
+            } else {
+              uint32_t o2[16];
+              tmem_ld16(tmem_O + lane_off + 32, o2);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
+              tmem_st16(tmem_O + lane_off + 32, o2);
+            }
+          }
+          tmem_st_wait();
+        }
+      }
+      const float msc = m_new * sl2;
+      float rsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (c < nchunks) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          if (!partial || (c + 1) * 32 <= nvalid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -msc));
+              const float p1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
+              rsum += p0 + p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          } else {
+            const int lim = nvalid - c * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = i < lim ? ex2f(fmaf(__uint_as_float(v[i]), sl2, -msc)) : 0.f;
+              const float p1 = i + 1 < lim ? ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -msc)) : 0.f;
+              rsum += p0 + p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;          // keys beyond S contribute nothing
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(ptile_addr(sP_addr, row_local, c * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);           // S fully consumed: the next Q K^T may overwrite it
+      l = l * alpha + rsum;
+      m = m_new;
+      fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the tensor core
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> bf16, log-sum-exp
+    mbar_wait(pv_done, (nkb - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    bf16* orow = out + (static_cast<long long>(b) * S + row) * D + h * HD;
+    {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_off, o);
+      if (row < S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 8 * g) = u;
+        }
+      }
+    }
+    if (HD == 64) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_off + 32, o);
+      if (row < S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 32 + 8 * g) = u;
+        }
+      }
+    } else if (HD == 48) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + 32, o);
+      if (row < S) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 32 + 8 * g) = u;
+        }
+      }
+    }
+    if (row < S) lse[(static_cast<long long>(b) * H + h) * S + row] = m * scale + logf(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FWD_TMEM_COLS);
+  }
+}
+
+// =====================================================================================================
+// Backward.  Two kernels, both two CTAs per SM, TMEM budget 256 columns each; no atomics, deterministic.
+//   dK/dV kernel: CTA = (batch, head, 128 keys); rows (TMEM lanes) are KEYS.  Per 64-query block:
+//        S^T = K Q^T, dP^T = V dO^T   -> TMEM (2 x 64 cols)
+//        P^T = exp2(S^T*c - lse[q]),  dS^T = P^T (dP^T - delta[q])   (softmax threads, column-indexed stats in smem)
+//        dV += P^T dO,  dK += dS^T Q  (A = bf16 tiles written by the softmax threads, B = the TMA-loaded dO / Q
+//                                     tiles read MN-major, i.e. exactly as stored)
+//   dQ kernel:   CTA = (batch, head, 128 queries); rows are QUERIES.  Per 64-key block:
+//        S = Q K^T, dP = dO V^T -> TMEM;  dS = P (dP - delta[row]);  dQ += dS K  (K tile read MN-major)
+// =====================================================================================================
+constexpr int HALF_BYTES = 64 * 128;       // 64 rows x 64 bf16
+constexpr int BWD_THREADS = 192;
+constexpr int BWD_TMEM_COLS = 256;
+constexpr int DKDV_SMEM = 2 * TILE_BYTES + 4 * HALF_BYTES + 2 * TILE_BYTES + 1024 + 1024 + 128;
+constexpr int DQ_SMEM = 2 * TILE_BYTES + 4 * HALF_BYTES + TILE_BYTES + 1024 + 128;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int HD>
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                        const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
+                        const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sK = smem;                               // [128 keys][64]
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;              // 2 stages x [64 queries][64]
+  uint8_t* sdO = sQ + 2 * HALF_BYTES;               // 2 stages
+  uint8_t* sPt = sdO + 2 * HALF_BYTES;              // [128 keys][64 queries] bf16
+  uint8_t* sdSt = sPt + TILE_BYTES;
+  float* sStat = reinterpret_cast<float*>(sdSt + TILE_BYTES);   // [2 stages][lse 64 | delta 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 1024);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *s_full = bars + 5,
+           *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * HD;
+  const int nqb = (S + 63) / 64;
+  const float sl2 = scale * LOG2E;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_dV = tmem_base + 128, tmem_dK = tmem_base + 192;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+    tma_load_2d(smem_u32(sK), &tmQKV128, kv_full, D + h * HD, b * S + kt * TILE);
+    tma_load_2d(smem_u32(sV), &tmQKV128, kv_full, 2 * D + h * HD, b * S + kt * TILE);
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i & 1;
+      mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1u);
+      mbar_expect_tx(&qdo_full[st], 2 * HALF_BYTES);
+      tma_load_2d(smem_u32(sQ + st * HALF_BYTES), &tmQKV64, &qdo_full[st], h * HD, b * S + i * 64);
+      tma_load_2d(smem_u32(sdO + st * HALF_BYTES), &tmDO64, &qdo_full[st], h * HD, b * S + i * 64);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = make_idesc_bf16(TILE, 64, false, false);
+    const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
+    const uint64_t dK_ = make_sdesc_sw128(smem_u32(sK), false, 0);
+    const uint64_t dV_ = make_sdesc_sw128(smem_u32(sV), false, 0);
+    const uint64_t dPt = make_sdesc_sw128(smem_u32(sPt), false, 0);
+    const uint64_t dSt = make_sdesc_sw128(smem_u32(sdSt), false, 0);
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i & 1;
+      const uint64_t dQk = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), false, 0);
+      const uint64_t dOk = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), false, 0);
+      const uint64_t dQm = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), true, HALF_BYTES);
+      const uint64_t dOm = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), true, HALF_BYTES);
+      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      if (i > 0) mbar_wait(s_empty, (i - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dK_ + ks * 2, dQk + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_dP, dV_ + ks * 2, dOk + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+      tc_commit(s_full);
+      mbar_wait(p_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tc_mma(tmem_dV, dPt + ks * 2, dOm + ks * 128, idesc_g, (i > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tc_mma(tmem_dK, dSt + ks * 2, dQm + ks * 128, idesc_g, (i > 0 || ks > 0) ? 1u : 0u);
+      tc_commit(pv_done);
+      tc_commit(&qdo_empty[st]);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax-backward threads: one KEY row per thread =====================
+    const int q = warp & 3;
+    const int row_local = q * 32 + lane;
+    const int kvrow = kt * TILE + row_local;
+    const bool row_ok = kvrow < S;
+    const int tid = threadIdx.x - 64;                         // 0..127 within the group
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t sPt_addr = smem_u32(sPt), sdSt_addr = smem_u32(sdSt);
+    const float* lse_g = lse + (static_cast<long long>(b) * H + h) * S;
+    const float* delta_g = delta + (static_cast<long long>(b) * H + h) * S;
+    for (int i = 0; i < nqb; ++i) {
+      float* stat = sStat + (i & 1) * 128;
+      {
+        const int qr = i * 64 + (tid & 63);
+        const float v = qr < S ? (tid < 64 ? lse_g[qr] * LOG2E : delta_g[qr]) : 0.f;
+        stat[tid] = v;                                        // [0,64) lse*log2e, [64,128) delta
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      if (i > 0) { mbar_wait(pv_done, (i - 1) & 1); tc_fence_after(); }   // previous P^T / dS^T tiles consumed
+      const bool full_blk = (kt * TILE + TILE <= S) && (i * 64 + 64 <= S);     // warp-uniform
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, sv);
+        tmem_ld32(tmem_dP + lane_off + c * 32, dv);
+        uint32_t pk[16], dk[16];
+        if (full_blk) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 ls = *reinterpret_cast<const float2*>(stat + c * 32 + e);
+            const float2 dl = *reinterpret_cast<const float2*>(stat + 64 + c * 32 + e);
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y));
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+          }
+        } else {
+          const int lim = row_ok ? S - i * 64 - c * 32 : 0;    // valid query columns in this chunk
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 ls = *reinterpret_cast<const float2*>(stat + c * 32 + e);
+            const float2 dl = *reinterpret_cast<const float2*>(stat + 64 + c * 32 + e);
+            const float p0 = e < lim ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x)) : 0.f;
+            const float p1 = e + 1 < lim ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y)) : 0.f;
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          st_shared_v4(ptile_addr(sPt_addr, row_local, c * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          st_shared_v4(ptile_addr(sdSt_addr, row_local, c * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: dV, dK rows
+    mbar_wait(pv_done, (nqb - 1) & 1);
+    tc_fence_after();
+    bf16* dkrow = dqkv + (static_cast<long long>(b) * S + kvrow) * (3LL * D) + D + h * HD;
+    bf16* dvrow = dkrow + D;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t src = which == 0 ? tmem_dK : tmem_dV;
+      bf16* dst = which == 0 ? dkrow : dvrow;
+      const float sc = which == 0 ? scale : 1.0f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld16(src + lane_off + c0, o);
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * sc, __uint_as_float(o[8 * g + 1]) * sc);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * sc, __uint_as_float(o[8 * g + 3]) * sc);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * sc, __uint_as_float(o[8 * g + 5]) * sc);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * sc, __uint_as_float(o[8 * g + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c0 + 8 * g) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, BWD_TMEM_COLS); }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
+                      const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
+                      const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sQ = smem;                               // [128 queries][64]
+  uint8_t* sdO = smem + TILE_BYTES;
+  uint8_t* sK = smem + 2 * TILE_BYTES;              // 2 stages x [64 keys][64]
+  uint8_t* sV = sK + 2 * HALF_BYTES;
+  uint8_t* sdS = sV + 2 * HALF_BYTES;               // [128 queries][64 keys] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_BYTES);
+  uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_empty = bars + 3 /*[2]*/, *s_full = bars + 5,
+           *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = H * HD;
+  const int nkb = (S + 63) / 64;
+  const float sl2 = scale * LOG2E;
+
+  if (threadIdx.x == 0) {
+    mbar_init(qdo_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_dQ = tmem_base + 128;
+
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
+    tma_load_2d(smem_u32(sQ), &tmQKV128, qdo_full, h * HD, b * S + qt * TILE);
+    tma_load_2d(smem_u32(sdO), &tmDO128, qdo_full, h * HD, b * S + qt * TILE);
+    for (int j = 0; j < nkb; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1u);
+      mbar_expect_tx(&kv_full[st], 2 * HALF_BYTES);
+      tma_load_2d(smem_u32(sK + st * HALF_BYTES), &tmQKV64, &kv_full[st], D + h * HD, b * S + j * 64);
+      tma_load_2d(smem_u32(sV + st * HALF_BYTES), &tmQKV64, &kv_full[st], 2 * D + h * HD, b * S + j * 64);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc_s = make_idesc_bf16(TILE, 64, false, false);
+    const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
+    const uint64_t dQ_ = make_sdesc_sw128(smem_u32(sQ), false, 0);
+    const uint64_t dO_ = make_sdesc_sw128(smem_u32(sdO), false, 0);
+    const uint64_t dS_ = make_sdesc_sw128(smem_u32(sdS), false, 0);
+    mbar_wait(qdo_full, 0);
+    for (int j = 0; j < nkb; ++j) {
+      const int st = j & 1;
+      const uint64_t dKk = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), false, 0);
+      const uint64_t dVk = make_sdesc_sw128(smem_u32(sV + st * HALF_BYTES), false, 0);
+      const uint64_t dKm = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), true, HALF_BYTES);
+      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dQ_ + ks * 2, dKk + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_dP, dO_ + ks * 2, dVk + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+      tc_commit(s_full);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) tc_mma(tmem_dQ, dS_ + ks * 2, dKm + ks * 128, idesc_g, (j > 0 || ks > 0) ? 1u : 0u);
+      tc_commit(pv_done);
+      tc_commit(&kv_empty[st]);
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    const int row_local = q * 32 + lane;
+    const int row = qt * TILE + row_local;
+    const bool row_ok = row < S;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t sdS_addr = smem_u32(sdS);
+    const long long sidx = (static_cast<long long>(b) * H + h) * S + row;
+    const float lse_r = row_ok ? lse[sidx] * LOG2E : 0.f;
+    const float delta_r = row_ok ? delta[sidx] : 0.f;
+    for (int j = 0; j < nkb; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
+      const bool full_blk = j * 64 + 64 <= S;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, sv);
+        tmem_ld32(tmem_dP + lane_off + c * 32, dv);
+        uint32_t dk[16];
+        if (full_blk) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, -lse_r));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -lse_r));
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta_r), p1 * (__uint_as_float(dv[e + 1]) - delta_r));
+          }
+        } else {
+          const int lim = S - j * 64 - c * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = e < lim ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -lse_r)) : 0.f;
+            const float p1 = e + 1 < lim ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -lse_r)) : 0.f;
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta_r), p1 * (__uint_as_float(dv[e + 1]) - delta_r));
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_shared_v4(ptile_addr(sdS_addr, row_local, c * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (nkb - 1) & 1);
+    tc_fence_after();
+    bf16* dqrow = dqkv + (static_cast<long long>(b) * S + row) * (3LL * D) + h * HD;
+#pragma unroll 1
+    for (int c0 = 0; c0 < HD; c0 += 16) {
+      uint32_t o[16];
+      tmem_ld16(tmem_dQ + lane_off + c0, o);
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * scale, __uint_as_float(o[8 * g + 1]) * scale);
+          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * scale, __uint_as_float(o[8 * g + 3]) * scale);
+          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * scale, __uint_as_float(o[8 * g + 5]) * scale);
+          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * scale, __uint_as_float(o[8 * g + 7]) * scale);
+          *reinterpret_cast<uint4*>(dqrow + c0 + 8 * g) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, BWD_TMEM_COLS); }
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { hct_set_error("cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
+  return HCT_OK;
+}
+
+}  // namespace
+
+// Number of 128-row query tiles the tcgen05 kernels cover; the remaining (few) rows go to the mma.sync tail kernel.
+int hct_attn_tc_tiles(int S) {
+  const int rem = S % TILE;
+  if (S > TILE && rem != 0 && rem <= 32) return S / TILE;
+  return (S + TILE - 1) / TILE;
+}
+
+int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles,
+                         cudaStream_t st) {
+  CUtensorMap tm;
+  const long long D3 = 3LL * H * hd;
+  int rc = hct_make_tmap_bf16_2d(&tm, qkv, D3, static_cast<long long>(B) * S, D3, 64, TILE);
+  if (rc != HCT_OK) return rc;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  dim3 grid(n_tiles, H, B);
+  if (hd == 64) {
+    static bool cfg = false;
+    if (!cfg) { rc = set_smem(attn_fwd_tc_kernel<64>, FWD_SMEM); if (rc) return rc; cfg = true; }
+    attn_fwd_tc_kernel<64><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm, static_cast<bf16*>(out), lse, S, H, scale);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { rc = set_smem(attn_fwd_tc_kernel<48>, FWD_SMEM); if (rc) return rc; cfg = true; }
+    attn_fwd_tc_kernel<48><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm, static_cast<bf16*>(out), lse, S, H, scale);
+  }
+  return hct_check_launch("attn_fwd_tc_kernel");
+}
+
+template <int HD>
+static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorMap& do128, const CUtensorMap& do64,
+                         const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, cudaStream_t st) {
+  static bool cfg = false;
+  if (!cfg) {
+    int rc = set_smem(attn_bwd_dkdv_tc_kernel<HD>, DKDV_SMEM); if (rc) return rc;
+    rc = set_smem(attn_bwd_dq_tc_kernel<HD>, DQ_SMEM); if (rc) return rc;
+    cfg = true;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  dim3 grid((S + TILE - 1) / TILE, H, B);
+  attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, DKDV_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale);
+  int rc = hct_check_launch("attn_bwd_dkdv_tc_kernel");
+  if (rc) return rc;
+  attn_bwd_dq_tc_kernel<HD><<<grid, BWD_THREADS, DQ_SMEM, st>>>(q128, q64, do128, lse, delta, dqkv, S, H, scale);
+  return hct_check_launch("attn_bwd_dq_tc_kernel");
+}
+
+int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
+                         int H, int hd, cudaStream_t st) {
+  CUtensorMap q128, q64, do128, do64;
+  const long long D = static_cast<long long>(H) * hd, D3 = 3 * D, rows = static_cast<long long>(B) * S;
+  int rc = hct_make_tmap_bf16_2d(&q128, qkv, D3, rows, D3, 64, TILE); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&q64, qkv, D3, rows, D3, 64, 64); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&do128, dout, D, rows, D, 64, TILE); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&do64, dout, D, rows, D, 64, 64); if (rc) return rc;
+  if (hd == 64) return launch_bwd_tc<64>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, st);
+  return launch_bwd_tc<48>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, st);
+}
