@@ -205,8 +205,10 @@ def run_ours(args):
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev0.record()
+        t_host0 = time.perf_counter()
         for _ in range(args.steps):
             loss = train_step(resident)
+        host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps    # CPU time to enqueue one step
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
@@ -282,7 +284,7 @@ def run_ours(args):
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no explicit flush"
                                     % (resident.numel() * 4 / 1e6),
-                       "final_loss": final_loss},
+                       "final_loss": final_loss, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "tensor", "kernel": "hct_gemm_tcgen05_kernel (all epilogues)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
                          "peak_source": peaks["src"], "gemm_launches": int(gemm_n.value),

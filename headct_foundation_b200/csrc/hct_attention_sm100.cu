@@ -33,21 +33,23 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 constexpr int FWD_THREADS = 192;
-constexpr int FWD_TMEM_COLS = 256;         // S: cols [0,128), O: cols [128, 128+hd)
-constexpr int FWD_SMEM = 5 * TILE_BYTES + 1024 + 128;   // Q, K, V, P(2 halves) + align slack + barriers
+constexpr int FWD_TK = 64;                 // keys per inner block
+constexpr int FWD_TMEM_COLS = 128;         // S: cols [0,64), O: cols [64, 64+hd)  -> four CTAs per SM
+constexpr int FWD_KV_BYTES = FWD_TK * 128; // [64 keys][64 bf16]
+constexpr int FWD_SMEM = 2 * TILE_BYTES + 2 * FWD_KV_BYTES + 1024 + 128;   // Q, P, K, V + align slack + barriers
 
 template <int HD>
-__global__ void __launch_bounds__(FWD_THREADS, 2)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse, int S,
-                   int H, float scale) {
+__global__ void __launch_bounds__(FWD_THREADS, 4)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                   bf16* __restrict__ out, float* __restrict__ lse, int S, int H, float scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;
-  uint8_t* sV = smem + 2 * TILE_BYTES;
-  uint8_t* sP = smem + 3 * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint8_t* sP = smem + TILE_BYTES;                   // [128 queries][64 keys] bf16, K-major SW128
+  uint8_t* sK = smem + 2 * TILE_BYTES;
+  uint8_t* sV = sK + FWD_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FWD_KV_BYTES);
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
            *s_full = bars + 5, *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
@@ -55,11 +57,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = H * HD;
-  const int nkb = (S + TILE - 1) / TILE;
+  const int nkb = (S + FWD_TK - 1) / FWD_TK;
   const float sl2 = scale * LOG2E;
 
   if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQKV)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
     mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
     mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -69,29 +72,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     mbar_expect_tx(q_full, TILE_BYTES);
-    tma_load_2d(smem_u32(sQ), &tmQKV, q_full, h * HD, b * S + qt * TILE);
+    tma_load_2d(smem_u32(sQ), &tmQ, q_full, h * HD, b * S + qt * TILE);
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(k_empty, (j & 1) ^ 1u);
-      mbar_expect_tx(k_full, TILE_BYTES);
-      tma_load_2d(smem_u32(sK), &tmQKV, k_full, D + h * HD, b * S + j * TILE);
+      mbar_expect_tx(k_full, FWD_KV_BYTES);
+      tma_load_2d(smem_u32(sK), &tmKV, k_full, D + h * HD, b * S + j * FWD_TK);
       mbar_wait(v_empty, (j & 1) ^ 1u);
-      mbar_expect_tx(v_full, TILE_BYTES);
-      tma_load_2d(smem_u32(sV), &tmQKV, v_full, 2 * D + h * HD, b * S + j * TILE);
+      mbar_expect_tx(v_full, FWD_KV_BYTES);
+      tma_load_2d(smem_u32(sV), &tmKV, v_full, 2 * D + h * HD, b * S + j * FWD_TK);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc_s = make_idesc_bf16(TILE, TILE, false, false);
+    const uint32_t idesc_s = make_idesc_bf16(TILE, FWD_TK, false, false);
     const uint32_t idesc_o = make_idesc_bf16(TILE, HD, false, true);
     const uint64_t dQ = make_sdesc_sw128(smem_u32(sQ), false, 0);
     const uint64_t dK = make_sdesc_sw128(smem_u32(sK), false, 0);
-    const uint64_t dV = make_sdesc_sw128(smem_u32(sV), true, TILE_BYTES);
-    const uint64_t dP0 = make_sdesc_sw128(smem_u32(sP), false, 0);
-    const uint64_t dP1 = make_sdesc_sw128(smem_u32(sP + TILE_BYTES), false, 0);
+    const uint64_t dV = make_sdesc_sw128(smem_u32(sV), true, FWD_KV_BYTES);
+    const uint64_t dP = make_sdesc_sw128(smem_u32(sP), false, 0);
     mbar_wait(q_full, 0);
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(k_full, j & 1);
@@ -105,8 +107,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       mbar_wait(v_full, j & 1);
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < TILE / 16; ++ks)
-        tc_mma(tmem_O, (ks < 4 ? dP0 : dP1) + (ks & 3) * 2, dV + ks * 128, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < FWD_TK / 16; ++ks)
+        tc_mma(tmem_O, dP + ks * 2, dV + ks * 128, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
       tc_commit(pv_done);
       tc_commit(v_empty);
     }
@@ -121,91 +123,86 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int col_base = j * TILE;
-      const bool partial = col_base + TILE > S;
+      const int nvalid = min(FWD_TK, S - j * FWD_TK);         // valid key columns in this block (>= 1)
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem_S + lane_off, v0);
+      tmem_ld32(tmem_S + lane_off + 32, v1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);                    // S is in registers: the next Q K^T may overwrite it
       float mb = -INFINITY;
-      const int nvalid = partial ? S - col_base : TILE;       // valid key columns in this block (>= 1)
-      const int nchunks = (nvalid + 31) >> 5;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        if (!partial || (c + 1) * 32 <= nvalid) {
+      if (nvalid == FWD_TK) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mb = fmaxf(mb, __uint_as_float(v[i]));
-        } else {
-          const int lim = nvalid - c * 32;
+        for (int i = 0; i < 32; ++i) mb = fmaxf(mb, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mb = fmaxf(mb, i < lim ? __uint_as_float(v[i]) : -INFINITY);
+        for (int i = 0; i < 32; ++i) {
+          mb = fmaxf(mb, i < nvalid ? __uint_as_float(v0[i]) : -INFINITY);
+          mb = fmaxf(mb, i + 32 < nvalid ? __uint_as_float(v1[i]) : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m, mb);
-      const float alpha = ex2f((m - m_new) * sl2);
+      // Lazy rescaling: the reference point m only moves when the block maximum exceeds it by more than 2^8 in the
+      // exponent domain (or on the first block).  Probabilities are then at most 2^8 -- harmless in fp32 / bf16 --
+      // and the O accumulator in TMEM (whose read-back is the scarce resource here) is rescaled only rarely.
+      float alpha = 1.0f;
+      if (j == 0) {
+        m = mb;
+      } else if ((mb - m) * sl2 > 8.0f) {
+        alpha = ex2f((m - mb) * sl2);
+        m = mb;
+      }
+      const float msc = m * sl2;
+      float rsum = 0.f;
+      uint32_t pk[32];
+      if (nvalid == FWD_TK) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = ex2f(fmaf(__uint_as_float(v0[i]), sl2, -msc)), a1 = ex2f(fmaf(__uint_as_float(v0[i + 1]), sl2, -msc));
+          const float b0 = ex2f(fmaf(__uint_as_float(v1[i]), sl2, -msc)), b1 = ex2f(fmaf(__uint_as_float(v1[i + 1]), sl2, -msc));
+          rsum += (a0 + a1) + (b0 + b1);
+          pk[i >> 1] = pack_bf16x2(a0, a1);
+          pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float a0 = i < nvalid ? ex2f(fmaf(__uint_as_float(v0[i]), sl2, -msc)) : 0.f;
+          const float a1 = i + 1 < nvalid ? ex2f(fmaf(__uint_as_float(v0[i + 1]), sl2, -msc)) : 0.f;
+          const float b0 = i + 32 < nvalid ? ex2f(fmaf(__uint_as_float(v1[i]), sl2, -msc)) : 0.f;
+          const float b1 = i + 33 < nvalid ? ex2f(fmaf(__uint_as_float(v1[i + 1]), sl2, -msc)) : 0.f;
+          rsum += (a0 + a1) + (b0 + b1);
+          pk[i >> 1] = pack_bf16x2(a0, a1);
+          pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
+        }
+      }
+      l = l * alpha + rsum;
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1);                      // previous P V retired: P tile reusable, O stable
         tc_fence_after();
-        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {      // running max moved: rescale the O accumulator in TMEM
+        if (!__all_sync(0xffffffffu, alpha == 1.0f)) {        // running max moved: rescale the O accumulator in TMEM
           uint32_t o[32];
           tmem_ld32(tmem_O + lane_off, o);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
           tmem_st32(tmem_O + lane_off, o);
-          if (HD > 32) {
-            if (HD == 64) {
-              tmem_ld32(tmem_O + lane_off + 32, o);
+          if (HD == 64) {
+            tmem_ld32(tmem_O + lane_off + 32, o);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tmem_O + lane_off + 32, o);
-            } else {
-              uint32_t o2[16];
-              tmem_ld16(tmem_O + lane_off + 32, o2);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_off + 32, o);
+          } else if (HD == 48) {
+            uint32_t o2[16];
+            tmem_ld16(tmem_O + lane_off + 32, o2);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
-              tmem_st16(tmem_O + lane_off + 32, o2);
-            }
+            for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
+            tmem_st16(tmem_O + lane_off + 32, o2);
           }
           tmem_st_wait();
         }
       }
-      const float msc = m_new * sl2;
-      float rsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-        if (c < nchunks) {
-          uint32_t v[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, v);
-          if (!partial || (c + 1) * 32 <= nvalid) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = ex2f(fmaf(__uint_as_float(v[i]), sl2, -msc));
-              const float p1 = ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -msc));
-              rsum += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-          } else {
-            const int lim = nvalid - c * 32;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = i < lim ? ex2f(fmaf(__uint_as_float(v[i]), sl2, -msc)) : 0.f;
-              const float p1 = i + 1 < lim ? ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -msc)) : 0.f;
-              rsum += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;          // keys beyond S contribute nothing
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          st_shared_v4(ptile_addr(sP_addr, row_local, c * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);           // S fully consumed: the next Q K^T may overwrite it
-      l = l * alpha + rsum;
-      m = m_new;
+      for (int g = 0; g < 8; ++g)
+        st_shared_v4(ptile_addr(sP_addr, row_local, g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the tensor core
       tc_fence_before();
       __syncwarp();
@@ -216,38 +213,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     tc_fence_after();
     const float inv = 1.0f / l;
     bf16* orow = out + (static_cast<long long>(b) * S + row) * D + h * HD;
-    {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_off, o);
-      if (row < S) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 8 * g) = u;
-        }
-      }
-    }
-    if (HD == 64) {
-      uint32_t o[32];
-      tmem_ld32(tmem_O + lane_off + 32, o);
-      if (row < S) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 32 + 8 * g) = u;
-        }
-      }
-    } else if (HD == 48) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < HD; c0 += 16) {
       uint32_t o[16];
-      tmem_ld16(tmem_O + lane_off + 32, o);
+      tmem_ld16(tmem_O + lane_off + c0, o);
       if (row < S) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -256,7 +225,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
           u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
           u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 32 + 8 * g) = u;
+          *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = u;
         }
       }
     }
@@ -639,20 +608,22 @@ int hct_attn_tc_tiles(int S) {
 
 int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles,
                          cudaStream_t st) {
-  CUtensorMap tm;
+  CUtensorMap tmq, tmkv;
   const long long D3 = 3LL * H * hd;
-  int rc = hct_make_tmap_bf16_2d(&tm, qkv, D3, static_cast<long long>(B) * S, D3, 64, TILE);
+  int rc = hct_make_tmap_bf16_2d(&tmq, qkv, D3, static_cast<long long>(B) * S, D3, 64, TILE);
+  if (rc != HCT_OK) return rc;
+  rc = hct_make_tmap_bf16_2d(&tmkv, qkv, D3, static_cast<long long>(B) * S, D3, 64, FWD_TK);
   if (rc != HCT_OK) return rc;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   dim3 grid(n_tiles, H, B);
   if (hd == 64) {
     static bool cfg = false;
     if (!cfg) { rc = set_smem(attn_fwd_tc_kernel<64>, FWD_SMEM); if (rc) return rc; cfg = true; }
-    attn_fwd_tc_kernel<64><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm, static_cast<bf16*>(out), lse, S, H, scale);
+    attn_fwd_tc_kernel<64><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
   } else {
     static bool cfg = false;
     if (!cfg) { rc = set_smem(attn_fwd_tc_kernel<48>, FWD_SMEM); if (rc) return rc; cfg = true; }
-    attn_fwd_tc_kernel<48><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tm, static_cast<bf16*>(out), lse, S, H, scale);
+    attn_fwd_tc_kernel<48><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
   }
   return hct_check_launch("attn_fwd_tc_kernel");
 }
