@@ -74,13 +74,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
 constexpr float kG0 = -1.59534958f * 1.4426950408889634f, kG1 = -7.34984774e-02f * 1.4426950408889634f,
                 kG2 = 5.20865699e-04f * 1.4426950408889634f, kG3 = 1.64242936e-05f * 1.4426950408889634f;
 __device__ __forceinline__ float phi_cdf_fast(float x, float& x2_out) {
-  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-  const float x2 = xc * xc;
+  const float x2 = fminf(x * x, 36.0f);      // beyond |x| = 6 the argument keeps growing linearly: sigma saturates
   float q = fmaf(kG3, x2, kG2);
   q = fmaf(q, x2, kG1);
   q = fmaf(q, x2, kG0);
   x2_out = x2;
-  return rcp_approx(1.0f + ex2_approx(xc * q));
+  return rcp_approx(1.0f + ex2_approx(x * q));
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float x2;
@@ -93,8 +92,7 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   float pd = fmaf(7.0f * 1.64242936e-05f * -1.0f, x2, 5.0f * -5.20865699e-04f);
   pd = fmaf(pd, x2, 3.0f * 7.34984774e-02f);
   pd = fmaf(pd, x2, 1.59534958f);
-  const float xc = fminf(fmaxf(x, -6.0f), 6.0f);
-  return fmaf(xc * s * (1.0f - s), pd, s);
+  return fmaf(x * s * (1.0f - s), pd, s);
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -117,15 +115,17 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_unit(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0,
-                                              const uint32_t (&acc)[32]) {
-  // ---- phase 1: thread = row, write 8 x 16 B with chunk index XOR (row & 7)  (conflict-free)
+// ---- phase 1: thread = row, write 8 x 16 B with chunk index XOR (row & 7)  (conflict-free)
+__device__ __forceinline__ void epilogue_stage(uint32_t stg, int lane, const uint32_t (&acc)[32]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     st_shared_v4(stg + lane * 128 + ((j ^ (lane & 7)) << 4), acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
   __syncwarp();
-  // ---- phase 2: lane = (row sub-index, column group)
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0) {
+  // ---- phase 2: lane = (row sub-index, column group); rows handled in two groups of four to bound registers
   const int jj = lane & 7, rsub = lane >> 3;
   const int col = col0 + jj * 4;
   const bool col_ok = col < p.N;                       // N % 8 == 0 -> a group of 4 is all-in or all-out
@@ -134,76 +134,79 @@ __device__ __forceinline__ void epilogue_unit(const GemmParams& p, uint32_t stg,
     if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
   }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-  long long orow[8];
-  bool ok[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = row_base + i * 4 + rsub;
-    ok[i] = col_ok && row < p.M;
-    orow[i] = row;
-    if (p.rows_in > 0) {
-      const int g = row / p.rows_in, r = row % p.rows_in + p.row_off;
-      ok[i] = ok[i] && r >= 0 && r < p.rows_out;
-      orow[i] = static_cast<long long>(g) * p.rows_out + r;
-    }
-  }
-  // operands that do not depend on the accumulator: issue all loads first
-  float4 extra[8];
-  uint2 aux[8];
-  if (EPI == HCT_EPI_RES_F32) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (ok[i]) extra[i] = *reinterpret_cast<const float4*>(p.res + static_cast<long long>(row_base + i * 4 + rsub) * p.ldres + col);
-  }
-  if (EPI == HCT_EPI_POS_F32) {
+  for (int grp = 0; grp < 1; ++grp) {
+    long long orow[8];
+    bool ok[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (ok[i]) {
-        const int row = row_base + i * 4 + rsub;
-        const int pr = p.pos_idx != nullptr ? p.pos_idx[row] : (row % p.pos_period);
-        extra[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(pr) * p.ldpos + col));
+      const int row = row_base + (grp * 8 + i) * 4 + rsub;
+      ok[i] = col_ok && row < p.M;
+      orow[i] = row;
+      if (p.rows_in > 0) {
+        const int g = row / p.rows_in, r = row % p.rows_in + p.row_off;
+        ok[i] = ok[i] && r >= 0 && r < p.rows_out;
+        orow[i] = static_cast<long long>(g) * p.rows_out + r;
       }
     }
-  }
-  if (EPI == HCT_EPI_DGELU_BF16) {
+    // operands that do not depend on the accumulator: issue the group's loads first
+    float4 extra[8];
+    uint2 aux[8];
+    if (EPI == HCT_EPI_RES_F32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (ok[i]) aux[i] = *reinterpret_cast<const uint2*>(p.aux + static_cast<long long>(row_base + i * 4 + rsub) * p.ldaux + col);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
-    if (!ok[i]) continue;
-    if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_F32 || EPI == HCT_EPI_ATOMIC_F32) {
-      v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+      for (int i = 0; i < 8; ++i)
+        if (ok[i]) extra[i] = *reinterpret_cast<const float4*>(p.res + static_cast<long long>(row_base + (grp * 8 + i) * 4 + rsub) * p.ldres + col);
     }
-    v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-    if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) {
-      if (EPI == HCT_EPI_GELU_BF16) {
-        if (p.out2 != nullptr) {
-          uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + orow[i] * p.ldo2 + col) = u;
+    if (EPI == HCT_EPI_POS_F32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (ok[i]) {
+          const int row = row_base + (grp * 8 + i) * 4 + rsub;
+          const int pr = p.pos_idx != nullptr ? p.pos_idx[row] : (row % p.pos_period);
+          extra[i] = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<long long>(pr) * p.ldpos + col));
         }
-        v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
       }
-      if (EPI == HCT_EPI_DGELU_BF16) {
-        const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
-        v.x *= gelu_grad_fast(a0.x); v.y *= gelu_grad_fast(a0.y); v.z *= gelu_grad_fast(a1.x); v.w *= gelu_grad_fast(a1.y);
+    }
+    if (EPI == HCT_EPI_DGELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (ok[i]) aux[i] = *reinterpret_cast<const uint2*>(p.aux + static_cast<long long>(row_base + (grp * 8 + i) * 4 + rsub) * p.ldaux + col);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = (grp * 8 + i) * 4 + rsub;
+      float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+      if (!ok[i]) continue;
+      if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_F32 || EPI == HCT_EPI_ATOMIC_F32) {
+        v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
       }
-      uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow[i] * p.ldo + col) = u;
-      if (p.colsum != nullptr) {   // column sums of the values as the consumer will read them (bf16-rounded)
-        const float2 r0 = unpack_bf16x2(u.x), r1 = unpack_bf16x2(u.y);
-        csum.x += r0.x; csum.y += r0.y; csum.z += r1.x; csum.w += r1.y;
+      v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+      if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) {
+        if (EPI == HCT_EPI_GELU_BF16) {
+          if (p.out2 != nullptr) {
+            uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + orow[i] * p.ldo2 + col) = u;
+          }
+          v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+        }
+        if (EPI == HCT_EPI_DGELU_BF16) {
+          const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
+          v.x *= gelu_grad_fast(a0.x); v.y *= gelu_grad_fast(a0.y); v.z *= gelu_grad_fast(a1.x); v.w *= gelu_grad_fast(a1.y);
+        }
+        uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow[i] * p.ldo + col) = u;
+        if (p.colsum != nullptr) {   // column sums of the values as the consumer will read them (bf16-rounded)
+          const float2 r0 = unpack_bf16x2(u.x), r1 = unpack_bf16x2(u.y);
+          csum.x += r0.x; csum.y += r0.y; csum.z += r1.x; csum.w += r1.y;
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + orow[i] * p.ldo + col;
+        if (EPI == HCT_EPI_RES_F32 || EPI == HCT_EPI_POS_F32) {
+          v.x += extra[i].x; v.y += extra[i].y; v.z += extra[i].z; v.w += extra[i].w;
+        }
+        if (EPI == HCT_EPI_ATOMIC_F32) red_add_v4(o, v.x, v.y, v.z, v.w);
+        else *reinterpret_cast<float4*>(o) = v;
       }
-    } else {
-      float* o = reinterpret_cast<float*>(p.out) + orow[i] * p.ldo + col;
-      if (EPI == HCT_EPI_RES_F32 || EPI == HCT_EPI_POS_F32) {
-        v.x += extra[i].x; v.y += extra[i].y; v.z += extra[i].z; v.w += extra[i].w;
-      }
-      if (EPI == HCT_EPI_ATOMIC_F32) red_add_v4(o, v.x, v.y, v.z, v.w);
-      else *reinterpret_cast<float4*>(o) = v;
     }
   }
   if ((EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) && p.colsum != nullptr) {
@@ -398,21 +401,52 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int w = unit; w < total_work; w += num_units) {
       const int tile = w % tiles;
       const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * TILE_M + rank * BM;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < (BN / 2) / 32; ++c) {
-        const int col0 = n0 + half * (BN / 2) + c * 32;
-        if (col0 < p.N && m0 < p.M) {   // warp-uniform
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2) + c * 32, v);
-          epilogue_unit<EPI>(p, stg, lane, m0 + q * 32, col0, v);
+      if (EPI == HCT_EPI_RES_F32 || EPI == HCT_EPI_DGELU_BF16) {
+        // the residual / pre-activation tile this warp will stream in its epilogue: pull it into L2 while the
+        // main loop of this tile is still running (one 128-byte line per lane and step)
+        const int prow = m0 + q * 32 + lane;
+        const int pcol = n0 + half * (BN / 2);
+        if (prow < p.M) {
+          if (EPI == HCT_EPI_RES_F32) {
+            const char* base = reinterpret_cast<const char*>(p.res + static_cast<long long>(prow) * p.ldres + pcol);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (pcol + k * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + k * 128));
+          } else {
+            const char* base = reinterpret_cast<const char*>(p.aux + static_cast<long long>(prow) * p.ldaux + pcol);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              if (pcol + k * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + k * 128));
+          }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      // software pipeline over the warp's four 32-column units: the TMEM load of unit c+1 is in flight while unit c
+      // is drained from the staging buffer; the accumulator stage is handed back to the MMA warp as soon as the
+      // last load has landed (before the last drain).
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2);
+      const int colw = n0 + half * (BN / 2);
+      const bool tile_ok = m0 < p.M;
+      int nunits = 0;
+      if (tile_ok && colw < p.N) nunits = min(4, (p.N - colw + 31) / 32);
+      uint32_t v[32];
+      if (nunits > 0) tmem_ld32_issue(t0, v);
+#pragma unroll 1
+      for (int c = 0; c < nunits; ++c) {
+        tmem_ld_wait();
+        epilogue_stage(stg, lane, v);                      // v is dead after staging: reuse it for the next load
+        if (c + 1 < nunits) {
+          tmem_ld32_issue(t0 + (c + 1) * 32, v);
+        } else {
+          tc_fence_before(); __syncwarp();
+          if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
+        }
+        epilogue_drain<EPI>(p, stg, lane, m0 + q * 32, colw + c * 32);
+      }
+      if (nunits == 0) {
+        tc_fence_before(); __syncwarp();
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }

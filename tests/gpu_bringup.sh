@@ -7,8 +7,7 @@ run() {
   local r=$?; echo "== $name -> exit $r"; tail -n ${TAILN:-30} gpurun_out/$name.log | cut -c1-3000
   [ $r -ne 0 ] && rc=$r
 }
-run attn python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -k attention
-run kernels python -m pytest tests/test_gpu_kernels.py -q -m gpu --tb=short -k "not attention"
-run models python -m pytest tests/test_gpu_models.py -q -m gpu --tb=short
-run bench256 python bench.py --batch 256 --steps 5 --warmup 3 --no-cpu-baseline
+run tests python -m pytest tests -q -m gpu --tb=short
+run smoke python __graft_entry__.py smoke
+run bench256 python bench.py --batch 256 --steps 10 --warmup 3
 exit $rc
