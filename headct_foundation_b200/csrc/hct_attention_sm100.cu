@@ -95,14 +95,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint64_t dV = make_sdesc_sw128(smem_u32(sV), true, FWD_KV_BYTES);
     const uint64_t dP = make_sdesc_sw128(smem_u32(sP), false, 0);
     mbar_wait(q_full, 0);
-    for (int j = 0; j < nkb; ++j) {
-      mbar_wait(k_full, j & 1);
-      if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
-      tc_fence_after();
+    // S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax threads have pulled S_j into registers, i.e. it runs
+    // underneath their exp / P-store work; P_j V_j follows when P_j has landed in shared memory.
+    mbar_wait(k_full, 0);
+    tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dQ + ks * 2, dK + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
-      tc_commit(s_full);
-      tc_commit(k_empty);
+    for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dQ + ks * 2, dK + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+    tc_commit(s_full);
+    tc_commit(k_empty);
+    for (int j = 0; j < nkb; ++j) {
+      if (j + 1 < nkb) {
+        mbar_wait(k_full, (j + 1) & 1);
+        mbar_wait(s_empty, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dQ + ks * 2, dK + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
+        tc_commit(s_full);
+        tc_commit(k_empty);
+      }
       mbar_wait(p_full, j & 1);
       mbar_wait(v_full, j & 1);
       tc_fence_after();
@@ -251,7 +261,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 //        S = Q K^T, dP = dO V^T -> TMEM;  dS = P (dP - delta[row]);  dQ += dS K  (K tile read MN-major)
 // =====================================================================================================
 constexpr int HALF_BYTES = 64 * 128;       // 64 rows x 64 bf16
-constexpr int BWD_THREADS = 192;
+constexpr int BWD_THREADS = 320;        // TMA warp, MMA warp, 2 x 4 softmax warps (each group owns 32 of a block's 64 columns)
 constexpr int BWD_TMEM_COLS = 256;
 constexpr int DKDV_SMEM = 2 * TILE_BYTES + 4 * HALF_BYTES + 2 * TILE_BYTES + 1024 + 1024 + 128;
 constexpr int DQ_SMEM = 2 * TILE_BYTES + 4 * HALF_BYTES + TILE_BYTES + 1024 + 128;
@@ -289,7 +299,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
@@ -320,12 +330,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const uint64_t dPt = make_sdesc_sw128(smem_u32(sPt), false, 0);
     const uint64_t dSt = make_sdesc_sw128(smem_u32(sdSt), false, 0);
     mbar_wait(kv_full, 0);
-    for (int i = 0; i < nqb; ++i) {
+    auto issue_sdp = [&](int i) {          // S^T = K Q_i^T and dP^T = V dO_i^T into TMEM
       const int st = i & 1;
       const uint64_t dQk = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), false, 0);
       const uint64_t dOk = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), false, 0);
-      const uint64_t dQm = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), true, HALF_BYTES);
-      const uint64_t dOm = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), true, HALF_BYTES);
       mbar_wait(&qdo_full[st], (i >> 1) & 1);
       if (i > 0) mbar_wait(s_empty, (i - 1) & 1);
       tc_fence_after();
@@ -334,6 +342,15 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_dP, dV_ + ks * 2, dOk + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
       tc_commit(s_full);
+    };
+    issue_sdp(0);
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i & 1;
+      // run ahead: block i+1's S^T / dP^T are computed while the softmax threads work on block i (they release the
+      // TMEM buffer as soon as they hold block i in registers)
+      if (i + 1 < nqb) issue_sdp(i + 1);
+      const uint64_t dQm = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), true, HALF_BYTES);
+      const uint64_t dOm = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), true, HALF_BYTES);
       mbar_wait(p_full, i & 1);
       tc_fence_after();
 #pragma unroll
@@ -349,28 +366,32 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const int row_local = q * 32 + lane;
     const int kvrow = kt * TILE + row_local;
     const bool row_ok = kvrow < S;
-    const int tid = threadIdx.x - 64;                         // 0..127 within the group
+    const int tid = threadIdx.x - 64;                         // 0..255 within the softmax warps
+    const int wg = (warp - 2) >> 2;                           // which 32-column half of each block this warp owns
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sPt_addr = smem_u32(sPt), sdSt_addr = smem_u32(sdSt);
     const float* lse_g = lse + (static_cast<long long>(b) * H + h) * S;
     const float* delta_g = delta + (static_cast<long long>(b) * H + h) * S;
     for (int i = 0; i < nqb; ++i) {
       float* stat = sStat + (i & 1) * 128;
-      {
+      if (tid < 128) {
         const int qr = i * 64 + (tid & 63);
         const float v = qr < S ? (tid < 64 ? lse_g[qr] * LOG2E : delta_g[qr]) : 0.f;
         stat[tid] = v;                                        // [0,64) lse*log2e, [64,128) delta
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      if (i > 0) { mbar_wait(pv_done, (i - 1) & 1); tc_fence_after(); }   // previous P^T / dS^T tiles consumed
+      uint32_t sv[32], dv[32];
+      tmem_ld32_issue(tmem_S + lane_off + wg * 32, sv);
+      tmem_ld32_issue(tmem_dP + lane_off + wg * 32, dv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);                       // TMEM buffer free for block i+1
       const bool full_blk = (kt * TILE + TILE <= S) && (i * 64 + 64 <= S);     // warp-uniform
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, sv);
-        tmem_ld32(tmem_dP + lane_off + c * 32, dv);
+      {
+        const int c = wg;
         uint32_t pk[16], dk[16];
         if (full_blk) {
 #pragma unroll
@@ -394,15 +415,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
             dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
           }
         }
+        if (i > 0) { mbar_wait(pv_done, (i - 1) & 1); tc_fence_after(); }   // previous tiles consumed
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           st_shared_v4(ptile_addr(sPt_addr, row_local, c * 4 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
           st_shared_v4(ptile_addr(sdSt_addr, row_local, c * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -468,7 +487,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   if (threadIdx.x == 0) {
     mbar_init(qdo_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
@@ -496,11 +515,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const uint64_t dO_ = make_sdesc_sw128(smem_u32(sdO), false, 0);
     const uint64_t dS_ = make_sdesc_sw128(smem_u32(sdS), false, 0);
     mbar_wait(qdo_full, 0);
-    for (int j = 0; j < nkb; ++j) {
+    auto issue_sdp = [&](int j) {
       const int st = j & 1;
       const uint64_t dKk = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), false, 0);
       const uint64_t dVk = make_sdesc_sw128(smem_u32(sV + st * HALF_BYTES), false, 0);
-      const uint64_t dKm = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), true, HALF_BYTES);
       mbar_wait(&kv_full[st], (j >> 1) & 1);
       if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
       tc_fence_after();
@@ -509,6 +527,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_dP, dO_ + ks * 2, dVk + ks * 2, idesc_s, ks > 0 ? 1u : 0u);
       tc_commit(s_full);
+    };
+    issue_sdp(0);
+    for (int j = 0; j < nkb; ++j) {
+      const int st = j & 1;
+      if (j + 1 < nkb) issue_sdp(j + 1);
+      const uint64_t dKm = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), true, HALF_BYTES);
       mbar_wait(p_full, j & 1);
       tc_fence_after();
 #pragma unroll
@@ -523,19 +547,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const bool row_ok = row < S;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t sdS_addr = smem_u32(sdS);
+    const int wg = (warp - 2) >> 2;
     const long long sidx = (static_cast<long long>(b) * H + h) * S + row;
     const float lse_r = row_ok ? lse[sidx] * LOG2E : 0.f;
     const float delta_r = row_ok ? delta[sidx] : 0.f;
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
+      uint32_t sv[32], dv[32];
+      tmem_ld32_issue(tmem_S + lane_off + wg * 32, sv);
+      tmem_ld32_issue(tmem_dP + lane_off + wg * 32, dv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
       const bool full_blk = j * 64 + 64 <= S;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, sv);
-        tmem_ld32(tmem_dP + lane_off + c * 32, dv);
+      {
+        const int c = wg;
         uint32_t dk[16];
         if (full_blk) {
 #pragma unroll
@@ -553,13 +581,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
             dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta_r), p1 * (__uint_as_float(dv[e + 1]) - delta_r));
           }
         }
+        if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           st_shared_v4(ptile_addr(sdS_addr, row_local, c * 4 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
