@@ -542,12 +542,12 @@ int launch_bwd(const bf16* qkv, const bf16* dout, const float* lse, const float*
 }  // namespace
 
 // tcgen05 kernels (hct_attention_sm100.cu)
-int hct_attn_tc_tiles(int S);
+int hct_attn_tc_tiles(int S, int tail_on_mma_sync);
 int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles, cudaStream_t st);
 int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
                          int H, int hd, cudaStream_t st);
-static bool g_attn_tc = true;
-extern "C" int hct_attention_set_tcgen05(int enable) { g_attn_tc = enable != 0; return HCT_OK; }
+static int g_attn_tc = 2;     // 0: mma.sync kernels only; 1: tcgen05, forward tail rows (S % 128 <= 32) on mma.sync; 2: tcgen05 for every tile
+extern "C" int hct_attention_set_tcgen05(int mode) { g_attn_tc = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return HCT_OK; }
 
 extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H, int32_t hd,
                                  hct_stream_t s) {
@@ -558,7 +558,7 @@ extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t
   int q_start = 0;
   if (g_attn_tc && (hd == 64 || hd == 48)) {
     // full 128-row query tiles on tcgen05; the few rows behind them (the cls token makes S = 128 k + 1) on mma.sync
-    const int n_tiles = hct_attn_tc_tiles(S);
+    const int n_tiles = hct_attn_tc_tiles(S, g_attn_tc == 1);
     int rc = hct_attention_fwd_tc(qkv, out, lse, B, S, H, hd, n_tiles, st);
     if (rc != HCT_OK) return rc;
     q_start = n_tiles * 128;

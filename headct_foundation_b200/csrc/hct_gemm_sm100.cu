@@ -290,9 +290,12 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp id and CTA rank are made warp-uniform by construction (shfl): the control warps below run their loops as whole
+  // converged warps and issue TMA / MMA under elect_one(), so descriptors stay in uniform registers and the four
+  // UTCHMMA of a stage issue back to back (a divergent `lane == 0` branch costs an ELECT loop + R2UR moves per MMA).
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int rank = CTAS == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int rank = CTAS == 2 ? __shfl_sync(0xffffffffu, static_cast<int>(cluster_ctarank()), 0) : 0;
   const int unit = blockIdx.x / CTAS, num_units = gridDim.x / CTAS;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int total_work = tiles * p.splits;
@@ -323,8 +326,9 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
+    const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
     for (int w = unit; w < total_work; w += num_units) {
       const int tile = w % tiles, split = w / tiles;
@@ -343,10 +347,11 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (rank == 0) mbar_expect_tx(&full_bar[stage], bytes);
         const uint32_t a_dst = smem_u32(sA + stage * A_STAGE_BYTES);
         const uint32_t b_dst = smem_u32(sB + stage * C::B_STAGE);
-        if (CTAS == 2) {
+        if (!leader) {
+        } else if (CTAS == 2) {
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], bytes);
           if (!p.a_mn) tma_load_2d_2sm(a_dst, &tmA, &full_bar[stage], kb * BK, my_m0);
           else for (int i = 0; i < a_chunks; ++i)
             tma_load_2d_2sm(a_dst + i * MN_CHUNK_BYTES, &tmA, &full_bar[stage], my_m0 + i * 64, kb * BK);
@@ -354,6 +359,7 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           else for (int i = 0; i < b_chunks; ++i)
             tma_load_2d_2sm(b_dst + i * MN_CHUNK_BYTES, &tmB, &full_bar[stage], my_n0 + i * 64, kb * BK);
         } else {
+          mbar_expect_tx(&full_bar[stage], bytes);
           if (!p.a_mn) tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * BK, my_m0);
           else for (int i = 0; i < a_chunks; ++i)
             tma_load_2d(a_dst + i * MN_CHUNK_BYTES, &tmA, &full_bar[stage], my_m0 + i * 64, kb * BK);
@@ -361,11 +367,13 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           else for (int i = 0; i < b_chunks; ++i)
             tma_load_2d(b_dst + i * MN_CHUNK_BYTES, &tmB, &full_bar[stage], my_n0 + i * 64, kb * BK);
         }
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader CTA only) =====================
+    const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     const uint32_t a_kstep = p.a_mn ? (16 * 128) >> 4 : 32 >> 4;   // descriptor units of 16 B per UMMA_K=16
@@ -381,15 +389,19 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         tc_fence_after();
         const uint64_t adesc = make_sdesc(smem_u32(sA + stage * A_STAGE_BYTES), p.a_mn);
         const uint64_t bdesc = make_sdesc(smem_u32(sB + stage * C::B_STAGE), p.b_mn);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          if (CTAS == 2) tc_mma_2sm(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          else tc_mma(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            if (CTAS == 2) tc_mma_2sm(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (CTAS == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
         }
-        if (CTAS == 2) tc_commit_2sm(&empty_bar[stage]); else tc_commit(&empty_bar[stage]);
+        __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (CTAS == 2) tc_commit_2sm(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]);
+      if (leader) { if (CTAS == 2) tc_commit_2sm(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]); }
+      __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= FIRST_EPI_WARP) {

@@ -52,6 +52,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a converged warp.  The control warps (TMA producer, MMA issuer) run their loops warp-uniformly and issue
+// the single-thread instructions under this predicate: descriptors then live in uniform registers and consecutive
+// UTCHMMA issue back to back.  (As a divergent `lane == 0` branch the compiler wrapped every MMA in an ELECT loop with
+// R2UR round trips -- about 100 cycles per MMA, which made the issuing thread, not the tensor core, the bottleneck.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {

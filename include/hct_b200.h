@@ -184,8 +184,9 @@ int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, const float* im
  * ------------------------------------------------------------------------------------------- */
 int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H,
                       int32_t hd, hct_stream_t stream);
-/* 1 (default): tcgen05/TMEM kernels for hd 64/48 (mma.sync only for the S %% 128 tail rows); 0: mma.sync only */
-int hct_attention_set_tcgen05(int enable);
+/* hd 64/48 kernel choice.  2 (default): tcgen05/TMEM kernels for every tile; 1: tcgen05, but the forward's
+ * S %% 128 <= 32 tail rows on the mma.sync kernel; 0: mma.sync kernels only */
+int hct_attention_set_tcgen05(int mode);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
 int hct_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                       void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd,

@@ -1,10 +1,12 @@
-"""Timing of the attention kernels at the MAE step shapes: python tools/attn_bench.py"""
+"""Timing of the attention kernels at the MAE step shapes: python tools/attn_bench.py [modes, e.g. 2,1,0]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from headct_foundation_b200._cabi import call, stream_ptr, lib
 
 dev = torch.device("cuda")
+MODES = [int(m) for m in (sys.argv[1] if len(sys.argv) > 1 else "2,1").split(",")]
+NAMES = {2: "tcgen05", 1: "tcgen05+mma.sync tail", 0: "mma.sync"}
 
 
 def timeit(fn, iters=5):
@@ -30,10 +32,11 @@ for name, (B, S, H, hd) in {"dec": (256, 513, 16, 48), "enc": (256, 129, 12, 64)
     delta = torch.empty(B, H, S, device=dev)
     st = stream_ptr(dev)
     fl_f = 4.0 * B * H * S * S * hd
-    for mode in (1, 0):
+    for mode in MODES:
         lib().hct_attention_set_tcgen05(mode)
         f = timeit(lambda: call("hct_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, hd, st))
         b = timeit(lambda: call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(),
                                 dqkv.data_ptr(), delta.data_ptr(), B, S, H, hd, st))
-        print(f"{name} B={B} S={S} H={H} hd={hd} {'tcgen05' if mode else 'mma.sync'}: fwd {f:.3f} ms ({fl_f / f / 1e9:.0f} TFLOP/s)  "
+        print(f"{name} B={B} S={S} H={H} hd={hd} {NAMES[mode]}: fwd {f:.3f} ms ({fl_f / f / 1e9:.0f} TFLOP/s)  "
               f"bwd {b:.3f} ms ({2.5 * fl_f / b / 1e9:.0f} TFLOP/s algorithmic)")
+lib().hct_attention_set_tcgen05(2)
