@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "lib", "libhct_b200.so")
 _lib: Optional[C.CDLL] = None
 
-EPI_BF16, EPI_GELU_BF16, EPI_RES_F32, EPI_POS_F32, EPI_DGELU_BF16, EPI_F32, EPI_ATOMIC_F32 = range(7)
+EPI_BF16, EPI_GELU_BF16, EPI_RES_F32, EPI_POS_F32, EPI_DGELU_BF16, EPI_F32, EPI_ATOMIC_F32, EPI_GELU_DERIV_BF16, EPI_MUL_BF16 = range(9)
 
 
 class GemmDesc(C.Structure):

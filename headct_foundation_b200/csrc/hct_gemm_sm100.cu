@@ -54,45 +54,55 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, bool mn_major) {
   return make_sdesc_sw128(saddr, mn_major, MN_CHUNK_BYTES);
 }
 
-// GELU(x) = x * Phi(x) with the normal CDF evaluated as a logistic of an odd degree-7 polynomial,
-//   Phi(x) ~= 1 / (1 + exp(-x (c0 + c1 x^2 + c2 x^4 + c3 x^6))),   |x| clamped to 6,
-// fitted (least squares on [-6, 6]) to erf-exact GELU: max |gelu error| 1.3e-5, max |gelu' error| 5.8e-5 -- an
-// order of magnitude below the bf16 rounding of the stored result, so the outputs are those of exact-erf GELU
-// (torch nn.GELU(approximate='none')) up to bf16 ties.  Cost: 9 FP32 ops + ex2 + rcp per element instead of
-// ~20 for erff-based code; the GELU epilogues were ALU-bound before (0.39-0.51 of tensor peak).
-// Coefficients below are pre-multiplied by -log2(e) so that the exponential is a bare ex2.
+// GELU(x) = x * Phi(x) with the normal CDF evaluated as a logistic of an odd degree-7 polynomial, written with tanh
+// so that it costs ONE special-function op:
+//   Phi(x) ~= 1 / (1 + exp(-x p(x^2))) = 0.5 + 0.5 tanh(0.5 x p(x^2)),   p(t) = c0 + c1 t + c2 t^2 + c3 t^3,  |x| clamped to 6,
+// p fitted (least squares on [-6, 6]) to erf-exact GELU: max |gelu error| 1.3e-5 with an exact tanh; tanh.approx
+// (relative error <= 2^-11) keeps it below 8.5e-4 absolute -- under the bf16 rounding of the stored activations, so
+// the outputs are those of exact-erf GELU (torch nn.GELU(approximate='none')) up to bf16 ties.
+// The derivative uses the closed form Phi(x) + x phi(x) with the same Phi and an ex2 for the density.
+// Cost: 8 FP32 ops + 1 MUFU (forward), 10 + 2 MUFU (derivative); the erff-based code needed ~20 / ~30 and made the
+// GELU epilogues ALU-bound (a 128 x 256 tile has 32768 elements against a 6144-cycle K = 768 main loop).
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
+__device__ __forceinline__ float tanh_approx(float x) {
   float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-constexpr float kG0 = -1.59534958f * 1.4426950408889634f, kG1 = -7.34984774e-02f * 1.4426950408889634f,
-                kG2 = 5.20865699e-04f * 1.4426950408889634f, kG3 = 1.64242936e-05f * 1.4426950408889634f;
-__device__ __forceinline__ float phi_cdf_fast(float x, float& x2_out) {
-  const float x2 = fminf(x * x, 36.0f);      // beyond |x| = 6 the argument keeps growing linearly: sigma saturates
-  float q = fmaf(kG3, x2, kG2);
-  q = fmaf(q, x2, kG1);
-  q = fmaf(q, x2, kG0);
+constexpr float kH0 = 0.5f * 1.59534958f, kH1 = 0.5f * 7.34984774e-02f, kH2 = 0.5f * -5.20865699e-04f,
+                kH3 = 0.5f * -1.64242936e-05f;
+__device__ __forceinline__ float tanh_half_arg(float x, float& x2_out) {   // tanh(0.5 x p(x^2))
+  const float x2 = fminf(x * x, 36.0f);      // beyond |x| = 6 the argument keeps growing linearly: tanh saturates
+  float q = fmaf(kH3, x2, kH2);
+  q = fmaf(q, x2, kH1);
+  q = fmaf(q, x2, kH0);
   x2_out = x2;
-  return rcp_approx(1.0f + ex2_approx(x * q));
+  return tanh_approx(x * q);
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float x2;
-  return x * phi_cdf_fast(x, x2);
+  const float t = tanh_half_arg(x, x2);
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);                      // x (0.5 + 0.5 t)
+}
+__device__ __forceinline__ float gelu_and_grad_fast(float x, float& grad) {   // both from one tanh
+  float x2;
+  const float t = tanh_half_arg(x, x2);
+  const float h = 0.5f * x;
+  const float pdf = ex2_approx(x2 * (-0.5f * 1.4426950408889634f));
+  grad = fmaf(x * 0.3989422804014327f, pdf, fmaf(0.5f, t, 0.5f));
+  return fmaf(h, t, h);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float x2;
-  const float s = phi_cdf_fast(x, x2);
-  // d/dx [x s(p(x))] = s + x s (1 - s) p'(x),  p'(x) = c0 + 3 c1 x^2 + 5 c2 x^4 + 7 c3 x^6  (natural-log units)
-  float pd = fmaf(7.0f * 1.64242936e-05f * -1.0f, x2, 5.0f * -5.20865699e-04f);
-  pd = fmaf(pd, x2, 3.0f * 7.34984774e-02f);
-  pd = fmaf(pd, x2, 1.59534958f);
-  return fmaf(x * s * (1.0f - s), pd, s);
+  const float t = tanh_half_arg(x, x2);
+  const float cdf = fmaf(0.5f, t, 0.5f);
+  const float pdf = ex2_approx(x2 * (-0.5f * 1.4426950408889634f));       // exp(-x^2 / 2); 1.5e-8 at the clamp
+  return fmaf(x * 0.3989422804014327f, pdf, cdf);                          // Phi(x) + x phi(x)
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -124,16 +134,98 @@ __device__ __forceinline__ void epilogue_stage(uint32_t stg, int lane, const uin
 }
 
 template <int EPI>
+struct EpiTraits {
+  static constexpr bool bf16_out = EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16 ||
+                                   EPI == HCT_EPI_GELU_DERIV_BF16 || EPI == HCT_EPI_MUL_BF16;
+  static constexpr bool uses_aux = EPI == HCT_EPI_DGELU_BF16 || EPI == HCT_EPI_MUL_BF16;   // bf16 multiplicand, no bias
+  static constexpr bool gelu_fwd = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16;
+};
+
+template <int EPI>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0) {
+  using T = EpiTraits<EPI>;
   // ---- phase 2: lane = (row sub-index, column group); rows handled in two groups of four to bound registers
   const int jj = lane & 7, rsub = lane >> 3;
   const int col = col0 + jj * 4;
   const bool col_ok = col < p.N;                       // N % 8 == 0 -> a group of 4 is all-in or all-out
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (EPI != HCT_EPI_DGELU_BF16 && EPI != HCT_EPI_ATOMIC_F32) {
+  if (!T::uses_aux && EPI != HCT_EPI_ATOMIC_F32) {
     if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
   }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+  // Interior units (all 32 rows and 32 columns inside the matrix, no row remapping) take a path without per-row
+  // predicates and with incremental row pointers: the general path below spends ~40 % of its instructions on
+  // 64-bit address arithmetic and reconvergence, which made the GELU epilogues (not the MMAs) set the tile period.
+  const bool interior = EPI != HCT_EPI_POS_F32 && p.rows_in <= 0 && row_base + 32 <= p.M && col0 + 32 <= p.N;
+  if (interior) {
+    const long long r0 = row_base + rsub;
+    const bool has_colsum = p.colsum != nullptr;
+    float4 extra[8];
+    uint2 aux[8];
+    if (EPI == HCT_EPI_RES_F32) {
+      const float* rp = p.res + r0 * p.ldres + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) extra[i] = *reinterpret_cast<const float4*>(rp + static_cast<long long>(i) * 4 * p.ldres);
+    }
+    if (T::uses_aux) {
+      const bf16* ap = p.aux + r0 * p.ldaux + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) aux[i] = *reinterpret_cast<const uint2*>(ap + static_cast<long long>(i) * 4 * p.ldaux);
+    }
+    if (T::bf16_out) {
+      bf16* op = reinterpret_cast<bf16*>(p.out) + r0 * p.ldo + col;
+      bf16* op2 = (T::gelu_fwd && p.out2 != nullptr) ? reinterpret_cast<bf16*>(p.out2) + r0 * p.ldo2 + col : nullptr;
+      const long long ostep = 4 * p.ldo, ostep2 = 4 * p.ldo2;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+        if (EPI == HCT_EPI_BF16) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
+        if (!T::uses_aux) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+        if (EPI == HCT_EPI_GELU_BF16) {
+          if (op2 != nullptr) {
+            uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(op2 + i * ostep2) = u;
+          }
+          v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
+        }
+        if (EPI == HCT_EPI_GELU_DERIV_BF16) {
+          float4 d;
+          v.x = gelu_and_grad_fast(v.x, d.x); v.y = gelu_and_grad_fast(v.y, d.y);
+          v.z = gelu_and_grad_fast(v.z, d.z); v.w = gelu_and_grad_fast(v.w, d.w);
+          uint2 u; u.x = pack_bf16x2(d.x, d.y); u.y = pack_bf16x2(d.z, d.w);
+          *reinterpret_cast<uint2*>(op2 + i * ostep2) = u;
+        }
+        if (EPI == HCT_EPI_DGELU_BF16) {
+          const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
+          v.x *= gelu_grad_fast(a0.x); v.y *= gelu_grad_fast(a0.y); v.z *= gelu_grad_fast(a1.x); v.w *= gelu_grad_fast(a1.y);
+        }
+        if (EPI == HCT_EPI_MUL_BF16) {
+          const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
+          v.x *= a0.x; v.y *= a0.y; v.z *= a1.x; v.w *= a1.y;
+        }
+        uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(op + i * ostep) = u;
+        if (has_colsum) {            // column sums of the values as the consumer will read them (bf16-rounded)
+          const float2 q0 = unpack_bf16x2(u.x), q1 = unpack_bf16x2(u.y);
+          csum.x += q0.x; csum.y += q0.y; csum.z += q1.x; csum.w += q1.y;
+        }
+      }
+    } else {
+      float* op = reinterpret_cast<float*>(p.out) + r0 * p.ldo + col;
+      const long long ostep = 4 * p.ldo;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+        if (EPI == HCT_EPI_F32 || EPI == HCT_EPI_ATOMIC_F32) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
+        if (EPI != HCT_EPI_ATOMIC_F32) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
+        if (EPI == HCT_EPI_RES_F32) { v.x += extra[i].x; v.y += extra[i].y; v.z += extra[i].z; v.w += extra[i].w; }
+        if (EPI == HCT_EPI_ATOMIC_F32) red_add_v4(op + i * ostep, v.x, v.y, v.z, v.w);
+        else *reinterpret_cast<float4*>(op + i * ostep) = v;
+      }
+    }
+  } else
 #pragma unroll
   for (int grp = 0; grp < 1; ++grp) {
     long long orow[8];
@@ -167,7 +259,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
         }
       }
     }
-    if (EPI == HCT_EPI_DGELU_BF16) {
+    if (T::uses_aux) {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         if (ok[i]) aux[i] = *reinterpret_cast<const uint2*>(p.aux + static_cast<long long>(row_base + (grp * 8 + i) * 4 + rsub) * p.ldaux + col);
@@ -181,7 +273,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
         v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
       }
       v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
-      if (EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) {
+      if (T::bf16_out) {
         if (EPI == HCT_EPI_GELU_BF16) {
           if (p.out2 != nullptr) {
             uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
@@ -189,9 +281,20 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
           }
           v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
         }
+        if (EPI == HCT_EPI_GELU_DERIV_BF16) {
+          float4 d;
+          v.x = gelu_and_grad_fast(v.x, d.x); v.y = gelu_and_grad_fast(v.y, d.y);
+          v.z = gelu_and_grad_fast(v.z, d.z); v.w = gelu_and_grad_fast(v.w, d.w);
+          uint2 u; u.x = pack_bf16x2(d.x, d.y); u.y = pack_bf16x2(d.z, d.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + orow[i] * p.ldo2 + col) = u;
+        }
         if (EPI == HCT_EPI_DGELU_BF16) {
           const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
           v.x *= gelu_grad_fast(a0.x); v.y *= gelu_grad_fast(a0.y); v.z *= gelu_grad_fast(a1.x); v.w *= gelu_grad_fast(a1.y);
+        }
+        if (EPI == HCT_EPI_MUL_BF16) {
+          const float2 a0 = unpack_bf16x2(aux[i].x), a1 = unpack_bf16x2(aux[i].y);
+          v.x *= a0.x; v.y *= a0.y; v.z *= a1.x; v.w *= a1.y;
         }
         uint2 u; u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
         *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + orow[i] * p.ldo + col) = u;
@@ -209,7 +312,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
       }
     }
   }
-  if ((EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_DGELU_BF16) && p.colsum != nullptr) {
+  if (T::bf16_out && p.colsum != nullptr) {
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
       csum.x += __shfl_xor_sync(0xffffffffu, csum.x, o); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, o);
@@ -413,7 +516,7 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int w = unit; w < total_work; w += num_units) {
       const int tile = w % tiles;
       const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * TILE_M + rank * BM;
-      if (EPI == HCT_EPI_RES_F32 || EPI == HCT_EPI_DGELU_BF16) {
+      if (EPI == HCT_EPI_RES_F32 || EpiTraits<EPI>::uses_aux) {
         // the residual / pre-activation tile this warp will stream in its epilogue: pull it into L2 while the
         // main loop of this tile is still running (one 128-byte line per lane and step)
         const int prow = m0 + q * 32 + lane;
@@ -545,6 +648,8 @@ int dispatch(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     case HCT_EPI_POS_F32: return launch<HCT_EPI_POS_F32, CTAS>(tmA, tmB, p, grid, st);
     case HCT_EPI_DGELU_BF16: return launch<HCT_EPI_DGELU_BF16, CTAS>(tmA, tmB, p, grid, st);
     case HCT_EPI_F32: return launch<HCT_EPI_F32, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_GELU_DERIV_BF16: return launch<HCT_EPI_GELU_DERIV_BF16, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_MUL_BF16: return launch<HCT_EPI_MUL_BF16, CTAS>(tmA, tmB, p, grid, st);
     default: return launch<HCT_EPI_ATOMIC_F32, CTAS>(tmA, tmB, p, grid, st);
   }
 }
@@ -569,7 +674,7 @@ extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
   HCT_REQUIRE((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->B) & 15) == 0,
               "hct_gemm_bf16: A/B must be 16-byte aligned");
   HCT_REQUIRE(d->out != nullptr && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "hct_gemm_bf16: out misaligned");
-  HCT_REQUIRE(d->epilogue >= 0 && d->epilogue <= HCT_EPI_ATOMIC_F32, "hct_gemm_bf16: bad epilogue %d", d->epilogue);
+  HCT_REQUIRE(d->epilogue >= 0 && d->epilogue <= HCT_EPI_MUL_BF16, "hct_gemm_bf16: bad epilogue %d", d->epilogue);
   const bool f32_out = d->epilogue == HCT_EPI_RES_F32 || d->epilogue == HCT_EPI_POS_F32 ||
                        d->epilogue == HCT_EPI_F32 || d->epilogue == HCT_EPI_ATOMIC_F32;
   HCT_REQUIRE(d->ldo % (f32_out ? 4 : 8) == 0, "hct_gemm_bf16: ldo=%lld breaks 16-byte row alignment", (long long)d->ldo);
@@ -578,10 +683,12 @@ extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
   if (d->epilogue == HCT_EPI_POS_F32)
     HCT_REQUIRE(d->pos != nullptr && d->ldpos % 4 == 0 && (d->pos_idx != nullptr || d->pos_period > 0),
                 "hct_gemm_bf16: POS epilogue needs pos and pos_idx/pos_period");
-  if (d->epilogue == HCT_EPI_DGELU_BF16)
-    HCT_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "hct_gemm_bf16: DGELU epilogue needs aux");
-  if (d->epilogue == HCT_EPI_GELU_BF16 && d->out2 != nullptr)
-    HCT_REQUIRE(d->ldo2 % 8 == 0, "hct_gemm_bf16: ldo2 misaligned");
+  if (d->epilogue == HCT_EPI_DGELU_BF16 || d->epilogue == HCT_EPI_MUL_BF16)
+    HCT_REQUIRE(d->aux != nullptr && d->ldaux % 8 == 0, "hct_gemm_bf16: DGELU / MUL epilogue needs aux");
+  if (d->epilogue == HCT_EPI_GELU_DERIV_BF16)
+    HCT_REQUIRE(d->out2 != nullptr, "hct_gemm_bf16: GELU_DERIV epilogue needs out2");
+  if ((d->epilogue == HCT_EPI_GELU_BF16 || d->epilogue == HCT_EPI_GELU_DERIV_BF16) && d->out2 != nullptr)
+    HCT_REQUIRE(d->ldo2 % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out2) & 15) == 0, "hct_gemm_bf16: out2 misaligned");
   HCT_REQUIRE(d->colsum == nullptr || !f32_out, "hct_gemm_bf16: colsum is only available with bf16-output epilogues");
   if (d->a_mn_major) HCT_REQUIRE(d->M % 8 == 0, "hct_gemm_bf16: MN-major A needs M %% 8 == 0");
   else HCT_REQUIRE(d->K % 8 == 0, "hct_gemm_bf16: K-major A needs K %% 8 == 0");

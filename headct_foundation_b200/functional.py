@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_POS_F32,
+from ._cabi import (EPI_ATOMIC_F32, EPI_BF16, EPI_DGELU_BF16, EPI_F32, EPI_GELU_BF16, EPI_GELU_DERIV_BF16, EPI_MUL_BF16, EPI_POS_F32,
                     EPI_RES_F32, GemmDesc, call, ptr, stream_ptr)
 
 BF16 = torch.bfloat16
@@ -200,8 +200,10 @@ class BlockFn(torch.autograd.Function):
         linear_fwd(att, proj_w, proj_b, epi=EPI_RES_F32, out=x2.view(M, D), res=x.view(M, D))
         h2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, eps, True, need_grad)
         F_ = fc1_w.shape[0]
+        # training: the fc1 epilogue also writes gelu'(pre-activation) (it shares the tanh with gelu itself), so the
+        # backward multiplies by it instead of re-deriving it from a saved pre-activation
         a = torch.empty((M, F_), dtype=BF16, device=dev) if need_grad else None
-        g = linear_fwd(h2.view(M, D), fc1_w, fc1_b, epi=EPI_GELU_BF16, out2=a)
+        g = linear_fwd(h2.view(M, D), fc1_w, fc1_b, epi=EPI_GELU_DERIV_BF16 if need_grad else EPI_GELU_BF16, out2=a)
         x3 = torch.empty_like(x)
         linear_fwd(g, fc2_w, fc2_b, epi=EPI_RES_F32, out=x3.view(M, D), res=x2.view(M, D))
         if need_grad:
@@ -229,7 +231,7 @@ class BlockFn(torch.autograd.Function):
         # ---- MLP branch
         dfc2_w = linear_wgrad(d3, g)
         dfc1_b = torch.zeros((a.shape[1],), dtype=F32, device=dev)
-        da = linear_dgrad(d3, fc2_w, epi=EPI_DGELU_BF16, aux=a, colsum=dfc1_b)          # [M, F] bf16 (+ column sums)
+        da = linear_dgrad(d3, fc2_w, epi=EPI_MUL_BF16, aux=a, colsum=dfc1_b)            # [M, F] bf16 (+ column sums)
         del d3
         dfc1_w = linear_wgrad(da, h2.view(M, D))
         dh2 = linear_dgrad(da, fc1_w)                                                   # [M, D] bf16

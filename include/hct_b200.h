@@ -54,7 +54,10 @@ enum hct_epilogue {
   HCT_EPI_POS_F32 = 3,    /* out_f32[remap(r)] = acc + bias + pos[pos_idx ? pos_idx[r] : r % pos_period] */
   HCT_EPI_DGELU_BF16 = 4, /* out_bf16 = acc * gelu_erf'(aux_bf16)                                */
   HCT_EPI_F32 = 5,        /* out_f32 = alpha*acc + bias                                          */
-  HCT_EPI_ATOMIC_F32 = 6  /* out_f32 += alpha*acc   (split-K reduction; out pre-zeroed by caller) */
+  HCT_EPI_ATOMIC_F32 = 6, /* out_f32 += alpha*acc   (split-K reduction; out pre-zeroed by caller) */
+  HCT_EPI_GELU_DERIV_BF16 = 7, /* t = acc + bias; out_bf16 = gelu_erf(t); out2_bf16 = gelu_erf'(t): the forward
+                                  saves the derivative, so that the backward of the activation is ...          */
+  HCT_EPI_MUL_BF16 = 8    /* ... out_bf16 = acc * aux_bf16  (no special-function work in the dgrad epilogue)   */
 };
 
 typedef struct hct_gemm_desc {
@@ -66,7 +69,7 @@ typedef struct hct_gemm_desc {
   void* out2; int64_t ldo2;
   const float* bias;                 /* [N] fp32 or NULL */
   const float* res; int64_t ldres;   /* fp32 residual */
-  const void* aux;  int64_t ldaux;   /* bf16 pre-activation (DGELU) */
+  const void* aux;  int64_t ldaux;   /* bf16 pre-activation (DGELU) or multiplicand (MUL) */
   const float* pos; int64_t ldpos;   /* fp32 position table */
   const int32_t* pos_idx;            /* per-row index into pos, or NULL */
   int32_t pos_period;

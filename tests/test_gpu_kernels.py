@@ -84,6 +84,24 @@ def test_gemm_epilogues(cuda, HF):
     a = aux.float().requires_grad_(True)
     torch.nn.functional.gelu(a).backward(acc)
     assert _rel(out.float(), a.grad) < 8e-3
+    # GELU + its derivative as the side output (training forward), then the multiplying dgrad epilogue + column sums
+    drv = torch.empty_like(out)
+    HF.gemm(A, B, M=M, N=N, K=K, lda=K, ldb=K, out=out, ldo=N, epi=HF.EPI_GELU_DERIV_BF16, bias=bias, out2=drv, ldo2=N)
+    t = (acc + bias).requires_grad_(True)
+    gl = torch.nn.functional.gelu(t)
+    gl.backward(torch.ones_like(gl))
+    assert _rel(out.float(), gl.detach()) < 8e-3
+    assert _rel(drv.float(), t.grad) < 8e-3
+    assert (out.float() - gl.detach()).abs().max() < 2e-2 and (drv.float() - t.grad).abs().max() < 1e-2
+    cs = torch.zeros(N, device=cuda)
+    HF.gemm(A, B, M=M, N=N, K=K, lda=K, ldb=K, out=out, ldo=N, epi=HF.EPI_MUL_BF16, aux=aux, ldaux=N, colsum=cs)
+    assert _rel(out.float(), acc * aux.float()) < 8e-3
+    assert _rel(cs, out.float().sum(0)) < 1e-4
+    # ragged edges (M, N not multiples of the 32-wide epilogue units) take the general epilogue path
+    Mr, Nr = 77, 40
+    o_r, d_r = torch.empty(Mr, Nr, device=cuda, dtype=torch.bfloat16), torch.empty(Mr, Nr, device=cuda, dtype=torch.bfloat16)
+    HF.gemm(A, B, M=Mr, N=Nr, K=K, lda=K, ldb=K, out=o_r, ldo=Nr, epi=HF.EPI_GELU_DERIV_BF16, bias=bias, out2=d_r, ldo2=Nr)
+    assert _rel(o_r.float(), gl.detach()[:Mr, :Nr]) < 8e-3 and _rel(d_r.float(), t.grad[:Mr, :Nr]) < 8e-3
     # fp32 store + position table with row remap (3 prefix rows per group of 64)
     pos = torch.randn(64, N, device=cuda, generator=g)
     groups = M // 64

@@ -26,7 +26,7 @@ def fwd(M, N, K, epi):
     bias = torch.randn(N, device=dev)
     f32 = epi in (HF.EPI_RES_F32, HF.EPI_F32)
     out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-    out2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if epi == HF.EPI_GELU_BF16 else None
+    out2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if epi in (HF.EPI_GELU_BF16, HF.EPI_GELU_DERIV_BF16) else None
     res = torch.randn(M, N, device=dev) if epi == HF.EPI_RES_F32 else None
     return lambda: HF.gemm(A, B, M=M, N=N, K=K, lda=K, ldb=K, out=out, ldo=N, epi=epi, bias=bias, out2=out2, ldo2=N,
                            res=res, ldres=N)
@@ -35,8 +35,8 @@ def fwd(M, N, K, epi):
 def dgrad(M, N, K, epi):   # dX[M,N] = dY[M,K] @ W[K,N]
     dY = torch.randn(M, K, device=dev).bfloat16(); W = torch.randn(K, N, device=dev).bfloat16()
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    aux = torch.randn(M, N, device=dev).bfloat16() if epi == HF.EPI_DGELU_BF16 else None
-    cs = torch.zeros(N, device=dev) if epi == HF.EPI_DGELU_BF16 else None
+    aux = torch.randn(M, N, device=dev).bfloat16() if epi in (HF.EPI_DGELU_BF16, HF.EPI_MUL_BF16) else None
+    cs = torch.zeros(N, device=dev) if epi in (HF.EPI_DGELU_BF16, HF.EPI_MUL_BF16) else None
     return lambda: HF.gemm(dY, W, M=M, N=N, K=K, lda=K, ldb=N, b_mn=True, out=out, ldo=N, epi=epi, aux=aux, ldaux=N, colsum=cs)
 
 
@@ -50,9 +50,9 @@ cases = []
 for tag, M in (("dec", 131328), ("enc", 33024)):
     cases += [(f"{tag} fwd qkv", fwd(M, 2304, 768, HF.EPI_BF16), M, 2304, 768),
               (f"{tag} fwd proj+res", fwd(M, 768, 768, HF.EPI_RES_F32), M, 768, 768),
-              (f"{tag} fwd fc1+gelu", fwd(M, 3072, 768, HF.EPI_GELU_BF16), M, 3072, 768),
+              (f"{tag} fwd fc1+gelu+gelu'", fwd(M, 3072, 768, HF.EPI_GELU_DERIV_BF16), M, 3072, 768),
               (f"{tag} fwd fc2+res", fwd(M, 768, 3072, HF.EPI_RES_F32), M, 768, 3072),
-              (f"{tag} dgrad da(dgelu)", dgrad(M, 3072, 768, HF.EPI_DGELU_BF16), M, 3072, 768),
+              (f"{tag} dgrad da(*gelu')", dgrad(M, 3072, 768, HF.EPI_MUL_BF16), M, 3072, 768),
               (f"{tag} dgrad dh2", dgrad(M, 768, 3072, HF.EPI_BF16), M, 768, 3072),
               (f"{tag} dgrad datt", dgrad(M, 768, 768, HF.EPI_BF16), M, 768, 768),
               (f"{tag} dgrad dh1", dgrad(M, 768, 2304, HF.EPI_BF16), M, 768, 2304),
