@@ -308,24 +308,38 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // =====================================================================================================
-// Backward.  Two kernels, both two CTAs per SM, TMEM budget 256 columns each; no atomics, deterministic.
-//   dK/dV kernel: CTA = (batch, head, 128 keys); rows (TMEM lanes) are KEYS.  Per 64-query block:
-//        S^T = K Q^T, dP^T = V dO^T   -> TMEM (2 x 64 cols)
-//        P^T = exp2(S^T*c - lse[q]),  dS^T = P^T (dP^T - delta[q])   (softmax threads, column-indexed stats in smem)
-//        dV += P^T dO,  dK += dS^T Q  (A = bf16 tiles written by the softmax threads, B = the TMA-loaded dO / Q
-//                                     tiles read MN-major, i.e. exactly as stored)
-//   dQ kernel:   CTA = (batch, head, 128 queries); rows are QUERIES.  Per 64-key block:
-//        S = Q K^T, dP = dO V^T -> TMEM;  dS = P (dP - delta[row]);  dQ += dS K  (K tile read MN-major)
+// Backward.  Two kernels, both two CTAs per SM with a 256-column TMEM budget each; no atomics, deterministic.
+// The bf16 operands the softmax threads produce (P^T, dS^T, dS) never touch shared memory: they are written to
+// tensor memory with tcgen05.st and consumed as the A operand of tcgen05.mma (A-from-TMEM form), which removes the
+// st.shared + proxy fence + 4 KiB-per-MMA shared-memory operand reads of the earlier version and frees the room for
+// a 4-deep TMA ring (the 2-deep ring had the TMA round trip on the critical path, see tools/attn_dbg.py).
+//
+//   dK/dV kernel: CTA = (batch, head, 128 keys); rows (TMEM lanes) are KEYS.  Per 64-query block i:
+//        S^T = K Q_i^T, dP^T = V dO_i^T                      -> TMEM cols [0,64) / [64,128)
+//        P^T = exp2(S^T c - lse[q]),  dS^T = P^T (dP^T - delta[q])   written IN PLACE over the fp32 columns each
+//                                                             softmax warp has just read (bf16 pairs, 16 columns)
+//        dV += P^T dO_i,  dK += dS^T Q_i                      A from TMEM, B = the TMA-loaded dO / Q tiles read MN-major
+//      The MMA warp issues [dV/dK(i), S^T/dP^T(i+1)] back to back: the tensor core executes in order, so block i+1
+//      overwrites the S^T / dP^T columns only after block i's operands have been consumed.
+//   dQ kernel:   CTA = (batch, head, 128 queries); rows are QUERIES.  Per 64-key block j:
+//        S = Q K_j^T, dP = dO V_j^T -> TMEM; dS = P (dP - delta[row]) -> one of two TMEM operand buffers;
+//        dQ += dS K_j (K tile read MN-major).  S/dP of block j+1 are issued as soon as block j sits in registers.
 // =====================================================================================================
 constexpr int HALF_BYTES = 64 * 128;       // 64 rows x 64 bf16
-constexpr int BWD_THREADS = 320;        // 2 x 4 softmax warps (each group owns 32 of a block's 64 columns), TMA warp, MMA warp
+constexpr int BWD_THREADS = 320;           // 2 x 4 softmax warps (each group owns 32 of a block's 64 columns), TMA warp, MMA warp
 constexpr int BWD_PRODUCER_WARP = 8, BWD_MMA_WARP = 9;
 constexpr int BWD_TMEM_COLS = 256;
-constexpr int DKDV_SMEM = 2 * TILE_BYTES + 4 * HALF_BYTES + 2 * TILE_BYTES + 1024 + 1024 + 128;
-constexpr int DQ_SMEM = 2 * TILE_BYTES + 4 * HALF_BYTES + TILE_BYTES + 1024 + 128;
+constexpr int BWD_STAGES = 4;              // TMA ring depth for the streamed 64-row tiles
+constexpr int BWD_SMEM = 2 * TILE_BYTES + BWD_STAGES * 2 * HALF_BYTES + 8 * 512 + 1024 + 256;   // resident tiles, ring, per-warp stats, align, barriers
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// A operand from tensor memory: D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 template <int HD>
@@ -338,15 +352,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sK = smem;                               // [128 keys][64]
   uint8_t* sV = smem + TILE_BYTES;
-  uint8_t* sQ = smem + 2 * TILE_BYTES;              // 2 stages x [64 queries][64]
-  uint8_t* sdO = sQ + 2 * HALF_BYTES;               // 2 stages
-  uint8_t* sPt = sdO + 2 * HALF_BYTES;              // [128 keys][64 queries] bf16
-  uint8_t* sdSt = sPt + TILE_BYTES;
-  float* sStat = reinterpret_cast<float*>(sdSt + TILE_BYTES);   // [2 stages][lse 64 | delta 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 1024);
-  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[2]*/, *qdo_empty = bars + 3 /*[2]*/, *s_full = bars + 5,
-           *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sQ = smem + 2 * TILE_BYTES;              // BWD_STAGES x [64 queries][64]
+  uint8_t* sdO = sQ + BWD_STAGES * HALF_BYTES;      // BWD_STAGES x [64 queries][64]
+  float* sStat = reinterpret_cast<float*>(sdO + BWD_STAGES * HALF_BYTES);   // [8 warps][2 buffers][lse 32 | delta 32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 8 * 512);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[4]*/, *qdo_empty = bars + 5 /*[4]*/, *s_full = bars + 9,
+           *p_full = bars + 10, *done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
@@ -357,8 +369,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(pv_done, 1);
+    for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
@@ -368,7 +380,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_dV = tmem_base + 128, tmem_dK = tmem_base + 192;
   long long* trace = (g_trace != nullptr && kt == 1 && h == 3 && b == gridDim.z / 2) ? g_trace : nullptr;
-  // trace layout: [role 0 producer | 1 mma | 2 softmax warp 2 lane 0][block i][8 events]
+  // trace layout: [role 0 producer | 1 mma | 2 softmax warp 0 lane 0][block i][8 events]
 
   if (warp == BWD_PRODUCER_WARP) {
     // ===================== TMA producer =====================
@@ -379,9 +391,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       tma_load_2d(smem_u32(sV), &tmQKV128, kv_full, 2 * D + h * HD, b * S + kt * TILE);
     }
     for (int i = 0; i < nqb; ++i) {
-      const int st = i & 1;
+      const int st = i % BWD_STAGES;
       TRACE(0 * 256 + i * 8 + 0);
-      mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1u);
+      mbar_wait(&qdo_empty[st], ((i / BWD_STAGES) & 1) ^ 1u);
       TRACE(0 * 256 + i * 8 + 1);
       if (leader) {
         mbar_expect_tx(&qdo_full[st], 2 * HALF_BYTES);
@@ -399,187 +411,163 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
     const uint64_t dK_ = make_sdesc_sw128(smem_u32(sK), false, 0);
     const uint64_t dV_ = make_sdesc_sw128(smem_u32(sV), false, 0);
-    const uint64_t dPt = make_sdesc_sw128(smem_u32(sPt), false, 0);
-    const uint64_t dSt = make_sdesc_sw128(smem_u32(sdSt), false, 0);
     mbar_wait(kv_full, 0);
     auto issue_sdp = [&](int i) {          // S^T = K Q_i^T and dP^T = V dO_i^T into TMEM
-      const int st = i & 1;
+      const int st = i % BWD_STAGES;
       TRACE(1 * 256 + i * 8 + 0);
-      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      mbar_wait(&qdo_full[st], (i / BWD_STAGES) & 1);
       TRACE(1 * 256 + i * 8 + 1);
-      if (i > 0) mbar_wait(s_empty, (i - 1) & 1);
-      TRACE(1 * 256 + i * 8 + 2);
       tc_fence_after();
       if (leader) {
         const uint32_t id = (i == nqb - 1 && tail16) ? idesc_s16 : idesc_s;
         const uint64_t dQk = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), false, 0);
         const uint64_t dOk = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), false, 0);
-        // the two accumulate chains are interleaved so that consecutive MMAs are independent
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
+        for (int ks = 0; ks < HD / 16; ++ks) {      // the two accumulate chains interleaved: consecutive MMAs independent
           tc_mma(tmem_S, dK_ + ks * 2, dQk + ks * 2, id, ks > 0 ? 1u : 0u);
           tc_mma(tmem_dP, dV_ + ks * 2, dOk + ks * 2, id, ks > 0 ? 1u : 0u);
         }
         tc_commit(s_full);
       }
       __syncwarp();
-      TRACE(1 * 256 + i * 8 + 3);
+      TRACE(1 * 256 + i * 8 + 2);
     };
     issue_sdp(0);
     for (int i = 0; i < nqb; ++i) {
-      const int st = i & 1;
-      // run ahead: block i+1's S^T / dP^T are computed while the softmax threads work on block i (they release the
-      // TMEM buffer as soon as they hold block i in registers)
-      if (i + 1 < nqb) issue_sdp(i + 1);
+      const int st = i % BWD_STAGES;
+      TRACE(1 * 256 + i * 8 + 3);
+      mbar_wait(p_full, i & 1);                       // P^T / dS^T of block i sit in TMEM (and every warp has read S^T / dP^T)
       TRACE(1 * 256 + i * 8 + 4);
-      mbar_wait(p_full, i & 1);
-      TRACE(1 * 256 + i * 8 + 5);
       tc_fence_after();
       if (leader) {
         const uint64_t dQm = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), true, HALF_BYTES);
         const uint64_t dOm = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), true, HALF_BYTES);
         const uint32_t acc = i > 0 ? 1u : 0u;
+        // k-step ks covers queries [16 ks, 16 ks + 16): packed by warp group ks / 2 at column 32 (ks / 2) + 8 (ks % 2)
         if (i == nqb - 1 && tail16) {
-          tc_mma(tmem_dV, dPt, dOm, idesc_g, acc);
-          tc_mma(tmem_dK, dSt, dQm, idesc_g, acc);
+          tc_mma_ts(tmem_dV, tmem_S, dOm, idesc_g, acc);
+          tc_mma_ts(tmem_dK, tmem_dP, dQm, idesc_g, acc);
         } else {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            tc_mma(tmem_dV, dPt + ks * 2, dOm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
-            tc_mma(tmem_dK, dSt + ks * 2, dQm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+            tc_mma_ts(tmem_dV, tmem_S + (ks >> 1) * 32 + (ks & 1) * 8, dOm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+            tc_mma_ts(tmem_dK, tmem_dP + (ks >> 1) * 32 + (ks & 1) * 8, dQm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
           }
         }
-        tc_commit(pv_done);
         tc_commit(&qdo_empty[st]);
+        if (i == nqb - 1) tc_commit(done);
       }
       __syncwarp();
-      TRACE(1 * 256 + i * 8 + 6);
+      TRACE(1 * 256 + i * 8 + 5);
+      if (i + 1 < nqb) issue_sdp(i + 1);
     }
   } else if (warp < 8) {
     // ===================== softmax-backward threads: one KEY row per thread =====================
     const int q = warp & 3;
-    const int row_local = q * 32 + lane;
-    const int kvrow = kt * TILE + row_local;
+    const int kvrow = kt * TILE + q * 32 + lane;
     const bool row_ok = kvrow < S;
     const bool warp_active = kt * TILE + q * 32 < S;          // warps without a valid key row only keep the barriers moving
-    const int tid = threadIdx.x;                              // 0..255 within the softmax warps
-    const int wg = warp >> 2;                           // which 32-column half of each block this warp owns
+    const int wg = warp >> 2;                                 // which 32-column half of each block this warp owns
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sPt_addr = smem_u32(sPt), sdSt_addr = smem_u32(sdSt);
     const float* lse_g = lse + (static_cast<long long>(b) * H + h) * S;
     const float* delta_g = delta + (static_cast<long long>(b) * H + h) * S;
-    // per-query statistics of block i: [0,64) lse*log2e, [64,128) delta; loaded one block ahead (global-load latency
-    // stays off the critical path), double-buffered in shared memory
-    auto load_stat = [&](int i) -> float {
-      const int qr = i * 64 + (tid & 63);
-      return qr < S ? (tid < 64 ? lse_g[qr] : delta_g[qr]) : 0.f;    // scaled by log2(e) where it is stored
-    };
-    float stat_next = 0.f;
-    if (tid < 128) sStat[tid] = load_stat(0) * (tid < 64 ? LOG2E : 1.0f);
+    // per-query statistics of this warp's 32 columns: lse*log2e | delta, loaded one block ahead (the global-load
+    // latency stays off the critical path) into a private, double-buffered shared-memory slot -- no CTA-wide barrier
+    float* wstat = sStat + warp * 128;
+    auto load_lse = [&](int i) { const int qr = i * 64 + wg * 32 + lane; return qr < S ? lse_g[qr] : 0.f; };
+    auto load_delta = [&](int i) { const int qr = i * 64 + wg * 32 + lane; return qr < S ? delta_g[qr] : 0.f; };
+    float ls_n = load_lse(0), dl_n = load_delta(0);
     for (int i = 0; i < nqb; ++i) {
-      const float* stat = sStat + (i & 1) * 128;
-      if (tid < 128 && i + 1 < nqb) stat_next = load_stat(i + 1);
       long long* tr = (warp == 0 && lane == 0) ? trace : nullptr;
+      float* stat = wstat + (i & 1) * 64;
+      stat[lane] = ls_n * LOG2E;
+      stat[32 + lane] = dl_n;
+      __syncwarp();
+      if (i + 1 < nqb) { ls_n = load_lse(i + 1); dl_n = load_delta(i + 1); }
       if (tr) tr[2 * 256 + i * 8 + 0] = clock64();
-      named_bar_sync(1, 256);                                  // stat[i & 1] (written during block i-1) is visible
-      if (tr) tr[2 * 256 + i * 8 + 1] = clock64();
       mbar_wait(s_full, i & 1);
-      if (tr) tr[2 * 256 + i * 8 + 2] = clock64();
+      if (tr) tr[2 * 256 + i * 8 + 1] = clock64();
       tc_fence_after();
       const int ncol = min(64, S - i * 64);                    // valid query columns in this block
       const bool t16 = (i == nqb - 1) && tail16;
-      const bool works = warp_active && !(t16 && wg == 1);
-      uint32_t pk[16], dk[16];
-      if (!works) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);
-      } else if (t16) {
-        uint32_t sv[16], dv[16];
-        tmem_ld16(tmem_S + lane_off, sv);
-        tmem_ld16(tmem_dP + lane_off, dv);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);
+      if (warp_active && !(t16 && wg == 1)) {
+        uint32_t pk[16], dk[16];
+        if (t16) {
+          uint32_t sv[16], dv[16];
+          tmem_ld16(tmem_S + lane_off, sv);
+          tmem_ld16(tmem_dP + lane_off, dv);
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          const float2 ls = *reinterpret_cast<const float2*>(stat + e);
-          const float2 dl = *reinterpret_cast<const float2*>(stat + 64 + e);
-          const float p0 = e < ncol ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x)) : 0.f;
-          const float p1 = e + 1 < ncol ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y)) : 0.f;
-          pk[e >> 1] = pack_bf16x2(p0, p1);
-          dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
-        }
-      } else {
-        uint32_t sv[32], dv[32];
-        tmem_ld32_issue(tmem_S + lane_off + wg * 32, sv);
-        tmem_ld32_issue(tmem_dP + lane_off + wg * 32, dv);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);                       // TMEM buffer free for block i+1
-        const int lim = ncol - wg * 32;                          // valid query columns in this warp's chunk
-        if (lim < 32) {
+          for (int e = 0; e < 16; e += 2) {
+            const float2 ls = *reinterpret_cast<const float2*>(stat + e);
+            const float2 dl = *reinterpret_cast<const float2*>(stat + 32 + e);
+            const float p0 = e < ncol ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x)) : 0.f;
+            const float p1 = e + 1 < ncol ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y)) : 0.f;
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+          }
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (e >= lim) sv[e] = 0xff800000u;                   // exp2(-inf) = 0: P and dS vanish outside the problem
-        }
+          for (int e = 8; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
+        } else {
+          uint32_t sv[32], dv[32];
+          tmem_ld32_issue(tmem_S + lane_off + wg * 32, sv);
+          tmem_ld32_issue(tmem_dP + lane_off + wg * 32, dv);
+          tmem_ld_wait();
+          const int lim = ncol - wg * 32;                          // valid query columns in this warp's chunk
+          if (lim < 32) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          const float4 ls = *reinterpret_cast<const float4*>(stat + wg * 32 + e);
-          const float4 dl = *reinterpret_cast<const float4*>(stat + 64 + wg * 32 + e);
-          const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x));
-          const float p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y));
-          const float p2 = ex2f(fmaf(__uint_as_float(sv[e + 2]), sl2, -ls.z));
-          const float p3 = ex2f(fmaf(__uint_as_float(sv[e + 3]), sl2, -ls.w));
-          pk[e >> 1] = pack_bf16x2(p0, p1);
-          pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-          dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
-          dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) - dl.z), p3 * (__uint_as_float(dv[e + 3]) - dl.w));
-        }
-      }
-      if (tid < 128 && i + 1 < nqb) sStat[((i + 1) & 1) * 128 + tid] = stat_next * (tid < 64 ? LOG2E : 1.0f);
-      if (tr) tr[2 * 256 + i * 8 + 3] = clock64();
-      if (i > 0) { mbar_wait(pv_done, (i - 1) & 1); tc_fence_after(); }   // previous P^T / dS^T tiles consumed
-      if (tr) tr[2 * 256 + i * 8 + 4] = clock64();
-      if (works) {
-        const int ng = t16 ? 2 : 4, c0 = t16 ? 0 : wg * 4;
+            for (int e = 0; e < 32; ++e)
+              if (e >= lim) sv[e] = 0xff800000u;                   // exp2(-inf) = 0: P and dS vanish outside the problem
+          }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < ng) {
-            st_shared_v4(ptile_addr(sPt_addr, row_local, c0 + g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            st_shared_v4(ptile_addr(sdSt_addr, row_local, c0 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+          for (int e = 0; e < 32; e += 4) {
+            const float4 ls = *reinterpret_cast<const float4*>(stat + e);
+            const float4 dl = *reinterpret_cast<const float4*>(stat + 32 + e);
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y));
+            const float p2 = ex2f(fmaf(__uint_as_float(sv[e + 2]), sl2, -ls.z));
+            const float p3 = ex2f(fmaf(__uint_as_float(sv[e + 3]), sl2, -ls.w));
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+            dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) - dl.z), p3 * (__uint_as_float(dv[e + 3]) - dl.w));
           }
         }
-        fence_proxy_async_smem();
+        if (tr) tr[2 * 256 + i * 8 + 2] = clock64();
+        // in place: this thread's own lanes, inside the fp32 columns it has just read
+        tmem_st16(tmem_S + lane_off + wg * 32, pk);
+        tmem_st16(tmem_dP + lane_off + wg * 32, dk);
+        tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      if (tr) tr[2 * 256 + i * 8 + 5] = clock64();
+      if (tr) tr[2 * 256 + i * 8 + 3] = clock64();
     }
     // ---- epilogue: dV, dK rows
-    mbar_wait(pv_done, (nqb - 1) & 1);
+    mbar_wait(done, 0);
     tc_fence_after();
     bf16* dkrow = dqkv + (static_cast<long long>(b) * S + kvrow) * (3LL * D) + D + h * HD;
     bf16* dvrow = dkrow + D;
+    if (warp_active) {                       // both warp groups cover the same 128 rows: one writes dK, the other dV
+      {
+        const int which = wg;
+        const uint32_t src = which == 0 ? tmem_dK : tmem_dV;
+        bf16* dst = which == 0 ? dkrow : dvrow;
+        const float sc = which == 0 ? scale : 1.0f;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t src = which == 0 ? tmem_dK : tmem_dV;
-      bf16* dst = which == 0 ? dkrow : dvrow;
-      const float sc = which == 0 ? scale : 1.0f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < HD; c0 += 16) {
-        uint32_t o[16];
-        tmem_ld16(src + lane_off + c0, o);
-        if (row_ok) {
+        for (int c0 = 0; c0 < HD; c0 += 16) {
+          uint32_t o[16];
+          tmem_ld16(src + lane_off + c0, o);
+          if (row_ok) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * sc, __uint_as_float(o[8 * g + 1]) * sc);
-            u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * sc, __uint_as_float(o[8 * g + 3]) * sc);
-            u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * sc, __uint_as_float(o[8 * g + 5]) * sc);
-            u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * sc, __uint_as_float(o[8 * g + 7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c0 + 8 * g) = u;
+            for (int g = 0; g < 2; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * sc, __uint_as_float(o[8 * g + 1]) * sc);
+              u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * sc, __uint_as_float(o[8 * g + 3]) * sc);
+              u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * sc, __uint_as_float(o[8 * g + 5]) * sc);
+              u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * sc, __uint_as_float(o[8 * g + 7]) * sc);
+              *reinterpret_cast<uint4*>(dst + c0 + 8 * g) = u;
+            }
           }
         }
       }
@@ -600,13 +588,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;                               // [128 queries][64]
   uint8_t* sdO = smem + TILE_BYTES;
-  uint8_t* sK = smem + 2 * TILE_BYTES;              // 2 stages x [64 keys][64]
-  uint8_t* sV = sK + 2 * HALF_BYTES;
-  uint8_t* sdS = sV + 2 * HALF_BYTES;               // [128 queries][64 keys] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + TILE_BYTES);
-  uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[2]*/, *kv_empty = bars + 3 /*[2]*/, *s_full = bars + 5,
-           *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sK = smem + 2 * TILE_BYTES;              // BWD_STAGES x [64 keys][64]
+  uint8_t* sV = sK + BWD_STAGES * HALF_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + BWD_STAGES * HALF_BYTES + 8 * 512);
+  uint64_t *qdo_full = bars, *kv_full = bars + 1 /*[4]*/, *kv_empty = bars + 5 /*[4]*/, *s_full = bars + 9,
+           *s_empty = bars + 10, *p_full = bars + 11, *ds_free = bars + 12 /*[2]*/, *done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
@@ -617,8 +604,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
 
   if (threadIdx.x == 0) {
     mbar_init(qdo_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8); mbar_init(pv_done, 1);
+    for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 8); mbar_init(p_full, 8);
+    mbar_init(&ds_free[0], 1); mbar_init(&ds_free[1], 1); mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
@@ -626,7 +614,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_dQ = tmem_base + 128;
+  // S: [0,64)  dP: [64,128)  dQ: [128,192)  dS operand buffers (bf16 pairs, 32 columns each): [192,224), [224,256)
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_dQ = tmem_base + 128, tmem_dS = tmem_base + 192;
 
   if (warp == BWD_PRODUCER_WARP) {
     const bool leader = elect_one();
@@ -636,8 +625,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       tma_load_2d(smem_u32(sdO), &tmDO128, qdo_full, h * HD, b * S + qt * TILE);
     }
     for (int j = 0; j < nkb; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1u);
+      const int st = j % BWD_STAGES;
+      mbar_wait(&kv_empty[st], ((j / BWD_STAGES) & 1) ^ 1u);
       if (leader) {
         mbar_expect_tx(&kv_full[st], 2 * HALF_BYTES);
         tma_load_2d(smem_u32(sK + st * HALF_BYTES), &tmQKV64, &kv_full[st], D + h * HD, b * S + j * 64);
@@ -652,11 +641,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
     const uint64_t dQ_ = make_sdesc_sw128(smem_u32(sQ), false, 0);
     const uint64_t dO_ = make_sdesc_sw128(smem_u32(sdO), false, 0);
-    const uint64_t dS_ = make_sdesc_sw128(smem_u32(sdS), false, 0);
     mbar_wait(qdo_full, 0);
     auto issue_sdp = [&](int j) {
-      const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1);
+      const int st = j % BWD_STAGES;
+      mbar_wait(&kv_full[st], (j / BWD_STAGES) & 1);
       if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
       tc_fence_after();
       if (leader) {
@@ -674,32 +662,32 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     };
     issue_sdp(0);
     for (int j = 0; j < nkb; ++j) {
-      const int st = j & 1;
-      if (j + 1 < nkb) issue_sdp(j + 1);
+      const int st = j % BWD_STAGES;
+      if (j + 1 < nkb) issue_sdp(j + 1);            // runs underneath the softmax threads' work on block j
       mbar_wait(p_full, j & 1);
       tc_fence_after();
       if (leader) {
         const uint64_t dKm = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), true, HALF_BYTES);
+        const uint32_t a = tmem_dS + (j & 1) * 32;
         const uint32_t acc = j > 0 ? 1u : 0u;
         if (j == nkb - 1 && tail16) {
-          tc_mma(tmem_dQ, dS_, dKm, idesc_g, acc);
+          tc_mma_ts(tmem_dQ, a, dKm, idesc_g, acc);
         } else {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) tc_mma(tmem_dQ, dS_ + ks * 2, dKm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+          for (int ks = 0; ks < 4; ++ks) tc_mma_ts(tmem_dQ, a + ks * 8, dKm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
         }
-        tc_commit(pv_done);
+        tc_commit(&ds_free[j & 1]);
         tc_commit(&kv_empty[st]);
+        if (j == nkb - 1) tc_commit(done);
       }
       __syncwarp();
     }
   } else if (warp < 8) {
     const int q = warp & 3;
-    const int row_local = q * 32 + lane;
-    const int row = qt * TILE + row_local;
+    const int row = qt * TILE + q * 32 + lane;
     const bool row_ok = row < S;
     const bool warp_active = qt * TILE + q * 32 < S;          // warps without a valid query row only keep the barriers moving
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sdS_addr = smem_u32(sdS);
     const int wg = warp >> 2;
     const long long sidx = (static_cast<long long>(b) * H + h) * S + row;
     const float lse_r = row_ok ? lse[sidx] * LOG2E : 0.f;
@@ -727,6 +715,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           const float p1 = e + 1 < ncol ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -lse_r)) : 0.f;
           dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta_r), p1 * (__uint_as_float(dv[e + 1]) - delta_r));
         }
+#pragma unroll
+        for (int e = 8; e < 16; ++e) dk[e] = 0u;
       } else {
         uint32_t sv[32], dv[32];
         tmem_ld32_issue(tmem_S + lane_off + wg * 32, sv);
@@ -734,7 +724,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);
+        if (lane == 0) mbar_arrive(s_empty);                   // S / dP are in registers: block j+1 may overwrite them
         const int lim = ncol - wg * 32;
         if (lim < 32) {
 #pragma unroll
@@ -748,35 +738,36 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta_r), p1 * (__uint_as_float(dv[e + 1]) - delta_r));
         }
       }
-      if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
+      // operand buffer j & 1 is free once the dQ MMAs of block j - 2 have retired
+      if (j >= 2) { mbar_wait(&ds_free[j & 1], ((j >> 1) - 1) & 1); tc_fence_after(); }
       if (works) {
-        const int ng = t16 ? 2 : 4, c0 = t16 ? 0 : wg * 4;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (g < ng)
-            st_shared_v4(ptile_addr(sdS_addr, row_local, c0 + g), dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
-        fence_proxy_async_smem();
+        tmem_st16(tmem_dS + (j & 1) * 32 + lane_off + wg * 16, dk);
+        tmem_st_wait();
       }
+      // a warp with nothing to compute could otherwise run two blocks ahead and arrive twice in one phase
+      if (j > 0) mbar_wait(p_full, (j - 1) & 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
-    mbar_wait(pv_done, (nkb - 1) & 1);
+    mbar_wait(done, 0);
     tc_fence_after();
     bf16* dqrow = dqkv + (static_cast<long long>(b) * S + row) * (3LL * D) + h * HD;
+    if (warp_active) {                       // the two warp groups cover the same rows: alternate 16-column chunks
 #pragma unroll 1
-    for (int c0 = 0; c0 < HD; c0 += 16) {
-      uint32_t o[16];
-      tmem_ld16(tmem_dQ + lane_off + c0, o);
-      if (row_ok) {
+      for (int c0 = wg * 16; c0 < HD; c0 += 32) {
+        uint32_t o[16];
+        tmem_ld16(tmem_dQ + lane_off + c0, o);
+        if (row_ok) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * scale, __uint_as_float(o[8 * g + 1]) * scale);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * scale, __uint_as_float(o[8 * g + 3]) * scale);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * scale, __uint_as_float(o[8 * g + 5]) * scale);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * scale, __uint_as_float(o[8 * g + 7]) * scale);
-          *reinterpret_cast<uint4*>(dqrow + c0 + 8 * g) = u;
+          for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * scale, __uint_as_float(o[8 * g + 1]) * scale);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * scale, __uint_as_float(o[8 * g + 3]) * scale);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * scale, __uint_as_float(o[8 * g + 5]) * scale);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * scale, __uint_as_float(o[8 * g + 7]) * scale);
+            *reinterpret_cast<uint4*>(dqrow + c0 + 8 * g) = u;
+          }
         }
       }
     }
@@ -834,16 +825,16 @@ static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const 
                          const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) {
-    int rc = set_smem(attn_bwd_dkdv_tc_kernel<HD>, DKDV_SMEM); if (rc) return rc;
-    rc = set_smem(attn_bwd_dq_tc_kernel<HD>, DQ_SMEM); if (rc) return rc;
+    int rc = set_smem(attn_bwd_dkdv_tc_kernel<HD>, BWD_SMEM); if (rc) return rc;
+    rc = set_smem(attn_bwd_dq_tc_kernel<HD>, BWD_SMEM); if (rc) return rc;
     cfg = true;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   dim3 grid((S + TILE - 1) / TILE, H, B);
-  attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, DKDV_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale);
+  attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale);
   int rc = hct_check_launch("attn_bwd_dkdv_tc_kernel");
   if (rc) return rc;
-  attn_bwd_dq_tc_kernel<HD><<<grid, BWD_THREADS, DQ_SMEM, st>>>(q128, q64, do128, lse, delta, dqkv, S, H, scale);
+  attn_bwd_dq_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do128, lse, delta, dqkv, S, H, scale);
   return hct_check_launch("attn_bwd_dq_tc_kernel");
 }
 

@@ -28,8 +28,9 @@ for flags in [0]:
     lib().hct_attention_trace(None)
     t = tr.cpu().view(3, 32, 8)
     t0 = int(t[t > 0].min())
-    names = {0: ["wait qdo_empty", "got", "tma issued"], 1: ["sdp: wait qdo_full", "got; wait s_empty", "got", "S/dP issued+commit", "wait p_full", "got", "dV/dK issued+commit"],
-             2: ["at named bar", "passed; wait s_full", "got", "computed; wait pv_done", "got", "stored+arrived p_full"]}
+    names = {0: ["wait qdo_empty", "got", "tma issued"],
+             1: ["sdp: wait qdo_full", "got", "S/dP issued+commit", "wait p_full", "got", "dV/dK issued+commit"],
+             2: ["wait s_full", "got", "computed", "stored+arrived p_full"]}
     for role, rn in enumerate(["producer", "mma", "softmax w2"]):
         print(f"-- {rn}: " + " | ".join(names[role]))
         for i in range(9):
