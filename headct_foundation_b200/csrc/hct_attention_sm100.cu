@@ -1,13 +1,9 @@
 // Flash attention on tcgen05 / TMEM for sm_100a (F.scaled_dot_product_attention, attentionblock.py:61).
-//
-// Forward: one CTA per (batch, head, 128-query tile), two CTAs per SM.
-//   warp 0   TMA producer: Q once, then K_j / V_j tiles (128 keys) straight out of the qkv GEMM output
-//            ([B,S,3,H,hd], 128B-swizzled boxes of 64 columns; hd = 48 uses the first 48 of them)
-//   warp 1   MMA issuer:   S = Q K_j^T (128x128, K = hd) into TMEM, then O += P_j V_j (128 x hd, K = 128)
-//   warps 2-5 softmax:     one query row per thread (TMEM lane = row): tcgen05.ld S, online max / exp2 / sum,
-//            P_j written as bf16 into a 128B-swizzled K-major smem tile (the A operand of the PV MMA),
-//            O rescaled in TMEM when the running max moves, final O / l and log-sum-exp written out.
-// Everything between the roles is mbarrier-synchronised; S and O never leave the SM.
+// Forward and backward kernels below; every matmul runs on the tensor core with fp32 accumulators in tensor memory,
+// the softmax threads own one row (TMEM lane) each, and the bf16 probabilities / score gradients they produce go back
+// to the tensor core through tensor memory (A-from-TMEM MMA), never through shared memory.
+// Roles inside a CTA are warp-specialised and mbarrier-synchronised: TMA producer warp, MMA issuer warp (both run as
+// converged warps and issue under elect_one), softmax warps.
 #include "../../include/hct_b200.h"
 #include "hct_tcgen05.cuh"
 
@@ -26,24 +22,31 @@ __device__ __forceinline__ float ex2f(float x) {   // bare MUFU.EX2 (ftz); ex2(-
   return y;
 }
 
-// bf16 P/dS tile [128 rows][128 cols] as two 64-column K-major SW128 halves: address of 16-byte chunk `ch` (0..15)
-__device__ __forceinline__ uint32_t ptile_addr(uint32_t base, int row, int ch) {
-  return base + (ch >> 3) * TILE_BYTES + row * 128 + (((ch & 7) ^ (row & 7)) << 4);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 constexpr int FWD_THREADS = 192;
-// Warp roles.  The warp scheduler favours the highest warp id among eligible warps, so the two single-thread control
-// warps (TMA producer, MMA issuer) sit ABOVE the softmax warps: their few instructions must never queue behind the
-// exp / pack streams of the softmax warps (measured: the MMA issuer took > 1000 cycles to issue 8 MMAs as warp 1).
-constexpr int FWD_PRODUCER_WARP = 4, FWD_MMA_WARP = 5;      // warps 0-3: softmax (TMEM lane quarter = warp id)
+// Warp roles: warps 0-3 softmax (TMEM lane quarter = warp id), then the two control warps.
+constexpr int FWD_PRODUCER_WARP = 4, FWD_MMA_WARP = 5;
 constexpr int FWD_TK = 64;                 // keys per inner block
-constexpr int FWD_TMEM_COLS = 128;         // S: cols [0,64), O: cols [64, 64+hd)  -> four CTAs per SM
+constexpr int FWD_TMEM_COLS = 128;         // S: cols [0,64) (P overwrites [0,32) in place), O: cols [64, 64+hd)  -> four CTAs per SM
 constexpr int FWD_KV_BYTES = FWD_TK * 128; // [64 keys][64 bf16]
-constexpr int FWD_SMEM = 2 * TILE_BYTES + 2 * FWD_KV_BYTES + 1024 + 128;   // Q, P, K, V + align slack + barriers
+constexpr int FWD_SMEM = TILE_BYTES + 4 * FWD_KV_BYTES + 1024 + 128;   // Q, 2 x K, 2 x V + align slack + barriers
 
+// A operand from tensor memory: D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Forward: one CTA per (batch, head, 128-query tile), four CTAs per SM.
+//   producer warp : Q once, then K_j / V_j tiles (64 keys, double-buffered) straight out of the qkv GEMM output
+//   MMA warp      : S_0 = Q K_0^T;  then per block [O += P_j V_j (A = P_j from TMEM), S_{j+1} = Q K_{j+1}^T] back to back
+//   warps 0-3     : one query row per thread: tcgen05.ld S_j, online max / exp2 / sum, P_j written as bf16 pairs IN PLACE
+//                   over the first 32 of the 64 fp32 columns the thread has just read (tcgen05.st), O rescaled in TMEM
+//                   when the running max moves, final O / l and log-sum-exp written out.
+// S, P and O never leave the SM; P never touches shared memory.
 template <int HD>
 __global__ void __launch_bounds__(FWD_THREADS, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
@@ -52,13 +55,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* sQ = smem;
-  uint8_t* sP = smem + TILE_BYTES;                   // [128 queries][64 keys] bf16, K-major SW128
-  uint8_t* sK = smem + 2 * TILE_BYTES;
-  uint8_t* sV = sK + FWD_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + FWD_KV_BYTES);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-           *s_full = bars + 5, *s_empty = bars + 6, *p_full = bars + 7, *pv_done = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sK = smem + TILE_BYTES;                   // 2 x [64 keys][64]
+  uint8_t* sV = sK + 2 * FWD_KV_BYTES;               // 2 x [64 keys][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * FWD_KV_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1 /*[2]*/, *k_empty = bars + 3 /*[2]*/, *v_full = bars + 5 /*[2]*/,
+           *v_empty = bars + 7 /*[2]*/, *s_full = bars + 9, *p_full = bars + 10, *done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
@@ -70,8 +72,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
-    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(s_empty, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, FWD_TMEM_COLS);
@@ -89,15 +92,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_2d(smem_u32(sQ), &tmQ, q_full, h * HD, b * S + qt * TILE);
     }
     for (int j = 0; j < nkb; ++j) {
-      mbar_wait(k_empty, (j & 1) ^ 1u);
+      const int st = j & 1;
+      const uint32_t ph = ((j >> 1) & 1) ^ 1u;
+      mbar_wait(&k_empty[st], ph);
       if (leader) {
-        mbar_expect_tx(k_full, FWD_KV_BYTES);
-        tma_load_2d(smem_u32(sK), &tmKV, k_full, D + h * HD, b * S + j * FWD_TK);
+        mbar_expect_tx(&k_full[st], FWD_KV_BYTES);
+        tma_load_2d(smem_u32(sK + st * FWD_KV_BYTES), &tmKV, &k_full[st], D + h * HD, b * S + j * FWD_TK);
       }
-      mbar_wait(v_empty, (j & 1) ^ 1u);
+      mbar_wait(&v_empty[st], ph);
       if (leader) {
-        mbar_expect_tx(v_full, FWD_KV_BYTES);
-        tma_load_2d(smem_u32(sV), &tmKV, v_full, 2 * D + h * HD, b * S + j * FWD_TK);
+        mbar_expect_tx(&v_full[st], FWD_KV_BYTES);
+        tma_load_2d(smem_u32(sV + st * FWD_KV_BYTES), &tmKV, &v_full[st], 2 * D + h * HD, b * S + j * FWD_TK);
       }
       __syncwarp();
     }
@@ -108,57 +113,49 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t idesc_s16 = make_idesc_bf16(TILE, 16, false, false);
     const uint32_t idesc_o = make_idesc_bf16(TILE, HD, false, true);
     const uint64_t dQ = make_sdesc_sw128(smem_u32(sQ), false, 0);
-    const uint64_t dK = make_sdesc_sw128(smem_u32(sK), false, 0);
-    const uint64_t dV = make_sdesc_sw128(smem_u32(sV), true, FWD_KV_BYTES);
-    const uint64_t dP = make_sdesc_sw128(smem_u32(sP), false, 0);
     mbar_wait(q_full, 0);
-    // S_{j+1} = Q K_{j+1}^T is issued as soon as the softmax threads have pulled S_j into registers, i.e. it runs
-    // underneath their exp / P-store work; P_j V_j follows when P_j has landed in shared memory.
     // A last block with <= 16 valid keys (the cls token makes S = 64 k + 1) is computed 16 keys wide.
     auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      tc_fence_after();
       if (leader) {
         const uint32_t id = (j == nkb - 1 && tail16) ? idesc_s16 : idesc_s;
+        const uint64_t dK = make_sdesc_sw128(smem_u32(sK + st * FWD_KV_BYTES), false, 0);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) tc_mma(tmem_S, dQ + ks * 2, dK + ks * 2, id, ks > 0 ? 1u : 0u);
         tc_commit(s_full);
-        tc_commit(k_empty);
+        tc_commit(&k_empty[st]);
       }
       __syncwarp();
     };
-    mbar_wait(k_full, 0);
-    tc_fence_after();
     issue_s(0);
     for (int j = 0; j < nkb; ++j) {
-      if (j + 1 < nkb) {
-        mbar_wait(k_full, (j + 1) & 1);
-        mbar_wait(s_empty, j & 1);
-        tc_fence_after();
-        issue_s(j + 1);
-      }
-      mbar_wait(p_full, j & 1);
-      mbar_wait(v_full, j & 1);
+      const int st = j & 1;
+      mbar_wait(p_full, j & 1);                       // P_j sits in TMEM (and every softmax warp has read S_j)
+      mbar_wait(&v_full[st], (j >> 1) & 1);
       tc_fence_after();
       if (leader) {
+        const uint64_t dV = make_sdesc_sw128(smem_u32(sV + st * FWD_KV_BYTES), true, FWD_KV_BYTES);
         const uint32_t acc = j > 0 ? 1u : 0u;
         if (j == nkb - 1 && tail16) {
-          tc_mma(tmem_O, dP, dV, idesc_o, acc);
+          tc_mma_ts(tmem_O, tmem_S, dV, idesc_o, acc);
         } else {
 #pragma unroll
-          for (int ks = 0; ks < FWD_TK / 16; ++ks) tc_mma(tmem_O, dP + ks * 2, dV + ks * 128, idesc_o, ks > 0 ? 1u : acc);
+          for (int ks = 0; ks < FWD_TK / 16; ++ks) tc_mma_ts(tmem_O, tmem_S + ks * 8, dV + ks * 128, idesc_o, ks > 0 ? 1u : acc);
         }
-        tc_commit(pv_done);
-        tc_commit(v_empty);
+        tc_commit(&v_empty[st]);
+        if (j == nkb - 1) tc_commit(done);
       }
       __syncwarp();
+      if (j + 1 < nkb) issue_s(j + 1);                // executes after P_j V_j (in-order pipe): safe to overwrite S / P
     }
   } else if (warp < 4) {
     // ===================== softmax / correction / epilogue: one query row per thread =====================
     const int q = warp & 3;
-    const int row_local = q * 32 + lane;
-    const int row = qt * TILE + row_local;
+    const int row = qt * TILE + q * 32 + lane;
     const bool warp_active = qt * TILE + q * 32 < S;   // a warp whose 32 rows all lie past S only keeps the barriers moving
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t sP_addr = smem_u32(sP);
     float m = -INFINITY, l = 0.f;
     // Lazy rescaling: the reference point m only moves when the block maximum exceeds it by more than 2^8 in the
     // exponent domain (or on the first block).  Probabilities are then at most 2^8 -- harmless in fp32 / bf16 --
@@ -173,7 +170,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       return alpha;
     };
-    auto rescale_o = [&](float alpha) {                       // running max moved: rescale the O accumulator in TMEM
+    // S_j complete implies P_{j-1} V_{j-1} complete (one in-order pipe, one commit): O is stable until this warp arrives
+    auto rescale_o = [&](float alpha) {
       uint32_t o[16];
 #pragma unroll 1
       for (int c0 = 0; c0 < HD; c0 += 16) {
@@ -182,121 +180,102 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
         tmem_st16(tmem_O + lane_off + c0, o);
       }
-      tmem_st_wait();
     };
     for (int j = 0; j < nkb; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int nvalid = min(FWD_TK, S - j * FWD_TK);         // valid key columns in this block (>= 1)
-      if (!warp_active) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);
-        if (j > 0) mbar_wait(pv_done, (j - 1) & 1);
-        if (lane == 0) mbar_arrive(p_full);
-        continue;
-      }
-      if (j == nkb - 1 && tail16) {
-        // ---- 16-column tail block
-        uint32_t v[16];
-        tmem_ld16(tmem_S + lane_off, v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);
-        float mb = -INFINITY;
+      if (warp_active) {
+        if (j == nkb - 1 && tail16) {
+          // ---- 16-column tail block
+          uint32_t v[16];
+          tmem_ld16(tmem_S + lane_off, v);
+          float mb = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mb = fmaxf(mb, i < nvalid ? __uint_as_float(v[i]) : -INFINITY);
-        const float alpha = move_max(j, mb);
-        const float msc = m * sl2;
-        float rsum = 0.f;
-        uint32_t pk[8];
+          for (int i = 0; i < 16; ++i) mb = fmaxf(mb, i < nvalid ? __uint_as_float(v[i]) : -INFINITY);
+          const float alpha = move_max(j, mb);
+          const float msc = m * sl2;
+          float rsum = 0.f;
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float a0 = i < nvalid ? ex2f(fmaf(__uint_as_float(v[i]), sl2, -msc)) : 0.f;
-          const float a1 = i + 1 < nvalid ? ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -msc)) : 0.f;
-          rsum += a0 + a1;
-          pk[i >> 1] = pack_bf16x2(a0, a1);
-        }
-        l = l * alpha + rsum;
-        if (j > 0) {
-          mbar_wait(pv_done, (j - 1) & 1);
-          tc_fence_after();
-          if (!__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
-        }
-        st_shared_v4(ptile_addr(sP_addr, row_local, 0), pk[0], pk[1], pk[2], pk[3]);
-        st_shared_v4(ptile_addr(sP_addr, row_local, 1), pk[4], pk[5], pk[6], pk[7]);
-      } else {
-        // ---- full 64-column block (a partial one is padded with -inf first)
-        uint32_t v0[32], v1[32];
-        tmem_ld32_issue(tmem_S + lane_off, v0);
-        tmem_ld32_issue(tmem_S + lane_off + 32, v1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty);                  // S is in registers: the next Q K^T may overwrite it
-        if (nvalid < FWD_TK) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= nvalid) v0[i] = 0xff800000u;
-            if (i + 32 >= nvalid) v1[i] = 0xff800000u;
+          for (int i = 0; i < 16; i += 2) {
+            const float a0 = i < nvalid ? ex2f(fmaf(__uint_as_float(v[i]), sl2, -msc)) : 0.f;
+            const float a1 = i + 1 < nvalid ? ex2f(fmaf(__uint_as_float(v[i + 1]), sl2, -msc)) : 0.f;
+            rsum += a0 + a1;
+            pk[i >> 1] = pack_bf16x2(a0, a1);
           }
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+          for (int i = 8; i < 16; ++i) pk[i] = 0u;
+          l = l * alpha + rsum;
+          if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
+          tmem_st16(tmem_S + lane_off, pk);
+        } else {
+          // ---- full 64-column block (a partial one is padded with -inf first)
+          uint32_t v0[32], v1[32];
+          tmem_ld32_issue(tmem_S + lane_off, v0);
+          tmem_ld32_issue(tmem_S + lane_off + 32, v1);
+          tmem_ld_wait();
+          if (nvalid < FWD_TK) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) mx[t] = fmaxf(mx[t], fmaxf(__uint_as_float(v0[i + t]), __uint_as_float(v1[i + t])));
-        }
-        const float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        const float alpha = move_max(j, mb);
-        const float msc = m * sl2;
-        float rs0 = 0.f, rs1 = 0.f;
-        uint32_t pk[32];
+            for (int i = 0; i < 32; ++i) {
+              if (i >= nvalid) v0[i] = 0xff800000u;
+              if (i + 32 >= nvalid) v1[i] = 0xff800000u;
+            }
+          }
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float a0 = ex2f(fmaf(__uint_as_float(v0[i]), sl2, -msc)), a1 = ex2f(fmaf(__uint_as_float(v0[i + 1]), sl2, -msc));
-          const float b0 = ex2f(fmaf(__uint_as_float(v1[i]), sl2, -msc)), b1 = ex2f(fmaf(__uint_as_float(v1[i + 1]), sl2, -msc));
-          rs0 += a0 + a1;
-          rs1 += b0 + b1;
-          pk[i >> 1] = pack_bf16x2(a0, a1);
-          pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
-        }
-        l = l * alpha + (rs0 + rs1);
-        if (j > 0) {
-          mbar_wait(pv_done, (j - 1) & 1);                    // previous P V retired: P tile reusable, O stable
-          tc_fence_after();
-          if (!__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
-        }
+          for (int i = 0; i < 32; i += 4) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          st_shared_v4(ptile_addr(sP_addr, row_local, g), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+            for (int t = 0; t < 4; ++t) mx[t] = fmaxf(mx[t], fmaxf(__uint_as_float(v0[i + t]), __uint_as_float(v1[i + t])));
+          }
+          const float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          const float alpha = move_max(j, mb);
+          const float msc = m * sl2;
+          float rs0 = 0.f, rs1 = 0.f;
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float a0 = ex2f(fmaf(__uint_as_float(v0[i]), sl2, -msc)), a1 = ex2f(fmaf(__uint_as_float(v0[i + 1]), sl2, -msc));
+            const float b0 = ex2f(fmaf(__uint_as_float(v1[i]), sl2, -msc)), b1 = ex2f(fmaf(__uint_as_float(v1[i + 1]), sl2, -msc));
+            rs0 += a0 + a1;
+            rs1 += b0 + b1;
+            pk[i >> 1] = pack_bf16x2(a0, a1);
+            pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
+          }
+          l = l * alpha + (rs0 + rs1);
+          if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
+          tmem_st32(tmem_S + lane_off, pk);                   // keys 2c, 2c+1 -> column c: the A operand of P_j V_j
+        }
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the tensor core
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> bf16, log-sum-exp
-    mbar_wait(pv_done, (nkb - 1) & 1);
+    mbar_wait(done, 0);
     tc_fence_after();
-    const float inv = 1.0f / l;
-    bf16* orow = out + (static_cast<long long>(b) * S + row) * D + h * HD;
+    if (warp_active) {
+      const float inv = 1.0f / l;
+      bf16* orow = out + (static_cast<long long>(b) * S + row) * D + h * HD;
 #pragma unroll 1
-    for (int c0 = 0; c0 < HD; c0 += 16) {
-      uint32_t o[16];
-      tmem_ld16(tmem_O + lane_off + c0, o);
-      if (row < S) {
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld16(tmem_O + lane_off + c0, o);
+        if (row < S) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = u;
+          for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = u;
+          }
         }
       }
+      if (row < S) lse[(static_cast<long long>(b) * H + h) * S + row] = m * scale + logf(l);
     }
-    if (row < S) lse[(static_cast<long long>(b) * H + h) * S + row] = m * scale + logf(l);
   }
 
   tc_fence_before();
@@ -331,16 +310,6 @@ constexpr int BWD_PRODUCER_WARP = 8, BWD_MMA_WARP = 9;
 constexpr int BWD_TMEM_COLS = 256;
 constexpr int BWD_STAGES = 4;              // TMA ring depth for the streamed 64-row tiles
 constexpr int BWD_SMEM = 2 * TILE_BYTES + BWD_STAGES * 2 * HALF_BYTES + 8 * 512 + 1024 + 256;   // resident tiles, ring, per-warp stats, align, barriers
-
-// A operand from tensor memory: D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 template <int HD>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
