@@ -117,20 +117,50 @@ def linear_dgrad(dy16: torch.Tensor, w: torch.Tensor, *, epi: int = EPI_BF16, au
     return out
 
 
-def linear_wgrad(dy16: torch.Tensor, x16: torch.Tensor) -> torch.Tensor:
-    """dW[N,K] (fp32) = dy16[M,N]^T @ x16[M,K]   (both operands MN-major; split-K + fp32 red.add)."""
+class ZeroArena:
+    """One zero-filled fp32 allocation handed out in 256-byte-aligned slices.
+
+    A block's backward accumulates a dozen parameter gradients with atomics into pre-zeroed buffers; zeroing them
+    one `torch.zeros` at a time cost ~250 tiny fill launches per step, this costs one per autograd node."""
+
+    def __init__(self, sizes: Sequence[int], device: torch.device):
+        self._offs: List[int] = []
+        total = 0
+        for n in sizes:
+            self._offs.append(total)
+            total += (n + 63) // 64 * 64
+        self._buf = torch.zeros((max(total, 64),), dtype=F32, device=device)
+        self._sizes = list(sizes)
+        self._next = 0
+
+    def take(self, *shape: int) -> torch.Tensor:
+        i = self._next
+        self._next += 1
+        n = 1
+        for d in shape:
+            n *= d
+        assert n == self._sizes[i], (shape, self._sizes[i])
+        return self._buf[self._offs[i]:self._offs[i] + n].view(*shape)
+
+
+def linear_wgrad(dy16: torch.Tensor, x16: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[N,K] (fp32) = dy16[M,N]^T @ x16[M,K]   (both operands MN-major; split-K + fp32 red.add).
+    `out`: optional pre-zeroed fp32 [N,K]."""
     M, N = dy16.shape
     K = x16.shape[1]
     assert x16.shape[0] == M
-    out = torch.zeros((N, K), dtype=F32, device=dy16.device)
+    if out is None:
+        out = torch.zeros((N, K), dtype=F32, device=dy16.device)
     gemm(dy16, x16, M=N, N=K, K=M, lda=N, ldb=K, a_mn=True, b_mn=True, out=out, ldo=K, epi=EPI_ATOMIC_F32)
     return out
 
 
-def colsum(x: torch.Tensor, cols: int) -> torch.Tensor:
-    """fp32 [cols] = sum over rows of a contiguous [rows, cols] bf16/fp32 matrix (bias gradients)."""
+def colsum(x: torch.Tensor, cols: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [cols] = sum over rows of a contiguous [rows, cols] bf16/fp32 matrix (bias gradients).
+    `out`: optional pre-zeroed fp32 [cols]."""
     rows = x.numel() // cols
-    out = torch.zeros((cols,), dtype=F32, device=x.device)
+    if out is None:
+        out = torch.zeros((cols,), dtype=F32, device=x.device)
     call("hct_colsum", x.data_ptr(), int(x.dtype == BF16), cols, out.data_ptr(), rows, cols, stream_ptr(x.device))
     return out
 
@@ -155,14 +185,19 @@ def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd, dres: Optional[torch.Tensor],
-                  want_bf16: bool, want_param_grads: bool = True, want_colsum: bool = False):
+                  want_bf16: bool, want_param_grads: bool = True, want_colsum: bool = False,
+                  zeros: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+    """`zeros`: optional pre-zeroed fp32 [D] buffers for (dgamma, dbeta, column sums)."""
     D = x.shape[-1]
     rows = x.numel() // D
     dx = torch.empty(x.shape, dtype=F32, device=x.device)
     dx16 = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
-    dg = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
-    db = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
-    dsum = torch.zeros((D,), dtype=F32, device=x.device) if (want_colsum and want_bf16) else None
+    if zeros is not None:
+        dg, db, dsum = zeros
+    else:
+        dg = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
+        db = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
+        dsum = torch.zeros((D,), dtype=F32, device=x.device) if (want_colsum and want_bf16) else None
     call("hct_layernorm_bwd", dy.data_ptr(), int(dy.dtype == BF16), x.data_ptr(), w.data_ptr(), mean.data_ptr(),
          rstd.data_ptr(), ptr(dres), dx.data_ptr(), ptr(dx16), ptr(dg), ptr(db), ptr(dsum), rows, D,
          stream_ptr(x.device))
@@ -228,19 +263,23 @@ class BlockFn(torch.autograd.Function):
             d3 = rows_to_bf16(dout, groups=1, src_rows_per_group=M, src_row_off=0, rows_per_group=M, dim=D)
         if dfc2_b is None:
             dfc2_b = colsum(d3, D)
+        # every accumulated (atomics) output of this node comes out of ONE zero-filled allocation
+        F_ = a.shape[1]
+        zs = ZeroArena([D * F_, F_, F_ * D, D, D, D, D * D, 3 * D * D, 3 * D if ctx.has_qkv_bias else 0, D, D, D], dev)
         # ---- MLP branch
-        dfc2_w = linear_wgrad(d3, g)
-        dfc1_b = torch.zeros((a.shape[1],), dtype=F32, device=dev)
+        dfc2_w = linear_wgrad(d3, g, out=zs.take(D, F_))
+        dfc1_b = zs.take(F_)
         da = linear_dgrad(d3, fc2_w, epi=EPI_MUL_BF16, aux=a, colsum=dfc1_b)            # [M, F] bf16 (+ column sums)
         del d3
-        dfc1_w = linear_wgrad(da, h2.view(M, D))
+        dfc1_w = linear_wgrad(da, h2.view(M, D), out=zs.take(F_, D))
         dh2 = linear_dgrad(da, fc1_w)                                                   # [M, D] bf16
         del da
-        dx2, dx2_16, dn2w, dn2b, dproj_b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, True, want_colsum=True)
+        dx2, dx2_16, dn2w, dn2b, dproj_b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, True, want_colsum=True,
+                                                         zeros=(zs.take(D), zs.take(D), zs.take(D)))
         del dh2
         # ---- attention branch
         dx2_16 = dx2_16.view(M, D)
-        dproj_w = linear_wgrad(dx2_16, att)
+        dproj_w = linear_wgrad(dx2_16, att, out=zs.take(D, D))
         datt = linear_dgrad(dx2_16, proj_w)                                             # [M, D] bf16
         del dx2_16
         dqkv = torch.empty_like(qkv)
@@ -248,11 +287,13 @@ class BlockFn(torch.autograd.Function):
         call("hct_attention_bwd", qkv.data_ptr(), att.data_ptr(), datt.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
              delta.data_ptr(), B, S, heads, hd, st)
         del datt
-        dqkv_w = linear_wgrad(dqkv, h1.view(M, D))
-        dqkv_b = colsum(dqkv, 3 * D) if ctx.has_qkv_bias else None
+        dqkv_w = linear_wgrad(dqkv, h1.view(M, D), out=zs.take(3 * D, D))
+        zq = zs.take(3 * D if ctx.has_qkv_bias else 0)
+        dqkv_b = colsum(dqkv, 3 * D, out=zq) if ctx.has_qkv_bias else None
         dh1 = linear_dgrad(dqkv, qkv_w)
         del dqkv
-        dx, dx16, dn1w, dn1b, dxs = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True, want_colsum=True)
+        dx, dx16, dn1w, dn1b, dxs = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True, want_colsum=True,
+                                                  zeros=(zs.take(D), zs.take(D), zs.take(D)))
         put_bf16_shadow(dx, dx16, dxs)
         return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, None,
                 None)
