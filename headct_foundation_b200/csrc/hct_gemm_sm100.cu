@@ -141,8 +141,21 @@ struct EpiTraits {
   static constexpr bool gelu_fwd = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16;
 };
 
+// bf16 multiplicand rows of one interior 32 x 32 unit (lane = (row sub-index, 4-column group)), eight 8-byte loads
 template <int EPI>
-__device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0) {
+__device__ __forceinline__ bool unit_interior(const GemmParams& p, int row_base, int col0) {
+  return EPI != HCT_EPI_POS_F32 && p.rows_in <= 0 && row_base + 32 <= p.M && col0 + 32 <= p.N;
+}
+__device__ __forceinline__ void load_aux_unit(const GemmParams& p, int lane, int row_base, int col0, uint2 (&aux)[8]) {
+  const bf16* ap = p.aux + static_cast<long long>(row_base + (lane >> 3)) * p.ldaux + col0 + (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) aux[i] = *reinterpret_cast<const uint2*>(ap + static_cast<long long>(i) * 4 * p.ldaux);
+}
+
+// `pre`: the unit's aux operand already in registers (loaded one unit ahead by the caller), interior units only
+template <int EPI>
+__device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0,
+                                               const uint2 (&pre)[8], bool have_pre) {
   using T = EpiTraits<EPI>;
   // ---- phase 2: lane = (row sub-index, column group); rows handled in two groups of four to bound registers
   const int jj = lane & 7, rsub = lane >> 3;
@@ -156,7 +169,7 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
   // Interior units (all 32 rows and 32 columns inside the matrix, no row remapping) take a path without per-row
   // predicates and with incremental row pointers: the general path below spends ~40 % of its instructions on
   // 64-bit address arithmetic and reconvergence, which made the GELU epilogues (not the MMAs) set the tile period.
-  const bool interior = EPI != HCT_EPI_POS_F32 && p.rows_in <= 0 && row_base + 32 <= p.M && col0 + 32 <= p.N;
+  const bool interior = unit_interior<EPI>(p, row_base, col0);
   if (interior) {
     const long long r0 = row_base + rsub;
     const bool has_colsum = p.colsum != nullptr;
@@ -168,9 +181,12 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
       for (int i = 0; i < 8; ++i) extra[i] = *reinterpret_cast<const float4*>(rp + static_cast<long long>(i) * 4 * p.ldres);
     }
     if (T::uses_aux) {
-      const bf16* ap = p.aux + r0 * p.ldaux + col;
+      if (have_pre) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) aux[i] = *reinterpret_cast<const uint2*>(ap + static_cast<long long>(i) * 4 * p.ldaux);
+        for (int i = 0; i < 8; ++i) aux[i] = pre[i];
+      } else {
+        load_aux_unit(p, lane, row_base, col0, aux);
+      }
     }
     if (T::bf16_out) {
       bf16* op = reinterpret_cast<bf16*>(p.out) + r0 * p.ldo + col;
@@ -535,6 +551,15 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
         }
       }
+      // the bf16 multiplicand of a MUL / DGELU epilogue does not depend on the accumulator: the first unit's rows are
+      // requested before waiting for the tile, every further unit's while the previous one is drained
+      uint2 aux_cur[8], aux_nxt[8];
+      bool have_cur = false;
+      if (EpiTraits<EPI>::uses_aux) {
+        const int colw0 = n0 + half * (BN / 2);
+        have_cur = unit_interior<EPI>(p, m0 + q * 32, colw0);
+        if (have_cur) load_aux_unit(p, lane, m0 + q * 32, colw0, aux_cur);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       // software pipeline over the warp's four 32-column units: the TMEM load of unit c+1 is in flight while unit c
@@ -557,7 +582,17 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           tc_fence_before(); __syncwarp();
           if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
         }
-        epilogue_drain<EPI>(p, stg, lane, m0 + q * 32, colw + c * 32);
+        bool have_nxt = false;
+        if (EpiTraits<EPI>::uses_aux && c + 1 < nunits) {
+          have_nxt = unit_interior<EPI>(p, m0 + q * 32, colw + (c + 1) * 32);
+          if (have_nxt) load_aux_unit(p, lane, m0 + q * 32, colw + (c + 1) * 32, aux_nxt);
+        }
+        epilogue_drain<EPI>(p, stg, lane, m0 + q * 32, colw + c * 32, aux_cur, have_cur);
+        if (EpiTraits<EPI>::uses_aux) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) aux_cur[i] = aux_nxt[i];
+          have_cur = have_nxt;
+        }
       }
       if (nunits == 0) {
         tc_fence_before(); __syncwarp();

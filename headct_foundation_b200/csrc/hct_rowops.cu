@@ -74,7 +74,7 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
                "l"(gsrc) : "memory");
 }
 
-template <int NV, bool DY_BF16>
+template <int NV, bool DY_BF16, int LN_BWD_STAGES>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres_in,
@@ -83,41 +83,42 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
   extern __shared__ __align__(16) float sbuf[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = dim >> 2;
-  // per warp, per stage: x [dim] f32 | dres [dim] f32 | dy [dim] (f32 or bf16, sized for f32)
-  const int stage_floats = 3 * dim;
-  float* wbuf = sbuf + static_cast<size_t>(warp) * 2 * stage_floats;
+  // per warp, per stage: x [dim] f32 | dres [dim] f32 | dy [dim] (f32, or bf16 in half the space)
+  // LN_BWD_STAGES-deep cp.async ring per warp: two rows (15 KiB at dim 768) in flight per warp, ~120 KiB per SM --
+  // a 2-deep ring (60 KiB per SM) sat right at the bandwidth-delay product of HBM under load.
+  const int stage_floats = DY_BF16 ? 2 * dim + dim / 2 : 3 * dim;
+  float* wbuf = sbuf + static_cast<size_t>(warp) * LN_BWD_STAGES * stage_floats;
   float4 dg[NV], db[NV], ds[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = dg[i]; ds[i] = dg[i]; }
 
   const long long row0 = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
   const long long rstride = static_cast<long long>(gridDim.x) * LN_WARPS;
-  auto prefetch = [&](long long row, int stage) {
-    float* sx = wbuf + stage * stage_floats;
-    float* sr = sx + dim;
-    float* sd = sr + dim;
+  auto prefetch = [&](long long row, int stage) {          // always commits a group (possibly empty): uniform counting
+    if (row < rows) {
+      float* sx = wbuf + stage * stage_floats;
+      float* sr = sx + dim;
+      float* sd = sr + dim;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = i * 32 + lane;
-      if (c < nv) {
-        cp_async_16(sx + 4 * c, x + row * dim + 4 * c);
-        if (dres_in) cp_async_16(sr + 4 * c, dres_in + row * dim + 4 * c);
-        if (DY_BF16) cp_async_8(reinterpret_cast<bf16*>(sd) + 4 * c, reinterpret_cast<const bf16*>(dy) + row * dim + 4 * c);
-        else cp_async_16(sd + 4 * c, reinterpret_cast<const float*>(dy) + row * dim + 4 * c);
+      for (int i = 0; i < NV; ++i) {
+        const int c = i * 32 + lane;
+        if (c < nv) {
+          cp_async_16(sx + 4 * c, x + row * dim + 4 * c);
+          if (dres_in) cp_async_16(sr + 4 * c, dres_in + row * dim + 4 * c);
+          if (DY_BF16) cp_async_8(reinterpret_cast<bf16*>(sd) + 4 * c, reinterpret_cast<const bf16*>(dy) + row * dim + 4 * c);
+          else cp_async_16(sd + 4 * c, reinterpret_cast<const float*>(dy) + row * dim + 4 * c);
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  if (row0 < rows) prefetch(row0, 0);
+#pragma unroll
+  for (int k = 0; k < LN_BWD_STAGES - 1; ++k) prefetch(row0 + k * rstride, k);
   int stage = 0;
-  for (long long row = row0; row < rows; row += rstride, stage ^= 1) {
-    if (row + rstride < rows) {
-      prefetch(row + rstride, stage ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+  for (long long row = row0; row < rows; row += rstride, stage = (stage + 1 == LN_BWD_STAGES ? 0 : stage + 1)) {
+    prefetch(row + (LN_BWD_STAGES - 1) * rstride, (stage + LN_BWD_STAGES - 1) % LN_BWD_STAGES);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LN_BWD_STAGES - 1) : "memory");
     __syncwarp();
     const float mu = mean[row], rs = rstd[row];
     const float* sx = wbuf + stage * stage_floats;
@@ -169,7 +170,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
         }
       }
     }
-    __syncwarp();   // everyone done reading this stage before it is refilled two iterations later
+    __syncwarp();   // everyone done reading this stage before it is refilled by the next iteration's prefetch
   }
   // cross-warp reduction of the column accumulators (reuses the staging memory), one atomic per column per CTA
   __syncthreads();
@@ -359,27 +360,34 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
   HCT_REQUIRE(dxsum == nullptr || dx_out_bf16 != nullptr, "layernorm_bwd: dxsum needs the bf16 output");
   if (rows == 0) return HCT_OK;
   const int grid = grid_for(rows, LN_WARPS, hct_num_sms());
-  const size_t smem = static_cast<size_t>(LN_WARPS) * 2 * 3 * dim * sizeof(float);
+  const size_t stage_floats = dy_bf16 ? 2 * static_cast<size_t>(dim) + dim / 2 : 3 * static_cast<size_t>(dim);
+  const size_t scratch = static_cast<size_t>(LN_WARPS) * 3 * dim * sizeof(float);     // final cross-warp reduction
+  int stages = 3;                                                                      // deepest ring that fits
+  if (static_cast<size_t>(LN_WARPS) * 3 * stage_floats * sizeof(float) > 200 * 1024) stages = 2;
+  size_t smem = static_cast<size_t>(LN_WARPS) * stages * stage_floats * sizeof(float);
+  if (smem < scratch) smem = scratch;
   HCT_REQUIRE(smem <= 200 * 1024, "layernorm_bwd: dim=%d needs %zu bytes of shared memory", dim, smem);
   cudaStream_t st = static_cast<cudaStream_t>(s);
   bf16* dx16 = static_cast<bf16*>(dx_out_bf16);
-#define HCT_LN_BWD(NV, BF)                                                                                     \
+#define HCT_LN_BWD(NV, BF, ST)                                                                                 \
   do {                                                                                                         \
     static bool configured = false;                                                                            \
     if (!configured) {                                                                                         \
-      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
+      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
       configured = true;                                                                                       \
     }                                                                                                          \
-    ln_bwd_kernel<NV, BF><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32, dx16, \
-                                                             dgamma, dbeta, dxsum, rows, dim);                 \
+    ln_bwd_kernel<NV, BF, ST><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32, \
+                                                                 dx16, dgamma, dbeta, dxsum, rows, dim);       \
   } while (0)
+#define HCT_LN_BWD_S(NV, BF) do { if (stages == 3) HCT_LN_BWD(NV, BF, 3); else HCT_LN_BWD(NV, BF, 2); } while (0)
 #define HCT_LN_BWD_D(BF)                                                                                        \
   do {                                                                                                         \
-    if (dim <= 256) HCT_LN_BWD(2, BF); else if (dim <= 768) HCT_LN_BWD(6, BF);                                  \
-    else if (dim <= 1024) HCT_LN_BWD(8, BF); else HCT_LN_BWD(16, BF);                                           \
+    if (dim <= 256) HCT_LN_BWD_S(2, BF); else if (dim <= 768) HCT_LN_BWD_S(6, BF);                              \
+    else if (dim <= 1024) HCT_LN_BWD_S(8, BF); else HCT_LN_BWD_S(16, BF);                                       \
   } while (0)
   if (dy_bf16) HCT_LN_BWD_D(true); else HCT_LN_BWD_D(false);
 #undef HCT_LN_BWD_D
+#undef HCT_LN_BWD_S
 #undef HCT_LN_BWD
   return hct_check_launch("ln_bwd_kernel");
 }
