@@ -37,6 +37,19 @@ if ROOT not in sys.path:
 METRIC = "mae_pretrain_volumes_per_sec"
 UNIT = "volumes/s"
 MAE_FWD_BWD_GFLOP = 282.133      # algorithmic GFLOP per volume, BASELINE.md section 3
+WORKLOAD = ("MAE ViT-B 3D pretraining step (mae_HeadCT.yaml: 96^3x3 volumes, patch 12, mask 0.75, "
+            "enc 12x768 12h, dec 8x768 16h), fwd+loss+bwd+per-param-clip+AdamW")
+
+
+def _gemm_traffic():
+    """DRAM bytes per GEMM launch from the committed ncu pass over one step (profiles/r01_gemm_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+            t = json.load(f)
+        return {"bytes_per_launch": float(t["traffic_bytes_per_launch"]), "over_algorithmic": float(t["traffic_over_algorithmic"]),
+                "source": "profiles/r01_gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 248 GEMM launches of one step)"}
+    except Exception:
+        return None
 
 
 def _peaks():
@@ -131,8 +144,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MAE ViT-B 3D pretraining step (mae_HeadCT.yaml shape), mask 0.75, CPU fp32, batch 2 "
-                                   "(bounded sample of the batch-256 workload)", "patch": 12, "volume": "3x96x96x96"},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "global_batch": args.batch * args.gpus,
+                       "parallelism": f"dp{args.gpus}",
+                       "sample": "reference path on the host cores, fp32: fwd+loss+bwd of a batch of 2 volumes per step "
+                                 "(bounded sample of the batch-%d workload; the reference's optimizer step is not timed)" % args.batch},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -230,6 +245,16 @@ def run_ours(args):
             dev_hu[i % 2].copy_(host_hu[i % n_host], non_blocking=True)
             ready[i % 2].record(copy_stream)
 
+    # diagnostic: what the host link of this box delivers for one step's input (explains e2e when it trails `value`)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(copy_stream):
+        dev_hu[0].copy_(host_hu[0], non_blocking=True)
+        h0.record(copy_stream)
+        dev_hu[0].copy_(host_hu[0], non_blocking=True)
+        h1.record(copy_stream)
+    copy_stream.synchronize()
+    h2d_gbps = host_hu[0].numel() * 2 / 1e9 / (h0.elapsed_time(h1) / 1e3)
+
     e2e_steps = args.steps
     loss_host = torch.empty((e2e_steps,), dtype=torch.float32).pin_memory()   # per-step D2H landing zone
     for e in consumed:
@@ -267,6 +292,7 @@ def run_ours(args):
 
     if rank == 0:
         peaks = _peaks()
+        traffic = _gemm_traffic() if B == 256 else None
         value = B * world * args.steps / (ms / 1e3)
         e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
         achieved = (gemm_fl.value / 1e12) / (gemm_ms.value / 1e3) if gemm_ms.value > 0 else 0.0
@@ -278,15 +304,18 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "MAE ViT-B 3D pretraining step (mae_HeadCT.yaml: 96^3x3 volumes, patch 12, mask 0.75, "
-                                   "enc 12x768 12h, dec 8x768 16h), fwd+loss+bwd+per-param-clip+AdamW"
-                                   + (", DDP grad all-reduce" if world > 1 else ""),
+            "config": {"workload": WORKLOAD + (", DDP grad all-reduce" if world > 1 else ""),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no explicit flush"
                                     % (resident.numel() * 4 / 1e6),
                        "final_loss": final_loss, "host_issue_ms_per_step": host_issue_ms},
             "roofline": {"bound": "tensor", "kernel": "hct_gemm_tcgen05_kernel (all epilogues)", "achieved": achieved,
-                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                         "traffic": (traffic["bytes_per_launch"] if traffic else None),
+                         "traffic_over_algorithmic_bytes": (traffic["over_algorithmic"] if traffic else None),
+                         "traffic_source": (traffic["source"] if traffic else None),
+                         "algorithmic_flops_per_launch": (gemm_fl.value / gemm_n.value if gemm_n.value else None),
+                         "avg_launch_ms": (gemm_ms.value / gemm_n.value if gemm_n.value else None),
                          "peak_source": peaks["src"], "gemm_launches": int(gemm_n.value),
                          "gemm_ms_per_step": gemm_ms.value / args.steps,
                          "gemm_share_of_step": gemm_ms.value / ms if ms > 0 else None,
@@ -294,6 +323,7 @@ def run_ours(args):
                          "step_frac_of_peak": step_tflops / peaks["tflops"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
                     "h2d_bytes_per_step": int(host_hu[0].numel() * 2), "d2h_bytes_per_step": 4,
+                    "h2d_link_gbps_measured": h2d_gbps,
                     "path": "pinned int16 HU -> H2D (copy stream, double buffered) -> MultipleWindowScaleStack (GPU) -> "
                             "MaskedAutoencoderViT.forward/backward -> FusedAdamW -> async D2H of the loss into pinned memory"},
             "gpu_launches": launches_all,

@@ -1,4 +1,4 @@
-"""ncu target: the two GELU-epilogue GEMMs of a decoder block (fc1 + GELU forward, fc2 dgrad * GELU') at B = 64."""
+"""ncu target: the two activation-epilogue GEMMs of a decoder block (fc1 + GELU + GELU' forward, fc2 dgrad * GELU') at B = 64."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -26,8 +26,8 @@ def dgrad(M, N, K, epi):
     return lambda: HF.gemm(dY, W, M=M, N=N, K=K, lda=K, ldb=N, b_mn=True, out=out, ldo=N, epi=epi, aux=aux, ldaux=N, colsum=cs)
 
 
-f = fwd(M, 3072, 768, HF.EPI_GELU_BF16)
-d = dgrad(M, 3072, 768, HF.EPI_DGELU_BF16)
+f = fwd(M, 3072, 768, HF.EPI_GELU_DERIV_BF16)
+d = dgrad(M, 3072, 768, HF.EPI_MUL_BF16)
 for _ in range(3):
     f(); d()
 torch.cuda.synchronize()
