@@ -191,6 +191,9 @@ int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t
  * S %% 128 <= 32 tail rows on the mma.sync kernel; 0: mma.sync kernels only */
 int hct_attention_set_tcgen05(int mode);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
+/* Diagnostics: clock64 event timeline of one CTA of the dK/dV backward kernel.  buf = device buffer of >= 768 int64
+ * (layout: [producer | MMA | softmax warp 0][block][8 events], see tools/attn_dbg.py) or NULL to switch it off. */
+int hct_attention_trace(void* buf);
 int hct_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                       void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd,
                       hct_stream_t stream);
