@@ -12,8 +12,6 @@ dqkv = torch.empty_like(qkv); delta = torch.empty(B, H, S, device=dev); st = str
 call("hct_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, hd, st)
 def bwd():
     call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), B, S, H, hd, st)
-import ctypes
-lib().hct_attention_trace.argtypes = [ctypes.c_void_p]
 for flags in [0]:
     for _ in range(2): bwd()
     torch.cuda.synchronize()
