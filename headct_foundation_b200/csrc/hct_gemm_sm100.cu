@@ -50,6 +50,8 @@ struct GemmParams {
 
 using namespace hct_tc;
 
+__device__ long long* g_gemm_trace = nullptr;   // clock64 timeline of CTA 0 (tools/gemm_dbg.py); nullptr in production
+
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, bool mn_major) {
   return make_sdesc_sw128(saddr, mn_major, MN_CHUNK_BYTES);
 }
@@ -97,6 +99,48 @@ __device__ __forceinline__ float gelu_and_grad_fast(float x, float& grad) {   //
   grad = fmaf(x * 0.3989422804014327f, pdf, fmaf(0.5f, t, 0.5f));
   return fmaf(h, t, h);
 }
+// The same functions over NE elements, written stage by stage (NE independent dependency chains in flight) and with
+// the packed two-lane fp32 instructions of sm_100 (fma.rn.f32x2 & co.): the epilogue of a K = 768 GEMM has ~20 fp32
+// operations per output element against 0.19 tensor-pipe cycles, so the instruction count of this function sets the
+// tile period of the GELU GEMMs.
+template <int NE, bool WITH_GRAD>
+__device__ __forceinline__ void gelu_multi(float (&xs)[NE], float (&grads)[NE]) {
+  static_assert(NE % 2 == 0, "pairs");
+  constexpr int NP = NE / 2;
+  float2 x[NP], x2[NP], q[NP], t[NP];
+#pragma unroll
+  for (int e = 0; e < NP; ++e) x[e] = make_float2(xs[2 * e], xs[2 * e + 1]);
+#pragma unroll
+  for (int e = 0; e < NP; ++e) { x2[e] = __fmul2_rn(x[e], x[e]); x2[e].x = fminf(x2[e].x, 36.0f); x2[e].y = fminf(x2[e].y, 36.0f); }
+#pragma unroll
+  for (int e = 0; e < NP; ++e) q[e] = __ffma2_rn(make_float2(kH3, kH3), x2[e], make_float2(kH2, kH2));
+#pragma unroll
+  for (int e = 0; e < NP; ++e) q[e] = __ffma2_rn(q[e], x2[e], make_float2(kH1, kH1));
+#pragma unroll
+  for (int e = 0; e < NP; ++e) q[e] = __ffma2_rn(q[e], x2[e], make_float2(kH0, kH0));
+#pragma unroll
+  for (int e = 0; e < NP; ++e) { q[e] = __fmul2_rn(x[e], q[e]); t[e].x = tanh_approx(q[e].x); t[e].y = tanh_approx(q[e].y); }
+  if (WITH_GRAD) {
+    constexpr float kE = -0.5f * 1.4426950408889634f, kP = 0.3989422804014327f;
+#pragma unroll
+    for (int e = 0; e < NP; ++e) {
+      x2[e] = __fmul2_rn(x2[e], make_float2(kE, kE));
+      x2[e].x = ex2_approx(x2[e].x); x2[e].y = ex2_approx(x2[e].y);                    // exp(-x^2 / 2)
+    }
+#pragma unroll
+    for (int e = 0; e < NP; ++e) {
+      const float2 cdf = __ffma2_rn(make_float2(0.5f, 0.5f), t[e], make_float2(0.5f, 0.5f));
+      const float2 g = __ffma2_rn(__fmul2_rn(x[e], make_float2(kP, kP)), x2[e], cdf);     // Phi(x) + x phi(x)
+      grads[2 * e] = g.x; grads[2 * e + 1] = g.y;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NP; ++e) {
+    const float2 h = __fmul2_rn(x[e], make_float2(0.5f, 0.5f));
+    const float2 y = __ffma2_rn(h, t[e], h);
+    xs[2 * e] = y.x; xs[2 * e + 1] = y.y;
+  }
+}
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   float x2;
   const float t = tanh_half_arg(x, x2);
@@ -105,6 +149,9 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return fmaf(x * 0.3989422804014327f, pdf, cdf);                          // Phi(x) + x phi(x)
 }
 
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {   // 16-byte aligned, bytes % 16 == 0
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -153,18 +200,25 @@ __device__ __forceinline__ void load_aux_unit(const GemmParams& p, int lane, int
 }
 
 // `pre`: the unit's aux operand already in registers (loaded one unit ahead by the caller), interior units only
+// the four bias values of this lane's column group in a 32-column unit (zero where the epilogue has no bias)
+template <int EPI>
+__device__ __forceinline__ float4 load_bias_unit(const GemmParams& p, int lane, int col0) {
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!EpiTraits<EPI>::uses_aux && EPI != HCT_EPI_ATOMIC_F32) {
+    const int col = col0 + (lane & 7) * 4;
+    if (p.bias != nullptr && col < p.N) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+  }
+  return bias4;
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg, int lane, int row_base, int col0,
-                                               const uint2 (&pre)[8], bool have_pre) {
+                                               const float4 bias4, const uint2 (&pre)[8], bool have_pre) {
   using T = EpiTraits<EPI>;
   // ---- phase 2: lane = (row sub-index, column group); rows handled in two groups of four to bound registers
   const int jj = lane & 7, rsub = lane >> 3;
   const int col = col0 + jj * 4;
   const bool col_ok = col < p.N;                       // N % 8 == 0 -> a group of 4 is all-in or all-out
-  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!T::uses_aux && EPI != HCT_EPI_ATOMIC_F32) {
-    if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-  }
   float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
   // Interior units (all 32 rows and 32 columns inside the matrix, no row remapping) take a path without per-row
   // predicates and with incremental row pointers: the general path below spends ~40 % of its instructions on
@@ -192,10 +246,50 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
       bf16* op = reinterpret_cast<bf16*>(p.out) + r0 * p.ldo + col;
       bf16* op2 = (T::gelu_fwd && p.out2 != nullptr) ? reinterpret_cast<bf16*>(p.out2) + r0 * p.ldo2 + col : nullptr;
       const long long ostep = 4 * p.ldo, ostep2 = 4 * p.ldo2;
+      // all eight staged rows are pulled into registers first: the shared-memory loads are volatile asm, so a load
+      // placed inside the row loop could not move above the previous row's global store and the rows ran strictly
+      // one after the other (one dependent chain, ~5 cycles per instruction)
+      float4 vals[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + rsub;
-        float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+        vals[i] = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+      }
+      if (T::gelu_fwd) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {                  // two rows = eight independent elements per pass
+          float x[8] = {vals[i].x + bias4.x, vals[i].y + bias4.y, vals[i].z + bias4.z, vals[i].w + bias4.w,
+                        vals[i + 1].x + bias4.x, vals[i + 1].y + bias4.y, vals[i + 1].z + bias4.z, vals[i + 1].w + bias4.w};
+          float d[8];
+          if (EPI == HCT_EPI_GELU_BF16 && op2 != nullptr) {
+            uint2 u0, u1;
+            u0.x = pack_bf16x2(x[0], x[1]); u0.y = pack_bf16x2(x[2], x[3]);
+            u1.x = pack_bf16x2(x[4], x[5]); u1.y = pack_bf16x2(x[6], x[7]);
+            *reinterpret_cast<uint2*>(op2 + i * ostep2) = u0;
+            *reinterpret_cast<uint2*>(op2 + (i + 1) * ostep2) = u1;
+          }
+          gelu_multi<8, EPI == HCT_EPI_GELU_DERIV_BF16>(x, d);
+          if (EPI == HCT_EPI_GELU_DERIV_BF16) {
+            uint2 u0, u1;
+            u0.x = pack_bf16x2(d[0], d[1]); u0.y = pack_bf16x2(d[2], d[3]);
+            u1.x = pack_bf16x2(d[4], d[5]); u1.y = pack_bf16x2(d[6], d[7]);
+            *reinterpret_cast<uint2*>(op2 + i * ostep2) = u0;
+            *reinterpret_cast<uint2*>(op2 + (i + 1) * ostep2) = u1;
+          }
+          uint2 u0, u1;
+          u0.x = pack_bf16x2(x[0], x[1]); u0.y = pack_bf16x2(x[2], x[3]);
+          u1.x = pack_bf16x2(x[4], x[5]); u1.y = pack_bf16x2(x[6], x[7]);
+          *reinterpret_cast<uint2*>(op + i * ostep) = u0;
+          *reinterpret_cast<uint2*>(op + (i + 1) * ostep) = u1;
+          if (has_colsum) {
+            const float2 q0 = unpack_bf16x2(u0.x), q1 = unpack_bf16x2(u0.y), q2 = unpack_bf16x2(u1.x), q3 = unpack_bf16x2(u1.y);
+            csum.x += q0.x + q2.x; csum.y += q0.y + q2.y; csum.z += q1.x + q3.x; csum.w += q1.y + q3.y;
+          }
+        }
+      } else
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 v = vals[i];
         if (EPI == HCT_EPI_BF16) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
         if (!T::uses_aux) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
         if (EPI == HCT_EPI_GELU_BF16) {
@@ -230,10 +324,15 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
     } else {
       float* op = reinterpret_cast<float*>(p.out) + r0 * p.ldo + col;
       const long long ostep = 4 * p.ldo;
+      float4 vals[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + rsub;
-        float4 v = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+        vals[i] = ld_shared_f4(stg + r * 128 + ((jj ^ (r & 7)) << 4));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 v = vals[i];
         if (EPI == HCT_EPI_F32 || EPI == HCT_EPI_ATOMIC_F32) { v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha; }
         if (EPI != HCT_EPI_ATOMIC_F32) { v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w; }
         if (EPI == HCT_EPI_RES_F32) { v.x += extra[i].x; v.y += extra[i].y; v.z += extra[i].z; v.w += extra[i].w; }
@@ -444,6 +543,8 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long* trace = (g_gemm_trace != nullptr && blockIdx.x == 0) ? g_gemm_trace : nullptr;
+  // trace layout: [0,512): MMA warp, 8 events per tile; [512, 512+16*64): epilogue warp 4, 16 events per tile
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
@@ -500,7 +601,10 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     for (int w = unit; w < total_work; w += num_units) {
       const int split = w / tiles;
       const int kb0 = split * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, p.total_kb);
+      const int tix = (w - unit) / num_units;
+      if (trace && lane == 0 && tix < 64) trace[tix * 8 + 0] = clock64();
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      if (trace && lane == 0 && tix < 64) trace[tix * 8 + 1] = clock64();
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -521,6 +625,7 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       if (leader) { if (CTAS == 2) tc_commit_2sm(&tfull_bar[acc]); else tc_commit(&tfull_bar[acc]); }
       __syncwarp();
+      if (trace && lane == 0 && tix < 64) trace[tix * 8 + 2] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= FIRST_EPI_WARP) {
@@ -537,18 +642,13 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         // main loop of this tile is still running (one 128-byte line per lane and step)
         const int prow = m0 + q * 32 + lane;
         const int pcol = n0 + half * (BN / 2);
-        if (prow < p.M) {
-          if (EPI == HCT_EPI_RES_F32) {
-            const char* base = reinterpret_cast<const char*>(p.res + static_cast<long long>(prow) * p.ldres + pcol);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (pcol + k * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + k * 128));
-          } else {
-            const char* base = reinterpret_cast<const char*>(p.aux + static_cast<long long>(prow) * p.ldaux + pcol);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              if (pcol + k * 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + k * 128));
-          }
+        if (prow < p.M && pcol < p.N) {
+          // one bulk L2 prefetch per row segment (a plain prefetch.global.L2 only pulls the addressed sector)
+          const int ncols = min(BN / 2, p.N - pcol);
+          if (EPI == HCT_EPI_RES_F32)
+            prefetch_l2_bulk(p.res + static_cast<long long>(prow) * p.ldres + pcol, static_cast<uint32_t>(ncols) * 4u);
+          else
+            prefetch_l2_bulk(p.aux + static_cast<long long>(prow) * p.ldaux + pcol, static_cast<uint32_t>(ncols) * 2u);
         }
       }
       // the bf16 multiplicand of a MUL / DGELU epilogue does not depend on the accumulator: the first unit's rows are
@@ -560,7 +660,11 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         have_cur = unit_interior<EPI>(p, m0 + q * 32, colw0);
         if (have_cur) load_aux_unit(p, lane, m0 + q * 32, colw0, aux_cur);
       }
+      const int tix = (w - unit) / num_units;
+      long long* tr = (trace && warp == FIRST_EPI_WARP && lane == 0 && tix < 64) ? trace + 512 + tix * 16 : nullptr;
+      if (tr) tr[0] = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (tr) tr[1] = clock64();
       tc_fence_after();
       // software pipeline over the warp's four 32-column units: the TMEM load of unit c+1 is in flight while unit c
       // is drained from the staging buffer; the accumulator stage is handed back to the MMA warp as soon as the
@@ -574,8 +678,11 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       if (nunits > 0) tmem_ld32_issue(t0, v);
 #pragma unroll 1
       for (int c = 0; c < nunits; ++c) {
+        const float4 bias4 = load_bias_unit<EPI>(p, lane, colw + c * 32);   // requested before the TMEM wait: off the chain
         tmem_ld_wait();
+        if (tr) tr[2 + c * 3] = clock64();
         epilogue_stage(stg, lane, v);                      // v is dead after staging: reuse it for the next load
+        if (tr) tr[3 + c * 3] = clock64();
         if (c + 1 < nunits) {
           tmem_ld32_issue(t0 + (c + 1) * 32, v);
         } else {
@@ -587,12 +694,13 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           have_nxt = unit_interior<EPI>(p, m0 + q * 32, colw + (c + 1) * 32);
           if (have_nxt) load_aux_unit(p, lane, m0 + q * 32, colw + (c + 1) * 32, aux_nxt);
         }
-        epilogue_drain<EPI>(p, stg, lane, m0 + q * 32, colw + c * 32, aux_cur, have_cur);
+        epilogue_drain<EPI>(p, stg, lane, m0 + q * 32, colw + c * 32, bias4, aux_cur, have_cur);
         if (EpiTraits<EPI>::uses_aux) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) aux_cur[i] = aux_nxt[i];
           have_cur = have_nxt;
         }
+        if (tr) tr[4 + c * 3] = clock64();
       }
       if (nunits == 0) {
         tc_fence_before(); __syncwarp();
@@ -699,6 +807,10 @@ int hct_make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long inner, lo
 }
 
 extern "C" int hct_gemm_set_cta_pair(int enable) { g_gemm_ctas = enable ? 2 : 1; return HCT_OK; }
+extern "C" int hct_gemm_trace(void* buf) {     // device buffer of >= 1536 int64 (or NULL): timeline of CTA 0
+  long long* p = static_cast<long long*>(buf);
+  return cudaMemcpyToSymbol(g_gemm_trace, &p, sizeof(p)) == cudaSuccess ? HCT_OK : HCT_ERR_CUDA;
+}
 
 extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

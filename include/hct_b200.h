@@ -85,6 +85,9 @@ typedef struct hct_gemm_desc {
 int hct_gemm_bf16(const hct_gemm_desc* desc, hct_stream_t stream);
 /* 1 (default): CTA-pair kernel (tcgen05 cta_group::2, 256x256 tiles); 0: single-CTA kernel (128x256 tiles). */
 int hct_gemm_set_cta_pair(int enable);
+/* Diagnostics: clock64 timeline of CTA 0 (MMA warp and first epilogue warp, per tile); buf = device buffer of
+ * >= 1536 int64 or NULL to switch it off (tools/gemm_dbg.py). */
+int hct_gemm_trace(void* buf);
 
 /* ---------------------------------------------------------------------------------------------
  * Row kernels (HBM-bound)
