@@ -177,13 +177,14 @@ __global__ void center_ema_kernel(float* __restrict__ center, const float* __res
 
 // ------------------------------------------------------------------ multi-tensor kernels (grid.y = tensor index)
 __global__ void ema_multi_kernel(const long long* __restrict__ table, float m) {
-  const long long* e = table + 3LL * blockIdx.y;
+  const long long* e = table + 4LL * blockIdx.y;
   float* pk = reinterpret_cast<float*>(e[0]);
   const float* pq = reinterpret_cast<const float*>(e[1]);
   const long long n = e[2];
+  bf16* sh = reinterpret_cast<bf16*>(e[3]);              // bf16 shadow of the teacher tensor (GEMM operand copy) or null
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const float om = 1.f - m;
-  if (((reinterpret_cast<uintptr_t>(pk) | reinterpret_cast<uintptr_t>(pq)) & 15) == 0) {
+  if (((reinterpret_cast<uintptr_t>(pk) | reinterpret_cast<uintptr_t>(pq)) & 15) == 0 && (reinterpret_cast<uintptr_t>(sh) & 7) == 0) {
     const long long n4 = n >> 2;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
       float4 a = reinterpret_cast<float4*>(pk)[i];
@@ -191,18 +192,28 @@ __global__ void ema_multi_kernel(const long long* __restrict__ table, float m) {
       // param_k.mul_(m).add_((1 - m) * param_q)   (misc.py:397)
       a.x = a.x * m + om * q.x; a.y = a.y * m + om * q.y; a.z = a.z * m + om * q.z; a.w = a.w * m + om * q.w;
       reinterpret_cast<float4*>(pk)[i] = a;
+      if (sh != nullptr) {
+        uint2 u; u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+        reinterpret_cast<uint2*>(sh)[i] = u;
+      }
     }
-    for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-      pk[i] = pk[i] * m + om * pq[i];
+    for (long long i = (n4 << 2) + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float a = pk[i] * m + om * pq[i];
+      pk[i] = a;
+      if (sh != nullptr) sh[i] = __float2bfloat16(a);
+    }
   } else {
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-      pk[i] = pk[i] * m + om * pq[i];
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float a = pk[i] * m + om * pq[i];
+      pk[i] = a;
+      if (sh != nullptr) sh[i] = __float2bfloat16(a);
+    }
   }
 }
 
 __global__ void grad_sqnorm_multi_kernel(const long long* __restrict__ table, float* __restrict__ norms) {
   __shared__ float red[33];
-  const long long* e = table + 5LL * blockIdx.y;
+  const long long* e = table + 6LL * blockIdx.y;
   const float* g = reinterpret_cast<const float*>(e[1]);
   const long long n = e[4];
   float s = 0.f;
@@ -214,12 +225,13 @@ __global__ void grad_sqnorm_multi_kernel(const long long* __restrict__ table, fl
 
 __global__ void adamw_multi_kernel(const long long* __restrict__ table, const float* __restrict__ sqnorms, float clip,
                                    float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
-  const long long* e = table + 5LL * blockIdx.y;
+  const long long* e = table + 6LL * blockIdx.y;
   float* p = reinterpret_cast<float*>(e[0]);
   const float* g = reinterpret_cast<const float*>(e[1]);
   float* m = reinterpret_cast<float*>(e[2]);
   float* v = reinterpret_cast<float*>(e[3]);
   const long long n = e[4];
+  bf16* sh = reinterpret_cast<bf16*>(e[5]);              // bf16 shadow of the parameter (GEMM operand copy) or null
   float coef = 1.f;
   if (clip > 0.f) {
     // clip_coef = clip / (||g|| + 1e-6), applied per tensor when < 1 (misc.py:379-382)
@@ -236,6 +248,7 @@ __global__ void adamw_multi_kernel(const long long* __restrict__ table, const fl
     m[i] = mi; v[i] = vi;
     pi -= step_size * mi / (sqrtf(vi) / bc2_sqrt + eps);
     p[i] = pi;
+    if (sh != nullptr) sh[i] = __float2bfloat16(pi);     // the next forward's GEMM operand, refreshed in the same pass
   }
 }
 

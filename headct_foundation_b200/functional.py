@@ -48,6 +48,24 @@ def cast_f32(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def shadow_of(p: torch.Tensor) -> Optional[torch.Tensor]:
+    """The cached bf16 copy of a parameter if one exists for its current storage (regardless of version)."""
+    hit = getattr(p, _W16_ATTR, None)
+    if hit is not None and hit[0] == p.data_ptr() and hit[2].numel() == p.numel():
+        return hit[2]
+    return None
+
+
+def mark_updated(params: Sequence[torch.Tensor], refreshed: Sequence[Optional[torch.Tensor]]) -> None:
+    """Called by the multi-tensor kernels' hosts after they changed parameters through raw pointers: bump the autograd
+    version counters (as an in-place torch op would) and re-key the bf16 copies the kernel has just rewritten, so that
+    `w16` neither serves a stale copy nor recasts a fresh one."""
+    torch.autograd.graph.increment_version(list(params))
+    for p, t in zip(params, refreshed):
+        if t is not None:
+            setattr(p, _W16_ATTR, (p.data_ptr(), p._version, t))
+
+
 def w16(p: torch.Tensor) -> torch.Tensor:
     """bf16 copy of a (2-D viewable) fp32 weight, cached on (data_ptr, version)."""
     _require_cuda(p, "weight")
@@ -739,11 +757,14 @@ _EMA_TABLES: Dict[Tuple[int, int], Tuple[Tuple[int, ...], torch.Tensor]] = {}
 def ema_update(student_params: Sequence[torch.Tensor], teacher_params: Sequence[torch.Tensor], m: float) -> None:
     """_update_momentum_encoder (misc.py:386-397) as ONE launch over all parameter tensors."""
     ptrs: List[int] = []
+    shadows: List[Optional[torch.Tensor]] = []
     for pq, pk in zip(student_params, teacher_params):
         _require_cuda(pk, "teacher parameter")
         if pq.dtype != F32 or pk.dtype != F32 or not pq.is_contiguous() or not pk.is_contiguous():
             raise RuntimeError("ema_update expects contiguous fp32 parameters")
-        ptrs += [pk.data_ptr(), pq.data_ptr(), pk.numel()]
+        sh = shadow_of(pk)
+        shadows.append(sh)
+        ptrs += [pk.data_ptr(), pq.data_ptr(), pk.numel(), 0 if sh is None else sh.data_ptr()]
     if not ptrs:
         return
     dev = teacher_params[0].device
@@ -751,11 +772,12 @@ def ema_update(student_params: Sequence[torch.Tensor], teacher_params: Sequence[
     sig = tuple(ptrs)
     hit = _EMA_TABLES.get(key)
     if hit is None or hit[0] != sig:
-        table = torch.tensor(ptrs, dtype=torch.int64).view(-1, 3).to(dev)
+        table = torch.tensor(ptrs, dtype=torch.int64).view(-1, 4).to(dev)
         _EMA_TABLES[key] = (sig, table)
     else:
         table = hit[1]
     call("hct_ema_multi", table.data_ptr(), table.shape[0], float(m), stream_ptr(dev))
+    mark_updated(list(teacher_params), shadows)
 
 
 def window_scale_stack(hu: torch.Tensor, windows=((40, 80), (80, 200), (600, 2800)), out_dtype=F32) -> torch.Tensor:

@@ -13,6 +13,7 @@ from typing import Optional
 import torch
 
 from ._cabi import call, stream_ptr
+from .functional import mark_updated, shadow_of
 
 
 class FusedAdamW(torch.optim.Optimizer):
@@ -24,6 +25,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def _table(self, gi, group):
         ps = [p for p in group["params"] if p.grad is not None]
         rows = []
+        shadows = []
         for p in ps:
             if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or not p.is_cuda:
                 raise RuntimeError("FusedAdamW expects fp32 CUDA parameters and gradients")
@@ -35,7 +37,10 @@ class FusedAdamW(torch.optim.Optimizer):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             if g is not p.grad:
                 p.grad = g
-            rows.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
+            sh = shadow_of(p)        # bf16 GEMM-operand copy, rewritten by the AdamW launch itself
+            shadows.append(sh)
+            rows.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                         0 if sh is None else sh.data_ptr()))
         sig = tuple(rows)
         hit = self._tables.get(gi)
         if hit is None or hit[0] != sig:
@@ -44,7 +49,7 @@ class FusedAdamW(torch.optim.Optimizer):
             norms = torch.empty(len(rows), dtype=torch.float32, device=dev)
             hit = (sig, table, norms)
             self._tables[gi] = hit
-        return ps, hit[1], hit[2]
+        return ps, hit[1], hit[2], shadows
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -55,7 +60,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             if not any(p.grad is not None for p in group["params"]):
                 continue
-            ps, table, norms = self._table(gi, group)
+            ps, table, norms, shadows = self._table(gi, group)
             step = int(self.state[ps[0]]["step"].item()) + 1
             for p in ps:
                 self.state[p]["step"] += 1
@@ -66,4 +71,5 @@ class FusedAdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             call("hct_adamw_multi", table.data_ptr(), table.shape[0], norms.data_ptr(), clip, float(group["lr"]),
                  float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), step, st)
+            mark_updated(ps, shadows)     # the kernel wrote parameters (and their bf16 copies) through raw pointers
         return loss

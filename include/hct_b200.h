@@ -228,13 +228,15 @@ int hct_dino_loss(const float* student, const float* teacher, const float* cente
 int hct_center_ema(float* center, const float* batch_center_sum, float denom, float momentum,
                    int32_t K, hct_stream_t stream);
 /* _update_momentum_encoder (misc.py:386-397): one launch over a device table of n tensors.
- * table: int64 [n, 3] = {teacher_ptr, student_ptr, numel}. p_k = m*p_k + (1-m)*p_q (fp32). */
+ * table: int64 [n, 4] = {teacher_ptr, student_ptr, numel, teacher_bf16_shadow_ptr or 0}. p_k = m*p_k + (1-m)*p_q (fp32);
+ * when the shadow pointer is set the bf16 copy of the new p_k (the GEMM operand of the next forward) is written too. */
 int hct_ema_multi(const int64_t* table, int32_t n, float m, hct_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Train-step glue: per-parameter clip (misc.py:374-383) + AdamW
  * (optimizers.py:354-360) as one multi-tensor launch each.
- * table: int64 [n, 5] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel}.
+ * table: int64 [n, 6] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel, param_bf16_shadow_ptr or 0};
+ * the AdamW launch also refreshes the bf16 copy of every updated parameter that has one.
  * norms_ws: fp32 [n] workspace receiving each gradient's SQUARED L2 norm.
  * ------------------------------------------------------------------------------------------- */
 int hct_grad_norms_multi(const int64_t* table, int32_t n, float* norms_ws, hct_stream_t stream);

@@ -376,10 +376,14 @@ def test_ema_and_adamw_multi(cuda, HF):
     sp = [torch.randn(*s, generator=g) for s in shapes]; tp = [torch.randn(*s, generator=g) for s in shapes]
     tr = [t.clone() for t in tp]
     O.ema_update(tr, sp, 0.996)
-    tc = [t.to(cuda) for t in tp]
+    tc = [torch.nn.Parameter(t.to(cuda)) for t in tp]
+    w = HF.w16(tc[2])                                     # a cached bf16 copy exists for the 2-D weight
+    v0 = tc[2]._version
     HF.ema_update([s.to(cuda) for s in sp], tc, 0.996)
     for a, b in zip(tc, tr):
-        assert _rel(a.cpu(), b) < 1e-6
+        assert _rel(a.detach().cpu(), b) < 1e-6
+    assert tc[2]._version > v0                            # raw-pointer update is visible to version-keyed caches
+    assert HF.w16(tc[2]) is w and torch.equal(w, tc[2].detach().bfloat16())     # ... and the copy was refreshed in place
     # per-parameter clip + AdamW, two steps
     ps = [torch.randn(*s, generator=g) for s in shapes]
     gs = [torch.randn(*s, generator=g) * (10.0 if i % 2 else 0.01) for i, s in enumerate(shapes)]
@@ -387,8 +391,10 @@ def test_ema_and_adamw_multi(cuda, HF):
     mr = [torch.zeros_like(p) for p in ps]; vr = [torch.zeros_like(p) for p in ps]
     pc = [p.to(cuda) for p in ps]; gc = [x.to(cuda) for x in gs]
     mc = [torch.zeros_like(p) for p in pc]; vc = [torch.zeros_like(p) for p in pc]
-    table = torch.tensor([[p.data_ptr(), x.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()]
-                          for p, x, m, v in zip(pc, gc, mc, vc)], dtype=torch.int64, device=cuda)
+    # bf16 shadows (the GEMM operand copies) for every second tensor: the AdamW launch must keep them current
+    sh = [torch.zeros(p.shape, dtype=torch.bfloat16, device=cuda) if i % 2 == 0 else None for i, p in enumerate(pc)]
+    table = torch.tensor([[p.data_ptr(), x.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 0 if h is None else h.data_ptr()]
+                          for p, x, m, v, h in zip(pc, gc, mc, vc, sh)], dtype=torch.int64, device=cuda)
     norms = torch.empty(len(pc), device=cuda)
     for step in (1, 2):
         gclip = [x.clone() for x in gr]
@@ -400,3 +406,6 @@ def test_ema_and_adamw_multi(cuda, HF):
              stream_ptr(cuda))
     for a, b in zip(pc, pr):
         assert _rel(a.cpu(), b) < 1e-5
+    for a, h in zip(pc, sh):
+        if h is not None:
+            assert torch.equal(h, a.bfloat16())

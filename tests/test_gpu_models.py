@@ -212,3 +212,37 @@ def test_dino_head_full_size(cuda):
     assert abs(crit.center.double().sum().item() - float(gold["center1_sum"])) < 2e-2 * abs(float(gold["center1_sum"])) + 1e-3
     loss.backward()
     assert hs.last_layer.weight_v.grad is not None and hs.last_layer.weight_g.grad is None
+
+
+def test_training_steps_use_updated_weights(cuda):
+    """After FusedAdamW steps (parameters and their bf16 GEMM copies are rewritten through raw pointers) the next
+    forward must be the forward of the UPDATED fp32 weights: compare with the oracle evaluated on state_dict()."""
+    import headct_foundation_b200 as H
+    from headct_foundation_b200.optim import FusedAdamW
+    from oracle import headct_oracle as O, synth
+    gold = np.load(os.path.join(GOLD, "mae_small.npz"))
+    cfg = json.loads(str(gold["cfg"]))
+    model, _ = _mae(cfg, int(gold["w_seed"]), cuda)
+    x = synth.volume(4, cfg["in_chans"], cfg["input_size"], 5).to(cuda)
+    L = model.patch_embedding.n_patches
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05,
+                     clip_grad=3.0)
+    losses = []
+    for step in range(6):
+        noise = synth.noise(4, L, seed=100)              # same mask every step: the loss must go down
+        model.noise_override = noise.to(cuda)
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = model(x)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    noise = synth.noise(4, L, seed=999)
+    model.noise_override = noise.to(cuda)
+    with torch.no_grad():
+        got = model(x)[0].item()
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    want = O.mae_forward(sd, x.cpu(), noise, patch=(cfg["patch_size"],) * 3, mask_ratio=cfg["mask_ratio"],
+                         enc_heads=cfg["encoder_num_heads"], dec_heads=cfg["decoder_num_heads"],
+                         norm_pix=cfg["norm_pix_loss"])["loss"].item()
+    assert abs(got - want) <= 1e-2 * abs(want), (got, want, losses)
+    assert losses[-1] < losses[0]                       # and the optimisation actually moves the loss
