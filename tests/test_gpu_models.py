@@ -187,6 +187,17 @@ def test_dino_step_small(cuda):
     H.update_momentum_encoder(student, teacher, float(gold["ema_momentum"]))
     got = dict(teacher.named_parameters())["backbone.cls_token"].detach().cpu()
     assert _rel(got, torch.from_numpy(gold["ema_cls_token"])) < 1e-6
+    # the EMA launch rewrites the teacher's bf16 GEMM copies: a strongly moved teacher (m = 0.5) must give the output
+    # of a freshly built module holding the same fp32 weights, not the output of its previous weights
+    H.update_momentum_encoder(student, teacher, 0.5)
+    with torch.no_grad():
+        t_after = teacher(crops[:2])["dino_output"]
+    fresh = H.MultiCropWrapper(H.ViT(**vcfg), H.DINOHead(**hcfg)).to(cuda).train()
+    fresh.load_state_dict(teacher.state_dict(), strict=True)
+    with torch.no_grad():
+        t_fresh = fresh(crops[:2])["dino_output"]
+    assert torch.equal(t_after, t_fresh)
+    assert _rel(t_after, t_out) > 1e-3
 
 
 def test_dino_head_full_size(cuda):
