@@ -20,6 +20,7 @@ class DINOLoss(nn.Module):
             np.linspace(warmup_teacher_temp, teacher_temp, warmup_teacher_temp_epochs),
             np.ones(nepochs - warmup_teacher_temp_epochs) * teacher_temp))
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, student_output, teacher_output, epoch):
         temp = float(self.teacher_temp_schedule[epoch])
         with torch.autocast(device_type="cuda", enabled=False):

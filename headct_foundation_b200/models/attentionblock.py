@@ -21,6 +21,7 @@ class LoraLinear(nn.Module):
         self.lora_matrix_B = nn.Parameter(torch.zeros(out_features, r))
         self.lora_matrix_A = nn.Parameter(torch.randn(r, in_features))
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x):
         return torch.nn.functional.linear(x, torch.matmul(self.lora_matrix_B, self.lora_matrix_A))
 
@@ -39,6 +40,7 @@ class MLPBlock(nn.Module):
         self.drop1 = nn.Dropout(dropout_rate)
         self.drop2 = self.drop1
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x):
         h = HF.LinearFn.apply(x, self.linear1.weight, self.linear1.bias, True, False)
         y = HF.LinearFn.apply(h, self.linear2.weight, self.linear2.bias, False, False)
@@ -60,6 +62,7 @@ class SelfAttention(nn.Module):
             self.lora_v = LoraLinear(hidden_size, hidden_size, r=128)
         self.dropout = dropout
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x, attn_mask=None):
         if attn_mask is not None or self.lora or (self.dropout > 0 and self.training):
             raise NotImplementedError("attn_mask / LoRA / dropout are outside the accelerated path "
@@ -88,6 +91,7 @@ class AttentionBlock(nn.Module):
         self.ffn_norm = norm_layer(hidden_size)
         self.attn = SelfAttention(hidden_size, num_heads, dropout=dropout_rate, qkv_proj_bias=qkv_bias, lora=lora)
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, hidden_states, residual=None):
         if self.attn.lora or (self.dropout_rate > 0 and self.training):
             raise NotImplementedError("LoRA / dropout are outside the accelerated path")

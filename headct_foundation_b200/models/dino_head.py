@@ -18,6 +18,7 @@ class WeightNormLinear(nn.Module):
         self.weight_g = nn.Parameter(w.norm(2, dim=1, keepdim=True))
         self.weight_v = nn.Parameter(w.clone())
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x16):
         return HF.WeightNormLinearFn.apply(x16, self.weight_g, self.weight_v)
 
@@ -50,6 +51,7 @@ class DINOHead(nn.Module):
             if m.bias is not None:
                 nn.init.constant_(m.bias, 0)
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x):
         with torch.autocast(device_type="cuda", enabled=False):
             linears = [self.mlp] if isinstance(self.mlp, nn.Linear) else [m for m in self.mlp if isinstance(m, nn.Linear)]

@@ -83,6 +83,7 @@ class MaskedAutoencoderViT(nn.Module):
             nn.init.constant_(m.weight, 1.0)
 
     # ---- layout helpers (mae.py:150-192); pure index shuffles, used outside the training step only
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def patchify(self, x: Tensor) -> Tensor:
         B, C, H, W, D = x.shape
         ph, pw, pd = self.patch_size
@@ -90,6 +91,7 @@ class MaskedAutoencoderViT(nn.Module):
         x = x.reshape(B, C, gh, ph, gw, pw, gd, pd).permute(0, 2, 4, 6, 3, 5, 7, 1)
         return x.reshape(B, gh * gw * gd, ph * pw * pd * C)
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def unpatchify(self, x: Tensor, x_ori: Tensor) -> Tensor:
         B, C, H, W, D = x_ori.shape
         ph, pw, pd = self.patch_size
@@ -105,6 +107,7 @@ class MaskedAutoencoderViT(nn.Module):
             noise = torch.rand(N, L, device=device)     # same generator call, same order as the reference (mae.py:206)
         return HF.mask_indices(noise.to(device), len_keep)
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def random_masking(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
         N, L, D = x.shape
         ids_restore, ids_keep, mask = self._draw_indices(N, L, x.device)
@@ -113,6 +116,7 @@ class MaskedAutoencoderViT(nn.Module):
 
     # ---- encoder (mae.py:220-242).  Only the kept 25 % of the patches are ever embedded: the result equals
     # patch-embedding everything and gathering, at a quarter of the GEMM work.
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward_encoder(self, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         with torch.autocast(device_type="cuda", enabled=False):
             N = x.shape[0]
@@ -136,15 +140,18 @@ class MaskedAutoencoderViT(nn.Module):
         h = HF.LayerNormFn.apply(t, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm.eps, True)
         return HF.LinearFn.apply(h, self.decoder_pred.weight, self.decoder_pred.bias, False, False)
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward_decoder(self, x: Tensor, ids_restore: Tensor) -> Tensor:
         with torch.autocast(device_type="cuda", enabled=False):
             return self._decode_full(x, ids_restore)[:, 1:, :]
 
     # ---- loss (mae.py:277-301)
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward_loss(self, imgs: Tensor, pred: Tensor, mask: Tensor) -> Tensor:
         with torch.autocast(device_type="cuda", enabled=False):
             return HF.MaeLossFn.apply(pred.contiguous(), imgs, mask, self.patch_size[0], self.norm_pix_loss, False, 0)
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x: Tensor) -> Tuple[Tensor, None, None]:
         latent, mask, ids_restore = self.forward_encoder(x)
         with torch.autocast(device_type="cuda", enabled=False):

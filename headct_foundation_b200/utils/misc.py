@@ -18,6 +18,7 @@ class MultiCropWrapper(nn.Module):
         self.backbone = backbone
         self.head = head
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x):
         if not isinstance(x, list):
             x = [x]

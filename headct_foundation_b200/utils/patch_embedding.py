@@ -100,5 +100,6 @@ class PatchEmbeddingBlock(nn.Module):
         return HF.EmbedFn.apply(x, pe.weight, pe.bias, self.position_embeddings, prefix, ids_keep,
                                 self.patch_size[0])
 
+    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.embed(x)

@@ -257,3 +257,28 @@ def test_training_steps_use_updated_weights(cuda):
                          norm_pix=cfg["norm_pix_loss"])["loss"].item()
     assert abs(got - want) <= 1e-2 * abs(want), (got, want, losses)
     assert losses[-1] < losses[0]                       # and the optimisation actually moves the loss
+
+
+def test_torch_compile_wrapping_keeps_working(cuda):
+    """main_downstream.py:162 wraps the model in torch.compile.  The drop-in modules are opaque to the tracer (their
+    bodies enqueue C-ABI launches): the compiled wrapper must run and give the eager results, forward and backward."""
+    import headct_foundation_b200 as H
+    cfg = dict(in_chans=3, img_size=(24, 24, 24), patch_size=(12, 12, 12), hidden_size=96, mlp_dim=192, num_layers=2,
+               num_heads=2, pos_embed="sincos", qkv_bias=True)
+    torch.manual_seed(0)
+    m = H.ViT(**cfg).to(cuda).train()
+    clf = H.LinearClassifier(96, 2).to(cuda)
+    x = torch.rand(4, 3, 24, 24, 24, device=cuda)
+    y = torch.tensor([0, 1, 1, 0], device=cuda)
+
+    def step(model):
+        for p in m.parameters():
+            p.grad = None
+        tokens, hidden = model(x)
+        loss = torch.nn.functional.cross_entropy(clf(tokens[:, 0]), y)
+        loss.backward()
+        return loss.item(), tokens.detach().clone(), m.blocks[0].attn.qkv.weight.grad.detach().clone()
+
+    l0, t0, g0 = step(m)
+    l1, t1, g1 = step(torch.compile(m))
+    assert l0 == l1 and torch.equal(t0, t1) and torch.equal(g0, g1)
