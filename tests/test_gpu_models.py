@@ -282,3 +282,60 @@ def test_torch_compile_wrapping_keeps_working(cuda):
     l0, t0, g0 = step(m)
     l1, t1, g1 = step(torch.compile(m))
     assert l0 == l1 and torch.equal(t0, t1) and torch.equal(g0, g1)
+
+
+def test_reference_engine_step_with_amp_gradscaler_and_torch_adamw(cuda):
+    """The reference's own training step around the drop-in model (engine_pretrain_mae.py:52-86): fp16 autocast +
+    GradScaler, per-parameter clip_gradients with .item() (misc.py:374-383), stock torch.optim.AdamW.  Two steps must
+    follow the fp32 oracle trained the same way on the CPU (loss within 1e-2, updated weights aligned)."""
+    import headct_foundation_b200 as H
+    from oracle import headct_oracle as O, synth
+    gold = np.load(os.path.join(GOLD, "mae_small.npz"))
+    cfg = json.loads(str(gold["cfg"]))
+    model, sd0 = _mae(cfg, int(gold["w_seed"]), cuda)
+    x = synth.volume(4, cfg["in_chans"], cfg["input_size"], 5)
+    L = model.patch_embedding.n_patches
+    kw = dict(patch=(cfg["patch_size"],) * 3, mask_ratio=cfg["mask_ratio"], enc_heads=cfg["encoder_num_heads"],
+              dec_heads=cfg["decoder_num_heads"], norm_pix=cfg["norm_pix_loss"])
+
+    def clip_gradients(params, clip):                     # misc.py:374-383, on any iterable of tensors with .grad
+        for p in params:
+            if p.grad is not None:
+                n = p.grad.data.norm(2)
+                c = clip / (n + 1e-6)
+                if c < 1:
+                    p.grad.data.mul_(c)
+
+    # ---- oracle side: fp32, CPU
+    ref = {k: v.clone().requires_grad_(v.is_floating_point() and k != "decoder_pos_embed") for k, v in sd0.items()}
+    ref_params = [v for v in ref.values() if v.requires_grad]
+    ref_opt = torch.optim.AdamW(ref_params, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    # ---- drop-in side: the engine's AMP recipe
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    scaler = torch.amp.GradScaler("cuda")
+    xc = x.to(cuda)
+    for step in range(2):
+        noise = synth.noise(4, L, seed=300 + step)
+        ref_opt.zero_grad()
+        rl = O.mae_forward(ref, x, noise, **kw)["loss"]
+        rl.backward()
+        clip_gradients(ref_params, 3.0)
+        ref_opt.step()
+
+        model.noise_override = noise.to(cuda)
+        opt.zero_grad()
+        with torch.amp.autocast("cuda", dtype=torch.float16, enabled=True):
+            loss, _, _ = model(xc)
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        clip_gradients(model.parameters(), 3.0)
+        scaler.step(opt)
+        scaler.update()
+        assert abs(loss.item() - rl.item()) <= 1e-2 * abs(rl.item()), (step, loss.item(), rl.item())
+    model.noise_override = None
+    got = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    for k in ("blocks.0.attn.qkv.weight", "decoder_blocks.1.mlp.linear2.weight", "decoder_pred.bias", "cls_token",
+              "patch_embedding.patch_embeddings.weight"):
+        moved = (ref[k].detach() - sd0[k]).norm().item()
+        assert moved > 0
+        assert (got[k] - ref[k].detach()).norm().item() < 0.2 * moved + 1e-6, k      # the UPDATE itself agrees
