@@ -1,6 +1,8 @@
 // MAE-specific HBM-bound kernels: HU windowing, patchify (im2col for Conv3d k=s), random-masking
 // indices (stable rank sort), token gather/scatter, decoder input assembly, masked-MSE loss.
 #include "../../include/hct_b200.h"
+#include <cuda_fp16.h>
+
 #include "hct_common.cuh"
 
 namespace {
@@ -310,6 +312,86 @@ loss_reduce_kernel(const float* __restrict__ per_patch, const float* __restrict_
   if (threadIdx.x == 0) { loss_out[0] = a; loss_out[1] = b; loss_out[2] = a / b; }
 }
 
+// ------------------------------------------------------------------ train-time augmentation of cached volumes
+// RandFlipd x 3 + RandShiftIntensityd of mae3d_transforms (src/data/transforms.py:200-223) on a batch that already sits
+// in HBM: out[v, c, i, j, k] = in[v, c, i', j', k'] + offset[v], with an axis reversed where its flip bit is set.
+// One pass, 16-byte vectors along the innermost axis (reversed in registers when that axis flips).
+template <bool IN_F16>
+__global__ void flip_shift_kernel(const void* __restrict__ in, float* __restrict__ out, const unsigned char* __restrict__ flips,
+                                  const float* __restrict__ offsets, int C, int D0, int D1, int D2) {
+  // one CTA per (sample, channel, i0) plane of D1 x D2 voxels: no per-element 64-bit index arithmetic
+  const int plane = blockIdx.x;                               // (v * C + c) * D0 + i0
+  const int i0 = plane % D0;
+  const int vc = plane / D0;
+  const int v = vc / C;
+  const unsigned f = flips != nullptr ? flips[v] : 0u;
+  const float off = offsets != nullptr ? offsets[v] : 0.f;
+  const int si = (f & 1u) ? D0 - 1 - i0 : i0;
+  const long long src_plane = (static_cast<long long>(vc) * D0 + si) * D1 * D2;
+  const long long dst_plane = static_cast<long long>(plane) * D1 * D2;
+  const int w8n = D2 >> 3;
+  for (int t = threadIdx.x; t < D1 * w8n; t += blockDim.x) {
+    const int j = t / w8n, w8 = t - j * w8n;
+    const int sj = (f & 2u) ? D1 - 1 - j : j, sw = (f & 4u) ? w8n - 1 - w8 : w8;
+    const long long src = src_plane + static_cast<long long>(sj) * D2 + 8 * sw;
+    float x[8];
+    if (IN_F16) {
+      const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(in) + src);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        x[2 * k] = a.x; x[2 * k + 1] = a.y;
+      }
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + src);
+      const float4 b2 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + src + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b2.x; x[5] = b2.y; x[6] = b2.z; x[7] = b2.w;
+    }
+    float4 o0, o1;
+    if (f & 4u) {
+      o0 = make_float4(x[7] + off, x[6] + off, x[5] + off, x[4] + off);
+      o1 = make_float4(x[3] + off, x[2] + off, x[1] + off, x[0] + off);
+    } else {
+      o0 = make_float4(x[0] + off, x[1] + off, x[2] + off, x[3] + off);
+      o1 = make_float4(x[4] + off, x[5] + off, x[6] + off, x[7] + off);
+    }
+    float* dst = out + dst_plane + static_cast<long long>(j) * D2 + 8 * w8;
+    *reinterpret_cast<float4*>(dst) = o0;
+    *reinterpret_cast<float4*>(dst + 4) = o1;
+  }
+}
+
+// RandGaussianSmoothd (transforms.py:228-236): separable Gaussian with one sigma per sample and axis, zero padding.
+// One launch per axis over the n SMOOTHED samples only (prob 0.2): sample s is read from volume in_idx[s] of `in` and
+// written to volume out_idx[s] of `out` (NULL = s), so the three passes run batch -> compact scratch -> compact scratch
+// -> batch without touching the other samples.  `taps` = each sample's kernel for this axis ([n][2 R + 1]).
+// One CTA per (sample, channel, i0) plane; the kernel taps sit in shared memory.
+__global__ void gauss_axis_kernel(const float* __restrict__ in, const int* __restrict__ in_idx, float* __restrict__ out,
+                                  const int* __restrict__ out_idx, const float* __restrict__ taps, int R,
+                                  int C, int D0, int D1, int D2, int axis) {
+  __shared__ float st[129];
+  const int plane = blockIdx.x;                               // (s * C + c) * D0 + i0
+  const int i0 = plane % D0;
+  const int sc = plane / D0;
+  const int s = sc / C, c = sc - s * C;
+  for (int k = threadIdx.x; k < 2 * R + 1; k += blockDim.x) st[k] = taps[static_cast<long long>(s) * (2 * R + 1) + k];
+  __syncthreads();
+  const long long vol = static_cast<long long>(C) * D0 * D1 * D2;
+  const long long off = (static_cast<long long>(c) * D0 + i0) * D1 * D2;
+  const float* src = in + (in_idx != nullptr ? in_idx[s] : s) * vol + off;
+  float* dst = out + (out_idx != nullptr ? out_idx[s] : s) * vol + off;
+  const int n_axis = axis == 0 ? D0 : (axis == 1 ? D1 : D2);
+  const int stride = axis == 0 ? D1 * D2 : (axis == 1 ? D2 : 1);
+  for (int t = threadIdx.x; t < D1 * D2; t += blockDim.x) {
+    const int pos = axis == 0 ? i0 : (axis == 1 ? t / D2 : t % D2);
+    const int lo = max(-R, -pos), hi = min(R, n_axis - 1 - pos);
+    float acc = 0.f;
+    for (int k = lo; k <= hi; ++k) acc = fmaf(st[k + R], src[t + k * stride], acc);
+    dst[t] = acc;
+  }
+}
+
 }  // namespace
 
 extern "C" int hct_window_scale_stack(const void* hu, int hu_i16, void* out, int out_bf16, int64_t nvol, int64_t vox,
@@ -456,4 +538,30 @@ extern "C" int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, cons
                                                           mask_sum, static_cast<bf16*>(dpred), L, C, H, W, D, p,
                                                           norm_pix, pred_prefix_rows);
   return hct_check_launch("mae_loss_kernel<bwd>");
+}
+
+extern "C" int hct_flip_shift(const void* in, int32_t in_f16, float* out, const uint8_t* flip_bits, const float* offsets,
+                              int64_t nvol, int32_t C, int32_t D0, int32_t D1, int32_t D2, hct_stream_t s) {
+  HCT_REQUIRE(C > 0 && D0 > 0 && D1 > 0 && D2 > 0 && D2 % 8 == 0, "flip_shift: bad volume %dx%dx%dx%d (innermost %% 8)", C, D0, D1, D2);
+  HCT_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "flip_shift: pointers must be 16-byte aligned");
+  if (nvol <= 0) return HCT_OK;
+  const long long planes = nvol * C * D0;
+  HCT_REQUIRE(planes <= 2147483647LL, "flip_shift: too many planes (%lld)", planes);
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  if (in_f16) flip_shift_kernel<true><<<static_cast<unsigned>(planes), 256, 0, st>>>(in, out, flip_bits, offsets, C, D0, D1, D2);
+  else flip_shift_kernel<false><<<static_cast<unsigned>(planes), 256, 0, st>>>(in, out, flip_bits, offsets, C, D0, D1, D2);
+  return hct_check_launch("flip_shift_kernel");
+}
+
+extern "C" int hct_gaussian_smooth_axis(const float* in, const int32_t* in_idx, float* out, const int32_t* out_idx,
+                                        const float* taps, int32_t radius, int64_t n, int32_t C, int32_t D0, int32_t D1,
+                                        int32_t D2, int32_t axis, hct_stream_t s) {
+  HCT_REQUIRE(axis >= 0 && axis <= 2 && radius >= 0 && radius <= 64, "gaussian_smooth_axis: axis=%d radius=%d", axis, radius);
+  HCT_REQUIRE(in != out, "gaussian_smooth_axis: in-place filtering is not supported");
+  if (n <= 0) return HCT_OK;
+  const long long planes = n * C * D0;
+  HCT_REQUIRE(planes <= 2147483647LL, "gaussian_smooth_axis: too many planes (%lld)", planes);
+  gauss_axis_kernel<<<static_cast<unsigned>(planes), 256, 0, static_cast<cudaStream_t>(s)>>>(
+      in, in_idx, out, out_idx, taps, radius, C, D0, D1, D2, axis);
+  return hct_check_launch("gauss_axis_kernel");
 }

@@ -22,3 +22,69 @@ class MultipleWindowScaleStack:
         d = dict(data)
         d["image"] = HF.window_scale_stack(d["image"], self.window_sizes, self.out_dtype)
         return d
+
+
+def gaussian_taps(sigma: float, truncated: float = 4.0, radius: int | None = None) -> torch.Tensor:
+    """MONAI `gaussian_1d(sigma, truncated, approx="erf")`: tail = max(int(sigma * truncated + 0.5), 1), weights
+    0.5 (erf((x + 0.5) / (sigma sqrt 2)) - erf((x - 0.5) / (sigma sqrt 2))) clamped at 0 (not renormalised).
+    `radius` pads the kernel with zeros to a common length."""
+    import math
+    tail = max(int(float(sigma) * truncated + 0.5), 1)
+    x = torch.arange(-tail, tail + 1, dtype=torch.float64)
+    t = 0.70710678 / abs(float(sigma))
+    w = (0.5 * ((t * (x + 0.5)).erf() - (t * (x - 0.5)).erf())).clamp(min=0).float()
+    if radius is not None and radius > tail:
+        w = torch.nn.functional.pad(w, (radius - tail, radius - tail))
+    return w
+
+
+class MAE3DTrainAugment:
+    """The random part of `mae3d_transforms(mode='train')` (src/data/transforms.py:195-236) for a batch of cached
+    volumes that already sits in HBM: RandFlipd(prob) on each spatial axis, RandShiftIntensityd(offsets, prob_shift),
+    optionally RandGaussianSmoothd(sigma in [0.5, 1], prob_smooth).  The draws are made on the host with a numpy
+    RandomState (as MONAI does, one set per sample); two launches (+3 for a batch with smoothed samples) apply them.
+    Input fp16 (the cache format) or fp32 [B, C, D0, D1, D2]; output fp32."""
+
+    def __init__(self, prob_flip: float = 0.1, offsets: float = 0.1, prob_shift: float = 0.5, smooth: bool = True,
+                 sigma=(0.5, 1.0), prob_smooth: float = 0.2, seed: int | None = None) -> None:
+        import numpy as np
+        self.prob_flip, self.offsets, self.prob_shift = prob_flip, offsets, prob_shift
+        self.smooth, self.sigma, self.prob_smooth = smooth, tuple(sigma), prob_smooth
+        self.R = np.random.RandomState(seed)
+
+    def randomize(self, batch: int):
+        """Per-sample draws: flip bits (uint8), offsets (fp32), sigmas (fp32 [B, 3], 0 = not smoothed)."""
+        import numpy as np
+        flips = np.zeros(batch, dtype=np.uint8)
+        for k in range(3):
+            flips |= ((self.R.rand(batch) < self.prob_flip).astype(np.uint8) << k)
+        do_shift = self.R.rand(batch) < self.prob_shift
+        offs = np.where(do_shift, self.R.uniform(-self.offsets, self.offsets, batch), 0.0).astype(np.float32)
+        sig = np.zeros((batch, 3), dtype=np.float32)
+        if self.smooth:
+            on = self.R.rand(batch) < self.prob_smooth
+            sig[on] = self.R.uniform(self.sigma[0], self.sigma[1], (int(on.sum()), 3)).astype(np.float32)
+        return torch.from_numpy(flips), torch.from_numpy(offs), torch.from_numpy(sig)
+
+    def apply(self, vol: torch.Tensor, flips: torch.Tensor, offs: torch.Tensor, sig: torch.Tensor) -> torch.Tensor:
+        out = HF.flip_shift(vol, flips, offs)
+        sig = sig.cpu()
+        on = torch.nonzero(sig[:, 0] > 0).flatten()
+        if on.numel() > 0:                                  # only the smoothed samples are filtered (in place)
+            s_on = sig[on].double()                                           # [n, 3]
+            tails = (s_on * 4.0 + 0.5).floor().clamp(min=1)                   # gaussian_1d: max(int(sigma * 4 + 0.5), 1)
+            radius = int(tails.max())
+            x = torch.arange(-radius, radius + 1, dtype=torch.float64)
+            taps = []
+            for k in range(3):                                                # all samples of an axis at once
+                t = (0.70710678 / s_on[:, k]).unsqueeze(1)
+                wk = (0.5 * ((t * (x + 0.5)).erf() - (t * (x - 0.5)).erf())).clamp(min=0)
+                wk = wk * (x.abs().unsqueeze(0) <= tails[:, k].unsqueeze(1))   # each sample's own truncation
+                taps.append(wk.float())
+            HF.gaussian_smooth(out, taps, on.to(torch.int32))
+        return out
+
+    def __call__(self, data: Dict[str, Any]) -> Dict[str, Any]:
+        d = dict(data)
+        d["image"] = self.apply(d["image"], *self.randomize(d["image"].shape[0]))
+        return d

@@ -796,3 +796,44 @@ def window_scale_stack(hu: torch.Tensor, windows=((40, 80), (80, 200), (600, 280
     call("hct_window_scale_stack", hu.data_ptr(), int(hu.dtype == torch.int16), out.data_ptr(), int(out_dtype == BF16),
          nvol, vox, nwin, a_min, a_max, stream_ptr(hu.device))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# 8(f) rank 3: train-time augmentation of cached volumes on the GPU (src/data/transforms.py:195-236)
+# --------------------------------------------------------------------------------------------
+def flip_shift(vol: torch.Tensor, flip_bits: Optional[torch.Tensor], offsets: Optional[torch.Tensor]) -> torch.Tensor:
+    """[B, C, D0, D1, D2] fp16 / fp32 -> fp32: reverse spatial axis k of sample b where bit k of flip_bits[b] is set,
+    add offsets[b].  One pass (CastToTyped + 3 x RandFlipd + RandShiftIntensityd of mae3d_transforms)."""
+    _require_cuda(vol, "volume batch")
+    if vol.dtype not in (F32, torch.float16):
+        vol = vol.float()
+    vol = vol.contiguous()
+    B, Cc, D0, D1, D2 = vol.shape
+    out = torch.empty(vol.shape, dtype=F32, device=vol.device)
+    fb = None if flip_bits is None else flip_bits.to(device=vol.device, dtype=torch.uint8).contiguous()
+    of = None if offsets is None else offsets.to(device=vol.device, dtype=F32).contiguous()
+    call("hct_flip_shift", vol.data_ptr(), int(vol.dtype == torch.float16), out.data_ptr(), ptr(fb), ptr(of), B, Cc, D0,
+         D1, D2, stream_ptr(vol.device))
+    return out
+
+
+def gaussian_smooth(vol: torch.Tensor, taps: Sequence[torch.Tensor], samples: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Separable, zero-padded Gaussian filtering IN PLACE on the listed samples of vol (fp32 [B, C, D0, D1, D2]):
+    taps[k] fp32 [n, 2 R_k + 1] holds each listed sample's kernel for spatial axis k; `samples` int32 [n] (default:
+    all).  Three launches that only touch the listed samples (batch -> scratch -> scratch -> batch)."""
+    _require_cuda(vol, "volume batch")
+    assert vol.is_contiguous() and vol.dtype == F32
+    B, Cc, D0, D1, D2 = vol.shape
+    dev = vol.device
+    idx = None if samples is None else samples.to(device=dev, dtype=torch.int32).contiguous()
+    n = B if idx is None else int(idx.numel())
+    if n == 0:
+        return vol
+    tmp = [torch.empty((n, Cc, D0, D1, D2), dtype=F32, device=dev) for _ in range(2)]
+    route = [(vol, idx, tmp[0], None), (tmp[0], None, tmp[1], None), (tmp[1], None, vol, idx)]
+    for axis, (t, (src, si, dst, di)) in enumerate(zip(taps, route)):
+        t = t.to(device=dev, dtype=F32).contiguous()
+        assert t.shape[0] == n and t.shape[1] % 2 == 1
+        call("hct_gaussian_smooth_axis", src.data_ptr(), ptr(si), dst.data_ptr(), ptr(di), t.data_ptr(),
+             (t.shape[1] - 1) // 2, n, Cc, D0, D1, D2, axis, stream_ptr(dev))
+    return vol

@@ -233,6 +233,24 @@ int hct_center_ema(float* center, const float* batch_center_sum, float denom, fl
 int hct_ema_multi(const int64_t* table, int32_t n, float m, hct_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Train-time augmentation of volumes that already sit in HBM (MAE / ViT chain):
+ * mae3d_transforms, src/data/transforms.py:195-236.  Random draws stay on the host (MONAI draws them with a numpy
+ * RandomState); the kernels apply them.
+ * ------------------------------------------------------------------------------------------- */
+/* CastToTyped(float32) + RandFlipd on spatial axes 0/1/2 + RandShiftIntensityd (transforms.py:195-223):
+ * in: fp16 (in_f16, the cached format of cpu_caching.py) or fp32 [nvol, C, D0, D1, D2]; out fp32 same shape;
+ * flip_bits[v]: bit k set = reverse spatial axis k (NULL = none); offsets[v]: added to every voxel (NULL = 0). */
+int hct_flip_shift(const void* in, int32_t in_f16, float* out, const uint8_t* flip_bits, const float* offsets,
+                   int64_t nvol, int32_t C, int32_t D0, int32_t D1, int32_t D2, hct_stream_t stream);
+/* One axis of RandGaussianSmoothd (transforms.py:228-236; MONAI GaussianFilter is separable, zero-padded), applied to
+ * n samples: sample s is volume in_idx[s] of `in` (NULL: s) and is written to volume out_idx[s] of `out` (NULL: s) --
+ * only the smoothed fraction of a batch is touched.  out[.., p, ..] = sum_k taps[s][k + radius] * in[.., p + k, ..];
+ * taps fp32 [n, 2*radius+1]; volumes fp32 [C, D0, D1, D2]; in != out. */
+int hct_gaussian_smooth_axis(const float* in, const int32_t* in_idx, float* out, const int32_t* out_idx,
+                             const float* taps, int32_t radius, int64_t n, int32_t C, int32_t D0, int32_t D1,
+                             int32_t D2, int32_t axis, hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Train-step glue: per-parameter clip (misc.py:374-383) + AdamW
  * (optimizers.py:354-360) as one multi-tensor launch each.
  * table: int64 [n, 6] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel, param_bf16_shadow_ptr or 0};

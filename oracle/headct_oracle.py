@@ -363,3 +363,44 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, *, lr: flo
     bc2 = 1 - beta2 ** step
     denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
     p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------------------------
+# 8(f) rank 3: the random part of mae3d_transforms(mode='train') (src/data/transforms.py:195-236), CPU restatement.
+# MONAI is not installed here (monai==1.3.2, setup.py:13): the published algorithms are restated -- RandFlip = numpy
+# flip of a spatial axis, RandShiftIntensity = img + offset, GaussianFilter = separable zero-padded convolution with
+# gaussian_1d(sigma, truncated=4, approx="erf").  PARITY UNPINNED against MONAI itself; the draws are inputs.
+# --------------------------------------------------------------------------------------------
+def flip_shift(vol: Tensor, flip_bits: Tensor, offsets: Tensor) -> Tensor:
+    out = vol.float().clone()
+    for b in range(vol.shape[0]):
+        dims = [k + 1 for k in range(3) if (int(flip_bits[b]) >> k) & 1]
+        if dims:
+            out[b] = torch.flip(out[b], dims)
+        out[b] += float(offsets[b])
+    return out
+
+
+def gaussian_kernel_1d(sigma: float, truncated: float = 4.0) -> Tensor:
+    tail = max(int(sigma * truncated + 0.5), 1)
+    x = torch.arange(-tail, tail + 1, dtype=torch.float64)
+    t = 0.70710678 / abs(sigma)
+    return (0.5 * ((t * (x + 0.5)).erf() - (t * (x - 0.5)).erf())).clamp(min=0).float()
+
+
+def gaussian_smooth(vol: Tensor, sigmas: Tensor) -> Tensor:
+    """vol fp32 [B, C, D0, D1, D2]; sigmas [B, 3] (0 = sample not smoothed)."""
+    out = vol.clone()
+    for b in range(vol.shape[0]):
+        if not bool((sigmas[b] > 0).all()):
+            continue
+        x = out[b][:, None]                                  # [C, 1, D0, D1, D2]
+        for axis in range(3):
+            k = gaussian_kernel_1d(float(sigmas[b, axis]))
+            shape = [1, 1, 1, 1, 1]
+            shape[2 + axis] = k.numel()
+            pad = [0, 0, 0]
+            pad[axis] = k.numel() // 2
+            x = torch.nn.functional.conv3d(x, k.view(shape), padding=pad)
+        out[b] = x[:, 0]
+    return out
