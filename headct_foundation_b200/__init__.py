@@ -13,9 +13,10 @@ from .utils.pos_embed import build_sincos_position_embedding
 from .utils.misc import MultiCropWrapper, _update_momentum_encoder, update_momentum_encoder
 from .utils.checkpoint import save_checkpoint, load_model, load_optimizer, interpolate_pos_embed, strip_wrapper_prefixes
 from .losses.losses import DINOLoss
-from .data.transforms import MultipleWindowScaleStack
+from .data.transforms import MultipleWindowScaleStack, MAE3DTrainAugment, ViTTrainAugment, DataAugmentationDINO3D
 
 __all__ = ["MaskedAutoencoderViT", "ViT", "AttentionBlock", "SelfAttention", "MLPBlock", "DINOHead",
            "LinearClassifier", "PatchEmbeddingBlock", "build_sincos_position_embedding", "MultiCropWrapper",
            "update_momentum_encoder", "DINOLoss", "MultipleWindowScaleStack", "save_checkpoint", "load_model",
-           "load_optimizer", "interpolate_pos_embed", "strip_wrapper_prefixes"]
+           "load_optimizer", "interpolate_pos_embed", "strip_wrapper_prefixes", "MAE3DTrainAugment", "ViTTrainAugment",
+           "DataAugmentationDINO3D"]

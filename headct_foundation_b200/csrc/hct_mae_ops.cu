@@ -392,6 +392,94 @@ __global__ void gauss_axis_kernel(const float* __restrict__ in, const int* __res
   }
 }
 
+// ------------------------------------------------------------------ DINO multi-crop (DataAugmentationDINO3D)
+// ResizeWithPadOrCrop + (Center)SpatialCrop + RandSpatialCrop + Resize(mode="area") of src/data/transforms.py:75-105
+// as ONE gather: crop n takes the box [start, start + size) (in SOURCE voxel coordinates; whatever falls outside the
+// source volume is the zero padding of ResizeWithPadOrCrop) of sample src_idx[n] and area-resizes it to T0 x T1 x T2.
+// Area interpolation = adaptive average pooling: out[i] = mean over [floor(i a / T), ceil((i + 1) a / T)) per axis.
+struct CropBox { int sample, s0, s1, s2, n0, n1, n2, flips; };   // flips: bit k = reverse OUTPUT axis k (RandFlip after the resize)
+template <bool IN_F16>
+__global__ void crop_resize_area_kernel(const void* __restrict__ src, const CropBox* __restrict__ boxes,
+                                        const float* __restrict__ offsets, float* __restrict__ out,
+                                        int C, int S0, int S1, int S2, int T0, int T1, int T2) {
+  const int plane = blockIdx.x;                               // (crop * C + c) * T0 + i_out
+  const int i_out = plane % T0;
+  const int nc = plane / T0;
+  const int n = nc / C, c = nc - n * C;
+  const CropBox bx = boxes[n];
+  const float off = offsets != nullptr ? offsets[n] : 0.f;    // RandShiftIntensity after the resize
+  const int i = (bx.flips & 1) ? T0 - 1 - i_out : i_out;
+  const long long vbase = (static_cast<long long>(bx.sample) * C + c) * S0;
+  const int a0 = static_cast<int>((static_cast<long long>(i) * bx.n0) / T0);
+  const int b0 = static_cast<int>((static_cast<long long>(i + 1) * bx.n0 + T0 - 1) / T0);
+  // the part of each averaging window that lies inside the source volume (the rest is zero padding: it only counts
+  // in the divisor), as global index ranges -> no bounds checks in the loops
+  const int g0a = max(bx.s0 + a0, 0), g0b = min(bx.s0 + b0, S0);
+  float* dst = out + static_cast<long long>(plane) * T1 * T2;
+  for (int t = threadIdx.x; t < T1 * T2; t += blockDim.x) {
+    const int j_out = t / T2, k_out = t - j_out * T2;
+    const int j = (bx.flips & 2) ? T1 - 1 - j_out : j_out, k = (bx.flips & 4) ? T2 - 1 - k_out : k_out;
+    const int a1 = (j * bx.n1) / T1, b1 = ((j + 1) * bx.n1 + T1 - 1) / T1;
+    const int a2 = (k * bx.n2) / T2, b2 = ((k + 1) * bx.n2 + T2 - 1) / T2;
+    const int g1a = max(bx.s1 + a1, 0), g1b = min(bx.s1 + b1, S1);
+    const int g2a = max(bx.s2 + a2, 0), g2b = min(bx.s2 + b2, S2);
+    float acc = 0.f;
+    for (int g0 = g0a; g0 < g0b; ++g0) {
+      for (int g1 = g1a; g1 < g1b; ++g1) {
+        const long long row = ((vbase + g0) * S1 + g1) * S2;
+        if (IN_F16) {
+          const __half* r = reinterpret_cast<const __half*>(src) + row;
+          for (int g2 = g2a; g2 < g2b; ++g2) acc += __half2float(__ldg(r + g2));
+        } else {
+          const float* r = reinterpret_cast<const float*>(src) + row;
+          for (int g2 = g2a; g2 < g2b; ++g2) acc += __ldg(r + g2);
+        }
+      }
+    }
+    dst[t] = acc / static_cast<float>((b0 - a0) * (b1 - a1) * (b2 - a2)) + off;
+  }
+}
+
+// RandAdjustContrast (transforms.py:92): ((x - min) / (range + 1e-7))^gamma * range + min over the whole sample.
+// Pass 1: per-sample min / max (ordered-int atomics); pass 2: apply to the samples whose gamma is set (> 0).
+__device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__global__ void minmax_init_kernel(int* __restrict__ mm, int n) {      // {ordered(+inf), ordered(-inf)} per sample
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) { mm[2 * s] = float_ordered(INFINITY); mm[2 * s + 1] = float_ordered(-INFINITY); }
+}
+__global__ void sample_minmax_kernel(const float* __restrict__ x, const float* __restrict__ gamma, int* __restrict__ mm,
+                                     long long per_sample) {
+  const int s = blockIdx.y;
+  if (gamma[s] <= 0.f) return;
+  const float4* p = reinterpret_cast<const float4*>(x + static_cast<long long>(s) * per_sample);
+  float lo = INFINITY, hi = -INFINITY;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < (per_sample >> 2);
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = p[i];
+    lo = fminf(lo, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+    hi = fmaxf(hi, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm + 2 * s, float_ordered(lo)); atomicMax(mm + 2 * s + 1, float_ordered(hi)); }
+}
+__global__ void gamma_kernel(float* __restrict__ x, const float* __restrict__ gamma, const int* __restrict__ mm, long long per_sample) {
+  const int s = blockIdx.y;
+  const float g = gamma[s];
+  if (g <= 0.f) return;
+  const float lo = ordered_float(mm[2 * s]), range = ordered_float(mm[2 * s + 1]) - lo;
+  const float inv = 1.0f / (range + 1e-7f);
+  float4* p = reinterpret_cast<float4*>(x + static_cast<long long>(s) * per_sample);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < (per_sample >> 2);
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 v = p[i];
+    v.x = powf((v.x - lo) * inv, g) * range + lo; v.y = powf((v.y - lo) * inv, g) * range + lo;
+    v.z = powf((v.z - lo) * inv, g) * range + lo; v.w = powf((v.w - lo) * inv, g) * range + lo;
+    p[i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" int hct_window_scale_stack(const void* hu, int hu_i16, void* out, int out_bf16, int64_t nvol, int64_t vox,
@@ -564,4 +652,33 @@ extern "C" int hct_gaussian_smooth_axis(const float* in, const int32_t* in_idx, 
   gauss_axis_kernel<<<static_cast<unsigned>(planes), 256, 0, static_cast<cudaStream_t>(s)>>>(
       in, in_idx, out, out_idx, taps, radius, C, D0, D1, D2, axis);
   return hct_check_launch("gauss_axis_kernel");
+}
+
+extern "C" int hct_crop_resize_area(const void* src, int32_t src_f16, const int32_t* boxes, const float* offsets, float* out, int64_t ncrops,
+                                    int32_t C, int32_t S0, int32_t S1, int32_t S2, int32_t T0, int32_t T1, int32_t T2,
+                                    hct_stream_t s) {
+  HCT_REQUIRE(C > 0 && S0 > 0 && S1 > 0 && S2 > 0 && T0 > 0 && T1 > 0 && T2 > 0, "crop_resize_area: bad shapes");
+  if (ncrops <= 0) return HCT_OK;
+  const long long planes = ncrops * C * T0;
+  HCT_REQUIRE(planes <= 2147483647LL, "crop_resize_area: too many planes (%lld)", planes);
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  const CropBox* bx = reinterpret_cast<const CropBox*>(boxes);
+  if (src_f16) crop_resize_area_kernel<true><<<static_cast<unsigned>(planes), 256, 0, st>>>(src, bx, offsets, out, C, S0, S1, S2, T0, T1, T2);
+  else crop_resize_area_kernel<false><<<static_cast<unsigned>(planes), 256, 0, st>>>(src, bx, offsets, out, C, S0, S1, S2, T0, T1, T2);
+  return hct_check_launch("crop_resize_area_kernel");
+}
+
+extern "C" int hct_adjust_contrast(float* x, const float* gamma, int32_t* minmax_ws, int64_t nsamples, int64_t per_sample,
+                                   hct_stream_t s) {
+  HCT_REQUIRE(per_sample > 0 && per_sample % 4 == 0 && nsamples <= 65535, "adjust_contrast: per_sample=%lld nsamples=%lld",
+              (long long)per_sample, (long long)nsamples);
+  if (nsamples <= 0) return HCT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  minmax_init_kernel<<<static_cast<unsigned>((nsamples + 127) / 128), 128, 0, st>>>(minmax_ws, static_cast<int>(nsamples));
+  const dim3 grid(64, static_cast<unsigned>(nsamples));
+  sample_minmax_kernel<<<grid, 256, 0, st>>>(x, gamma, minmax_ws, per_sample);
+  int rc = hct_check_launch("sample_minmax_kernel");
+  if (rc) return rc;
+  gamma_kernel<<<grid, 256, 0, st>>>(x, gamma, minmax_ws, per_sample);
+  return hct_check_launch("gamma_kernel");
 }

@@ -837,3 +837,39 @@ def gaussian_smooth(vol: torch.Tensor, taps: Sequence[torch.Tensor], samples: Op
         call("hct_gaussian_smooth_axis", src.data_ptr(), ptr(si), dst.data_ptr(), ptr(di), t.data_ptr(),
              (t.shape[1] - 1) // 2, n, Cc, D0, D1, D2, axis, stream_ptr(dev))
     return vol
+
+
+def crop_resize_area(src: torch.Tensor, boxes: torch.Tensor, out_size: Sequence[int],
+                     flip_bits: Optional[torch.Tensor] = None, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DINO crop + Resize(mode='area') (+ the RandFlip / RandShiftIntensity that follow it) as one gather.
+    src fp16/fp32 [B, C, S0, S1, S2]; boxes int [n, 7] = (sample, start0, start1, start2, size0, size1, size2) in source
+    voxel coordinates (outside the volume = zero padding); flip_bits uint8 [n] reverse OUTPUT axes; offsets fp32 [n];
+    returns fp32 [n, C, *out_size]."""
+    _require_cuda(src, "volume batch")
+    if src.dtype not in (F32, torch.float16):
+        src = src.float()
+    src = src.contiguous()
+    B, Cc, S0, S1, S2 = src.shape
+    n = boxes.shape[0]
+    bx = torch.zeros((n, 8), dtype=torch.int32)
+    bx[:, :7] = boxes.to(torch.int32).cpu()
+    if flip_bits is not None:
+        bx[:, 7] = flip_bits.to(torch.int32).cpu()
+    bx = bx.to(src.device)
+    of = None if offsets is None else offsets.to(device=src.device, dtype=F32).contiguous()
+    T0, T1, T2 = (int(v) for v in out_size)
+    out = torch.empty((n, Cc, T0, T1, T2), dtype=F32, device=src.device)
+    call("hct_crop_resize_area", src.data_ptr(), int(src.dtype == torch.float16), bx.data_ptr(), ptr(of), out.data_ptr(), n,
+         Cc, S0, S1, S2, T0, T1, T2, stream_ptr(src.device))
+    return out
+
+
+def adjust_contrast_(vol: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    """In place RandAdjustContrast: per sample ((x - min) / (range + 1e-7))^gamma * range + min where gamma[b] > 0."""
+    _require_cuda(vol, "volume batch")
+    assert vol.is_contiguous() and vol.dtype == F32
+    n = vol.shape[0]
+    g = gamma.to(device=vol.device, dtype=F32).contiguous()
+    ws = torch.empty((2 * n,), dtype=torch.int32, device=vol.device)
+    call("hct_adjust_contrast", vol.data_ptr(), g.data_ptr(), ws.data_ptr(), n, vol.numel() // n, stream_ptr(vol.device))
+    return vol

@@ -250,6 +250,21 @@ int hct_gaussian_smooth_axis(const float* in, const int32_t* in_idx, float* out,
                              const float* taps, int32_t radius, int64_t n, int32_t C, int32_t D0, int32_t D1,
                              int32_t D2, int32_t axis, hct_stream_t stream);
 
+/* DINO multi-crop (DataAugmentationDINO3D, src/data/transforms.py:39-105): ResizeWithPadOrCrop + CenterSpatialCrop +
+ * RandSpatialCrop + Resize(mode="area") of one crop as a single gather, with the RandFlip x 3 + RandShiftIntensity
+ * that follow the resize (transforms.py:61-66) folded in.  boxes: int32 [ncrops, 8] = {sample, start0, start1, start2,
+ * size0, size1, size2, flip_bits}; starts are SOURCE voxel coordinates (negative / past the end = the zero padding of
+ * ResizeWithPadOrCrop); flip bit k reverses OUTPUT axis k; offsets fp32 [ncrops] or NULL is added last.
+ * src fp16 / fp32 [B, C, S0, S1, S2]; out fp32 [ncrops, C, T0, T1, T2].
+ * Area resize = adaptive average pooling, windows [floor(i n / T), ceil((i + 1) n / T)). */
+int hct_crop_resize_area(const void* src, int32_t src_f16, const int32_t* boxes, const float* offsets, float* out, int64_t ncrops,
+                         int32_t C, int32_t S0, int32_t S1, int32_t S2, int32_t T0, int32_t T1, int32_t T2,
+                         hct_stream_t stream);
+/* RandAdjustContrast (transforms.py:92; MONAI AdjustContrast): x <- ((x - min) / (range + 1e-7))^gamma * range + min
+ * per sample, in place, for the samples with gamma[s] > 0.  x fp32 [nsamples, per_sample]; minmax_ws int32 [2 nsamples]. */
+int hct_adjust_contrast(float* x, const float* gamma, int32_t* minmax_ws, int64_t nsamples, int64_t per_sample,
+                        hct_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Train-step glue: per-parameter clip (misc.py:374-383) + AdamW
  * (optimizers.py:354-360) as one multi-tensor launch each.

@@ -404,3 +404,31 @@ def gaussian_smooth(vol: Tensor, sigmas: Tensor) -> Tensor:
             x = torch.nn.functional.conv3d(x, k.view(shape), padding=pad)
         out[b] = x[:, 0]
     return out
+
+
+def crop_resize_area(src: Tensor, boxes: Tensor, out_size) -> Tensor:
+    """DINO crop chain restated with torch: zero-pad/crop by indexing, then F.interpolate(mode='area') -- the op MONAI's
+    Resize(mode='area') calls.  boxes int [n, 7] = (sample, start0..2, size0..2) in source coordinates."""
+    outs = []
+    B, C, S0, S1, S2 = src.shape
+    for b, s0, s1, s2, n0, n1, n2 in boxes.tolist():
+        crop = torch.zeros(C, n0, n1, n2)
+        lo = [max(0, -s0), max(0, -s1), max(0, -s2)]
+        hi = [min(n0, S0 - s0), min(n1, S1 - s1), min(n2, S2 - s2)]
+        if all(h > l for l, h in zip(lo, hi)):
+            crop[:, lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = src[b, :, s0 + lo[0]:s0 + hi[0], s1 + lo[1]:s1 + hi[1],
+                                                                 s2 + lo[2]:s2 + hi[2]].float()
+        outs.append(torch.nn.functional.interpolate(crop[None], size=tuple(out_size), mode="area")[0])
+    return torch.stack(outs)
+
+
+def adjust_contrast(vol: Tensor, gamma: Tensor) -> Tensor:
+    """MONAI AdjustContrast per sample where gamma > 0 (epsilon 1e-7, min / range over the whole sample)."""
+    out = vol.clone()
+    for b in range(vol.shape[0]):
+        g = float(gamma[b])
+        if g > 0:
+            lo = out[b].min()
+            rng = out[b].max() - lo
+            out[b] = ((out[b] - lo) / (rng + 1e-7)) ** g * rng + lo
+    return out

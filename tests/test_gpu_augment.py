@@ -53,3 +53,62 @@ def test_mae3d_train_augment_end_to_end(cuda):
     assert (got - want).abs().max().item() < 1e-6
     out = aug({"image": vol.to(cuda)})["image"]
     assert out.shape == vol.shape and out.dtype == torch.float32 and out.is_cuda
+
+
+def test_crop_resize_area_matches_torch_area_interpolation(cuda):
+    from headct_foundation_b200 import functional as HF
+    from oracle import headct_oracle as O
+    g = torch.Generator().manual_seed(9)
+    src = torch.rand(3, 2, 40, 36, 44, generator=g)
+    boxes = torch.tensor([[0, 0, 0, 0, 40, 36, 44],        # whole volume, downsample
+                          [1, 5, 3, 7, 24, 24, 24],        # interior crop, same size as the target
+                          [2, -6, -4, 10, 30, 50, 40],     # runs over the border on three sides: zero padding
+                          [0, 10, 10, 10, 13, 17, 11],     # small crop, upsampled (area windows of 1-2 voxels)
+                          [1, 38, 0, 0, 9, 36, 44]], dtype=torch.int32)
+    for dt in (torch.float32, torch.float16):
+        s = src.to(dt)
+        got = HF.crop_resize_area(s.to(cuda), boxes, (24, 24, 24)).cpu()
+        want = O.crop_resize_area(s, boxes, (24, 24, 24))
+        assert got.shape == (5, 2, 24, 24, 24)
+        assert (got - want).abs().max().item() < 2e-6
+
+
+def test_adjust_contrast_matches_oracle(cuda):
+    from headct_foundation_b200 import functional as HF
+    from oracle import headct_oracle as O
+    g = torch.Generator().manual_seed(10)
+    vol = torch.rand(5, 3, 16, 16, 16, generator=g) * 1.4 - 0.2
+    gamma = torch.tensor([0.2, 0.0, 1.0, 0.55, 0.0])
+    got = HF.adjust_contrast_(vol.clone().to(cuda), gamma).cpu()
+    want = O.adjust_contrast(vol, gamma)
+    assert torch.equal(got[1], vol[1]) and torch.equal(got[4], vol[4])
+    assert (got - want).abs().max().item() < 2e-6
+
+
+def test_dino_multicrop_end_to_end(cuda):
+    """DataAugmentationDINO3D on a batch: every crop equals the oracle chain (pad/crop -> area resize -> flip -> shift ->
+    smooth / contrast) run with the same draws; a volume smaller than the 224 canvas exercises the zero padding."""
+    from headct_foundation_b200.data.transforms import DataAugmentationDINO3D
+    from oracle import headct_oracle as O
+    aug = DataAugmentationDINO3D((32, 32, 32), global_crops_size=112, local_crops_size=64, local_crops_number=2, seed=3)
+    B = 6
+    vol = torch.rand(B, 2, 200, 180, 230).half()
+    for trial in range(3):                                   # a few draw sets so that smoothing and contrast both occur
+        draws = aug.randomize(B, vol.shape[2:])
+        if bool((draws["sigma"][:, 0] > 0).any()) and bool((draws["gamma"] > 0).any()):
+            break
+    crops = aug.apply(vol.to(cuda), draws)
+    assert len(crops) == 4 and all(c.shape == (B, 2, 32, 32, 32) and c.dtype == torch.float32 for c in crops)
+    bx = draws["boxes"].view(4, B, 7)
+    assert int(bx[:2, :, 4:].min()) >= 112 and int(bx[:2, :, 4:].max()) <= 224        # global crop sizes
+    assert int(bx[2:, :, 4:].min()) >= 64 and int(bx[2:, :, 4:].max()) <= 112         # local crop sizes
+    for cidx in range(4):
+        want = O.crop_resize_area(vol, bx[cidx], (32, 32, 32))
+        want = O.flip_shift(want, draws["flips"].view(4, B)[cidx], draws["offsets"].view(4, B)[cidx])
+        if cidx == 0:
+            want = O.gaussian_smooth(want, draws["sigma"])
+        if cidx == 1:
+            want = O.adjust_contrast(want, draws["gamma"])
+        assert (crops[cidx].cpu() - want).abs().max().item() < 5e-6, cidx
+    out = aug(vol.to(cuda))
+    assert len(out) == 4 and out[0].is_cuda

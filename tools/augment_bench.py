@@ -37,3 +37,19 @@ x32 = vol.float()
 ms3 = timeit(lambda: HF.gaussian_smooth(x32, taps, on.to(dev)))
 gb3 = n_on * 3 * 96 ** 3 * 4 * 2 * 3 / 1e9
 print(f"gaussian (3 axes, {n_on} samples, radius 4): {ms3:.3f} ms  {gb3 / ms3 * 1e3:.0f} GB/s ({gb3 / ms3 * 1e3 / HBM:.2f} of HBM copy bandwidth)")
+
+# ---- DINO multi-crop: 64 cached volumes of 224^3 x 3 (fp16) -> 4 crops of 96^3 each
+from headct_foundation_b200.data.transforms import DataAugmentationDINO3D
+Bd = 64
+src = torch.rand(Bd, 3, 224, 224, 224, device=dev).half()
+dino = DataAugmentationDINO3D((96, 96, 96), 112, 64, 2, seed=0)
+draws = dino.randomize(Bd, src.shape[2:])
+bx = draws["boxes"]
+read_gb = float((bx[:, 4] * bx[:, 5] * bx[:, 6]).double().sum()) * 3 * 2 / 1e9
+write_gb = 4 * Bd * 3 * 96 ** 3 * 4 / 1e9
+msc = timeit(lambda: HF.crop_resize_area(src, draws["boxes"], (96, 96, 96), draws["flips"], draws["offsets"]), n=5)
+print(f"DINO crop+area-resize+flip+shift, {4 * Bd} crops: {msc:.3f} ms  {(read_gb + write_gb) / msc * 1e3:.0f} GB/s "
+      f"({(read_gb + write_gb) / msc * 1e3 / HBM:.2f} of HBM copy bandwidth); algorithmic {read_gb:.2f} GB read + {write_gb:.2f} GB written")
+msd = timeit(lambda: dino.apply(src, draws), n=5)
+print(f"DINO full multi-crop augment B={Bd}: {msd:.3f} ms per batch ({Bd / msd * 1e3:.0f} volumes/s), "
+      f"{int((draws['sigma'][:, 0] > 0).sum())} smoothed, {int((draws['gamma'] > 0).sum())} contrast-adjusted")
