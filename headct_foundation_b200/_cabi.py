@@ -82,6 +82,12 @@ _SIGNATURES = {
     "hct_gemm_trace": [C.c_void_p],
     "hct_profile_collect": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
     "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
+    "hct_lora_shuffle": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
+    "hct_colnorm_stats": [_P, _P, _I64, _I32, _F, _F, _P, _P, _P, _P, _P],
+    "hct_colnorm_apply": [_P, _P, _P, _I32, _F, _P, _P, _I32, _I64, _I32, _P],
+    "hct_colnorm_bwd": [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _P],
+    "hct_pool_attention_fwd": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _P],
+    "hct_pool_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _P],
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("hct_last_error", "hct_abi_version", "hct_launch_count")
 

@@ -16,6 +16,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
               long long rows, int dim, float eps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = dim >> 2;   // float4 per row
+  const bool rms = beta == nullptr;
   for (long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + warp; row < rows;
        row += static_cast<long long>(gridDim.x) * LN_WARPS) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
@@ -26,7 +27,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
       const int c = i * 32 + lane;
       if (c < nv) { v[i] = xr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
     }
-    const float mean = warp_sum(s) / dim;
+    const float mean = rms ? 0.f : warp_sum(s) / dim;     // RMSNorm (layers.py:29-40): no centring
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -46,7 +47,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
       const int c = i * 32 + lane;
       if (c < nv) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        const float4 b = rms ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(reinterpret_cast<const float4*>(beta) + c);
         const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
         const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
         if (y_bf16) {
@@ -120,7 +121,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
     prefetch(row + (LN_BWD_STAGES - 1) * rstride, (stage + LN_BWD_STAGES - 1) % LN_BWD_STAGES);
     asm volatile("cp.async.wait_group %0;" ::"n"(LN_BWD_STAGES - 1) : "memory");
     __syncwarp();
-    const float mu = mean[row], rs = rstd[row];
+    const float mu = mean ? mean[row] : 0.f, rs = rstd[row];      // mean == NULL: RMSNorm backward
     const float* sx = wbuf + stage * stage_floats;
     const float* sr = sx + dim;
     const float* sd = sr + dim;
@@ -148,7 +149,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
         db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
       }
     }
-    const float c1 = warp_sum(s1) / dim, c2 = warp_sum(s2) / dim;
+    const float c1 = mean ? warp_sum(s1) / dim : 0.f, c2 = warp_sum(s2) / dim;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = i * 32 + lane;
@@ -356,7 +357,8 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
                                  const float* rstd, const float* dres_in, float* dx_out_f32, void* dx_out_bf16,
                                  float* dgamma, float* dbeta, float* dxsum, int64_t rows, int32_t dim, hct_stream_t s) {
   HCT_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAXV * 128, "layernorm_bwd: dim=%d unsupported", dim);
-  HCT_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must both be set or both NULL");
+  HCT_REQUIRE(dbeta == nullptr || dgamma != nullptr, "layernorm_bwd: dbeta without dgamma");
+  HCT_REQUIRE(mean != nullptr || dbeta == nullptr, "layernorm_bwd: RMSNorm (mean == NULL) has no beta gradient");
   HCT_REQUIRE(dxsum == nullptr || dx_out_bf16 != nullptr, "layernorm_bwd: dxsum needs the bf16 output");
   if (rows == 0) return HCT_OK;
   const int grid = grid_for(rows, LN_WARPS, hct_num_sms());

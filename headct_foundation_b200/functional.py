@@ -136,29 +136,32 @@ def linear_dgrad(dy16: torch.Tensor, w: torch.Tensor, *, epi: int = EPI_BF16, au
 
 
 class ZeroArena:
-    """One zero-filled fp32 allocation handed out in 256-byte-aligned slices.
+    """One zero-filled fp32 allocation handed out in 256-byte-aligned named slices.
 
     A block's backward accumulates a dozen parameter gradients with atomics into pre-zeroed buffers; zeroing them
-    one `torch.zeros` at a time cost ~250 tiny fill launches per step, this costs one per autograd node."""
+    one `torch.zeros` at a time cost ~250 tiny fill launches per step, this costs one per autograd node.
+    `take` of a name that was not requested returns None (gradient not wanted)."""
 
-    def __init__(self, sizes: Sequence[int], device: torch.device):
-        self._offs: List[int] = []
+    def __init__(self, sizes: Dict[str, int], device: torch.device):
+        self._offs: Dict[str, Tuple[int, int]] = {}
         total = 0
-        for n in sizes:
-            self._offs.append(total)
+        for k, n in sizes.items():
+            self._offs[k] = (total, n)
             total += (n + 63) // 64 * 64
         self._buf = torch.zeros((max(total, 64),), dtype=F32, device=device)
-        self._sizes = list(sizes)
-        self._next = 0
 
-    def take(self, *shape: int) -> torch.Tensor:
-        i = self._next
-        self._next += 1
+    def has(self, name: str) -> bool:
+        return name in self._offs
+
+    def take(self, name: str, *shape: int) -> Optional[torch.Tensor]:
+        if name not in self._offs:
+            return None
+        off, size = self._offs.pop(name)
         n = 1
         for d in shape:
             n *= d
-        assert n == self._sizes[i], (shape, self._sizes[i])
-        return self._buf[self._offs[i]:self._offs[i] + n].view(*shape)
+        assert n == size, (name, shape, size)
+        return self._buf[off:off + n].view(*shape)
 
 
 def linear_wgrad(dy16: torch.Tensor, x16: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -191,13 +194,14 @@ def rows_to_bf16(src: torch.Tensor, *, groups: int, src_rows_per_group: int, src
     return out
 
 
-def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_bf16: bool, save_stats: bool):
+def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], eps: float, out_bf16: bool, save_stats: bool):
+    """nn.LayerNorm, or RMSNorm (src/models/layers.py:11-53) when `b` is None (then no mean is produced)."""
     D = x.shape[-1]
     rows = x.numel() // D
     y = torch.empty(x.shape, dtype=BF16 if out_bf16 else F32, device=x.device)
-    mean = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
+    mean = torch.empty((rows,), dtype=F32, device=x.device) if (save_stats and b is not None) else None
     rstd = torch.empty((rows,), dtype=F32, device=x.device) if save_stats else None
-    call("hct_layernorm_fwd", x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), int(out_bf16), ptr(mean),
+    call("hct_layernorm_fwd", x.data_ptr(), w.data_ptr(), ptr(b), y.data_ptr(), int(out_bf16), ptr(mean),
          ptr(rstd), rows, D, float(eps), stream_ptr(x.device))
     return y, mean, rstd
 
@@ -205,7 +209,7 @@ def layernorm_fwd(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float,
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd, dres: Optional[torch.Tensor],
                   want_bf16: bool, want_param_grads: bool = True, want_colsum: bool = False,
                   zeros: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
-    """`zeros`: optional pre-zeroed fp32 [D] buffers for (dgamma, dbeta, column sums)."""
+    """`zeros`: optional pre-zeroed fp32 [D] buffers for (dgamma, dbeta, column sums).  mean None = RMSNorm (no dbeta)."""
     D = x.shape[-1]
     rows = x.numel() // D
     dx = torch.empty(x.shape, dtype=F32, device=x.device)
@@ -216,7 +220,11 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd
         dg = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
         db = torch.zeros((D,), dtype=F32, device=x.device) if want_param_grads else None
         dsum = torch.zeros((D,), dtype=F32, device=x.device) if (want_colsum and want_bf16) else None
-    call("hct_layernorm_bwd", dy.data_ptr(), int(dy.dtype == BF16), x.data_ptr(), w.data_ptr(), mean.data_ptr(),
+    if mean is None:
+        db = None
+    elif db is not None and dg is None:
+        dg = torch.zeros((D,), dtype=F32, device=x.device)       # the kernel produces dbeta only together with dgamma
+    call("hct_layernorm_bwd", dy.data_ptr(), int(dy.dtype == BF16), x.data_ptr(), w.data_ptr(), ptr(mean),
          rstd.data_ptr(), ptr(dres), dx.data_ptr(), ptr(dx16), ptr(dg), ptr(db), ptr(dsum), rows, D,
          stream_ptr(x.device))
     if want_colsum:
@@ -230,22 +238,36 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd
 class BlockFn(torch.autograd.Function):
     """x -> x + proj(SDPA(qkv(LN(x)))) -> (+ linear2(GELU(linear1(LN(.))))), one autograd node.
 
-    Parameter order: att_norm.{w,b}, qkv.{w,b?}, proj.{w,b}, ffn_norm.{w,b}, linear1.{w,b}, linear2.{w,b}.
+    Parameter order: att_norm.{w,b?}, qkv.{w,b?}, proj.{w,b}, ffn_norm.{w,b?}, linear1.{w,b}, linear2.{w,b},
+    lora_q.{A,B}?, lora_v.{A,B}?.  A norm without bias is RMSNorm (src/models/layers.py:11-53).  The LoRA adapters
+    (attentionblock.py:45-59) are evaluated low-rank -- (h A^T) B^T instead of h (B A)^T -- and added to q and v
+    through the reference's reshape (`hct_lora_shuffle`).  Gradients are computed only for the inputs autograd asks
+    for (LoRA fine-tuning freezes every large weight, misc.py:349-359; that removes the wgrad GEMMs).
     """
 
     @staticmethod
-    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, heads, eps):
+    def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
+                lqA, lqB, lvA, lvB, heads, eps):
         _require_cuda(x, "AttentionBlock input")
         B, S, D = x.shape
         M = B * S
         hd = D // heads
         x = x.contiguous()
         dev = x.device
-        need_grad = ctx.needs_input_grad[0] or any(ctx.needs_input_grad[1:13])
+        need_grad = any(ctx.needs_input_grad[:17])
         st = stream_ptr(dev)
+        lora = lqA is not None
 
         h1, mean1, rstd1 = layernorm_fwd(x, n1w, n1b, eps, True, need_grad)
         qkv = linear_fwd(h1.view(M, D), qkv_w, qkv_b)                                   # [M, 3D] bf16
+        tq = tv = None
+        if lora:
+            tq = linear_fwd(h1.view(M, D), lqA, None)                                   # [M, r]
+            tv = linear_fwd(h1.view(M, D), lvA, None)
+            lq = linear_fwd(tq, lqB, None)                                              # [M, D]
+            lv = linear_fwd(tv, lvB, None)
+            call("hct_lora_shuffle", qkv.data_ptr(), lq.data_ptr(), lv.data_ptr(), B, S, heads, hd, 0, st)
+            del lq, lv
         att = torch.empty((M, D), dtype=BF16, device=dev)
         lse = torch.empty((B, heads, S), dtype=F32, device=dev)
         call("hct_attention_fwd", qkv.data_ptr(), att.data_ptr(), lse.data_ptr(), B, S, heads, hd, st)
@@ -261,43 +283,53 @@ class BlockFn(torch.autograd.Function):
         linear_fwd(g, fc2_w, fc2_b, epi=EPI_RES_F32, out=x3.view(M, D), res=x2.view(M, D))
         if need_grad:
             ctx.save_for_backward(x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2,
-                                  mean2, rstd2, a, g)
-            ctx.heads, ctx.has_qkv_bias = heads, qkv_b is not None
+                                  mean2, rstd2, a, g, lqA, lqB, lvA, lvB, tq, tv)
+            ctx.heads = heads
         return x3
 
     @staticmethod
     def backward(ctx, dout):
         (x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2, mean2, rstd2, a,
-         g) = ctx.saved_tensors
+         g, lqA, lqB, lvA, lvB, tq, tv) = ctx.saved_tensors
         B, S, D = x.shape
         M = B * S
         heads = ctx.heads
         hd = D // heads
         dev = x.device
         st = stream_ptr(dev)
+        need = ctx.needs_input_grad
+        (N1W, N1B, QKVW, QKVB, PROJW, PROJB, N2W, N2B, FC1W, FC1B, FC2W, FC2B, LQA, LQB, LVA, LVB) = range(1, 17)
+        lora = lqA is not None
         dout = dout.contiguous()
         d3, dfc2_b = take_bf16_shadow(dout, with_colsum=True)
         if d3 is None:
             d3 = rows_to_bf16(dout, groups=1, src_rows_per_group=M, src_row_off=0, rows_per_group=M, dim=D)
-        if dfc2_b is None:
+        if dfc2_b is None and need[FC2B]:
             dfc2_b = colsum(d3, D)
         # every accumulated (atomics) output of this node comes out of ONE zero-filled allocation
         F_ = a.shape[1]
-        zs = ZeroArena([D * F_, F_, F_ * D, D, D, D, D * D, 3 * D * D, 3 * D if ctx.has_qkv_bias else 0, D, D, D], dev)
+        r = lqA.shape[0] if lora else 0
+        want = {"fc2_w": (need[FC2W], D * F_), "fc1_b": (need[FC1B], F_), "fc1_w": (need[FC1W], F_ * D),
+                "n2w": (need[N2W], D), "n2b": (need[N2B] and mean2 is not None, D), "proj_b": (need[PROJB], D),
+                "proj_w": (need[PROJW], D * D), "qkv_w": (need[QKVW], 3 * D * D), "qkv_b": (need[QKVB], 3 * D),
+                "n1w": (need[N1W], D), "n1b": (need[N1B] and mean1 is not None, D), "dxs": (True, D),
+                "lqB": (lora and need[LQB], D * r), "lqA": (lora and need[LQA], r * D),
+                "lvB": (lora and need[LVB], D * r), "lvA": (lora and need[LVA], r * D)}
+        zs = ZeroArena({k: n for k, (on, n) in want.items() if on}, dev)
         # ---- MLP branch
-        dfc2_w = linear_wgrad(d3, g, out=zs.take(D, F_))
-        dfc1_b = zs.take(F_)
+        dfc2_w = linear_wgrad(d3, g, out=zs.take("fc2_w", D, F_)) if need[FC2W] else None
+        dfc1_b = zs.take("fc1_b", F_)
         da = linear_dgrad(d3, fc2_w, epi=EPI_MUL_BF16, aux=a, colsum=dfc1_b)            # [M, F] bf16 (+ column sums)
         del d3
-        dfc1_w = linear_wgrad(da, h2.view(M, D), out=zs.take(F_, D))
+        dfc1_w = linear_wgrad(da, h2.view(M, D), out=zs.take("fc1_w", F_, D)) if need[FC1W] else None
         dh2 = linear_dgrad(da, fc1_w)                                                   # [M, D] bf16
         del da
         dx2, dx2_16, dn2w, dn2b, dproj_b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, True, want_colsum=True,
-                                                         zeros=(zs.take(D), zs.take(D), zs.take(D)))
+                                                         zeros=(zs.take("n2w", D), zs.take("n2b", D), zs.take("proj_b", D)))
         del dh2
         # ---- attention branch
         dx2_16 = dx2_16.view(M, D)
-        dproj_w = linear_wgrad(dx2_16, att, out=zs.take(D, D))
+        dproj_w = linear_wgrad(dx2_16, att, out=zs.take("proj_w", D, D)) if need[PROJW] else None
         datt = linear_dgrad(dx2_16, proj_w)                                             # [M, D] bf16
         del dx2_16
         dqkv = torch.empty_like(qkv)
@@ -305,16 +337,36 @@ class BlockFn(torch.autograd.Function):
         call("hct_attention_bwd", qkv.data_ptr(), att.data_ptr(), datt.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
              delta.data_ptr(), B, S, heads, hd, st)
         del datt
-        dqkv_w = linear_wgrad(dqkv, h1.view(M, D), out=zs.take(3 * D, D))
-        zq = zs.take(3 * D if ctx.has_qkv_bias else 0)
-        dqkv_b = colsum(dqkv, 3 * D, out=zq) if ctx.has_qkv_bias else None
-        dh1 = linear_dgrad(dqkv, qkv_w)
+        dqkv_w = linear_wgrad(dqkv, h1.view(M, D), out=zs.take("qkv_w", 3 * D, D)) if need[QKVW] else None
+        dqkv_b = colsum(dqkv, 3 * D, out=zs.take("qkv_b", 3 * D)) if need[QKVB] else None
+        dlqA = dlqB = dlvA = dlvB = None
+        if not lora:
+            dh1 = linear_dgrad(dqkv, qkv_w)                                             # [M, D] bf16
+        else:
+            # adjoint of the reshape-add, then the two low-rank factors; their dgrads accumulate into an fp32 dh1
+            dlq = torch.empty((M, D), dtype=BF16, device=dev)
+            dlv = torch.empty((M, D), dtype=BF16, device=dev)
+            call("hct_lora_shuffle", dqkv.data_ptr(), dlq.data_ptr(), dlv.data_ptr(), B, S, heads, hd, 1, st)
+            dh1 = linear_dgrad(dqkv, qkv_w, epi=EPI_F32, out=torch.empty((M, D), dtype=F32, device=dev))
+            for dl, t, A_, B_, ka, kb in ((dlq, tq, lqA, lqB, "lqA", "lqB"), (dlv, tv, lvA, lvB, "lvA", "lvB")):
+                dB_ = linear_wgrad(dl, t, out=zs.take(kb, D, r)) if zs.has(kb) else None
+                dt = linear_dgrad(dl, B_)                                               # [M, r] bf16
+                dA_ = linear_wgrad(dt, h1.view(M, D), out=zs.take(ka, r, D)) if zs.has(ka) else None
+                linear_dgrad(dt, A_, epi=EPI_ATOMIC_F32, out=dh1)                       # dh1 += dt A
+                if ka == "lqA":
+                    dlqA, dlqB = dA_, dB_
+                else:
+                    dlvA, dlvB = dA_, dB_
+            del dlq, dlv
         del dqkv
         dx, dx16, dn1w, dn1b, dxs = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True, want_colsum=True,
-                                                  zeros=(zs.take(D), zs.take(D), zs.take(D)))
+                                                  zeros=(zs.take("n1w", D), zs.take("n1b", D), zs.take("dxs", D)))
         put_bf16_shadow(dx, dx16, dxs)
-        return (dx, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dn2w, dn2b, dfc1_w, dfc1_b, dfc2_w, dfc2_b, None,
-                None)
+
+        def opt(i, t):
+            return t if need[i] else None
+        return (dx, opt(N1W, dn1w), opt(N1B, dn1b), dqkv_w, dqkv_b, dproj_w, opt(PROJB, dproj_b), opt(N2W, dn2w),
+                opt(N2B, dn2b), dfc1_w, opt(FC1B, dfc1_b), dfc2_w, opt(FC2B, dfc2_b), dlqA, dlqB, dlvA, dlvB, None, None)
 
 
 class AttentionFn(torch.autograd.Function):
@@ -349,6 +401,122 @@ class AttentionFn(torch.autograd.Function):
         call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
              delta.data_ptr(), B, S, heads, D // heads, stream_ptr(qkv.device))
         return dqkv, None
+
+
+class LoraAddFn(torch.autograd.Function):
+    """q += reshape(lora_q(x)), v += reshape(lora_v(x)) on a qkv tensor [B,S,3*D] (attentionblock.py:57-59): the LoRA
+    outputs [B,S,D] are reinterpreted as [B,H,S,hd] without a transpose, exactly as the reference does."""
+
+    @staticmethod
+    def forward(ctx, qkv, lq, lv, heads):
+        B, S, D3 = qkv.shape
+        D = D3 // 3
+        out = qkv.contiguous().clone()
+        lq, lv = lq.contiguous(), lv.contiguous()
+        assert out.dtype == BF16 and lq.dtype == BF16 and lv.dtype == BF16
+        call("hct_lora_shuffle", out.data_ptr(), lq.data_ptr(), lv.data_ptr(), B, S, heads, D // heads, 0,
+             stream_ptr(qkv.device))
+        ctx.heads = heads
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, S, D3 = dout.shape
+        D = D3 // 3
+        dout = dout.contiguous()
+        dlq = torch.empty((B, S, D), dtype=BF16, device=dout.device)
+        dlv = torch.empty((B, S, D), dtype=BF16, device=dout.device)
+        call("hct_lora_shuffle", dout.data_ptr(), dlq.data_ptr(), dlv.data_ptr(), B, S, ctx.heads, D // ctx.heads, 1,
+             stream_ptr(dout.device))
+        return dout, dlq, dlv, None
+
+
+# --------------------------------------------------------------------------------------------
+# AttentionClassifier pieces (classifier.py:35-100): BatchNorm1d over token rows + attentive pooling
+# --------------------------------------------------------------------------------------------
+class ColNormFn(torch.autograd.Function):
+    """nn.BatchNorm1d(C, affine=False) on x.transpose(-2,-1) (classifier.py:89): per-channel statistics over every
+    (sample, token) row.  Training updates running_mean / running_var in place like torch."""
+
+    @staticmethod
+    def forward(ctx, x, running_mean, running_var, training, eps, momentum, out_bf16):
+        _require_cuda(x, "BatchNorm input")
+        x = x.contiguous()
+        if x.dtype != F32:
+            x = cast_f32(x) if x.dtype == BF16 else x.float()
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dev, st = x.device, stream_ptr(x.device)
+        y = torch.empty(x.shape, dtype=BF16 if out_bf16 else F32, device=dev)
+        if training:
+            sums = torch.zeros((2 * D,), dtype=F32, device=dev)
+            mean = torch.empty((D,), dtype=F32, device=dev)
+            invstd = torch.empty((D,), dtype=F32, device=dev)
+            call("hct_colnorm_stats", x.data_ptr(), sums.data_ptr(), rows, D, float(eps), float(momentum),
+                 mean.data_ptr(), invstd.data_ptr(), ptr(running_mean), ptr(running_var), st)
+            call("hct_colnorm_apply", x.data_ptr(), mean.data_ptr(), invstd.data_ptr(), 0, float(eps), None,
+                 y.data_ptr(), int(out_bf16), rows, D, st)
+        else:
+            mean = running_mean
+            invstd = torch.empty((D,), dtype=F32, device=dev)
+            call("hct_colnorm_apply", x.data_ptr(), mean.data_ptr(), running_var.data_ptr(), 1, float(eps),
+                 invstd.data_ptr(), y.data_ptr(), int(out_bf16), rows, D, st)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(x, mean.clone() if not training else mean, invstd)
+            ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd = ctx.saved_tensors
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dy = dy.contiguous()
+        if dy.dtype not in (BF16, F32):
+            dy = dy.float()
+        dx = torch.empty(x.shape, dtype=F32, device=x.device)
+        sums = torch.zeros((2 * D,), dtype=F32, device=x.device) if ctx.training else None
+        call("hct_colnorm_bwd", dy.data_ptr(), int(dy.dtype == BF16), x.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+             ptr(sums), dx.data_ptr(), rows, D, stream_ptr(x.device))
+        return dx, None, None, None, None, None, None
+
+
+class PoolAttentionFn(torch.autograd.Function):
+    """F.scaled_dot_product_attention(q, k, v) of AttentionClassifier.forward (classifier.py:85-94): `num_queries`
+    learned queries shared by the batch over the N tokens of each sample.  cls fp32 [nq, C]; kv bf16 [B, N, 2C] in
+    the wkv Linear's [2][H][hd] channel order; returns fp32 [B, nq, C]."""
+
+    @staticmethod
+    def forward(ctx, cls, kv, heads, scale_total):
+        _require_cuda(kv, "AttentionClassifier kv")
+        B, N, C2 = kv.shape
+        C = C2 // 2
+        nq = cls.shape[0]
+        kv = kv.contiguous()
+        if kv.dtype != BF16:
+            kv = cast_bf16(kv.float())
+        cls = cls.contiguous().float()
+        out = torch.empty((B, nq, C), dtype=F32, device=kv.device)
+        probs = torch.empty((B, heads, nq, N), dtype=F32, device=kv.device)
+        call("hct_pool_attention_fwd", cls.data_ptr(), kv.data_ptr(), out.data_ptr(), probs.data_ptr(), B, N, heads,
+             C // heads, nq, float(scale_total), stream_ptr(kv.device))
+        ctx.save_for_backward(cls, kv, out, probs)
+        ctx.meta = (heads, float(scale_total))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        cls, kv, out, probs = ctx.saved_tensors
+        heads, scale_total = ctx.meta
+        B, N, C2 = kv.shape
+        C = C2 // 2
+        nq = cls.shape[0]
+        dout = dout.contiguous().float()
+        dcls = torch.zeros_like(cls)
+        dkv = torch.empty_like(kv)
+        call("hct_pool_attention_bwd", cls.data_ptr(), kv.data_ptr(), out.data_ptr(), probs.data_ptr(), dout.data_ptr(),
+             dcls.data_ptr(), dkv.data_ptr(), B, N, heads, C // heads, nq, scale_total, stream_ptr(kv.device))
+        return dcls, dkv, None, None
 
 
 # A block's backward produces both the fp32 residual-stream gradient and its bf16 copy (the next GEMM

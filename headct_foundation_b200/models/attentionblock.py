@@ -10,11 +10,12 @@ import torch
 import torch.nn as nn
 
 from .. import functional as HF
+from .layers import RMSNorm
 
 
 class LoraLinear(nn.Module):
-    """Parameter container for the LoRA adapters (attentionblock.py:6-22).  `TRAIN.LORA` is False in every shipped
-    config, so the adapters are outside the accelerated path; they run as plain torch ops on top of q and v."""
+    """LoRA adapter (attentionblock.py:6-22): y = x (B A)^T, evaluated low-rank as (x A^T) B^T on the tcgen05 GEMM.
+    Inside an `AttentionBlock` the adapters are folded into `BlockFn`; this forward serves stand-alone use."""
 
     def __init__(self, in_features: int, out_features: int, r: int = 8):
         super().__init__()
@@ -23,7 +24,9 @@ class LoraLinear(nn.Module):
 
     @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x):
-        return torch.nn.functional.linear(x, torch.matmul(self.lora_matrix_B, self.lora_matrix_A))
+        t = HF.LinearFn.apply(x, self.lora_matrix_A, None, False, False)
+        y = HF.LinearFn.apply(t, self.lora_matrix_B, None, False, False)
+        return y.float() if x.dtype == torch.float32 else y
 
 
 class MLPBlock(nn.Module):
@@ -64,11 +67,17 @@ class SelfAttention(nn.Module):
 
     @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x, attn_mask=None):
-        if attn_mask is not None or self.lora or (self.dropout > 0 and self.training):
-            raise NotImplementedError("attn_mask / LoRA / dropout are outside the accelerated path "
+        if attn_mask is not None or (self.dropout > 0 and self.training):
+            raise NotImplementedError("attn_mask / dropout are outside the accelerated path "
                                       "(unused by every shipped config)")
         B, N, C = x.shape
         qkv = HF.LinearFn.apply(x, self.qkv.weight, self.qkv.bias, False, False)          # bf16 [B,N,3C]
+        if self.lora:
+            lq = HF.LinearFn.apply(HF.LinearFn.apply(x, self.lora_q.lora_matrix_A, None, False, False),
+                                   self.lora_q.lora_matrix_B, None, False, False)
+            lv = HF.LinearFn.apply(HF.LinearFn.apply(x, self.lora_v.lora_matrix_A, None, False, False),
+                                   self.lora_v.lora_matrix_B, None, False, False)
+            qkv = HF.LoraAddFn.apply(qkv, lq, lv, self.num_heads)                         # the reshape quirk, :57-59
         y = HF.AttentionFn.apply(qkv, self.num_heads)                                     # bf16 [B,N,C]
         y = HF.LinearFn.apply(y, self.proj.weight, self.proj.bias, False, False)
         return y.float() if x.dtype == torch.float32 else y
@@ -82,8 +91,8 @@ class AttentionBlock(nn.Module):
             raise ValueError("dropout_rate should be between 0 and 1.")
         if hidden_size % num_heads != 0:
             raise ValueError("hidden_size should be divisible by num_heads.")
-        if norm_layer is not nn.LayerNorm:
-            raise NotImplementedError("only nn.LayerNorm is accelerated (every shipped yaml sets NORM_LAYER: layernorm)")
+        if norm_layer not in (nn.LayerNorm, RMSNorm):
+            raise NotImplementedError("norm_layer must be nn.LayerNorm or RMSNorm (config NORM_LAYER: layernorm | rmsnorm)")
         self.dropout_rate = dropout_rate
         self.num_heads = num_heads
         self.mlp = MLPBlock(hidden_size, mlp_dim, dropout_rate)
@@ -93,13 +102,16 @@ class AttentionBlock(nn.Module):
 
     @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, hidden_states, residual=None):
-        if self.attn.lora or (self.dropout_rate > 0 and self.training):
-            raise NotImplementedError("LoRA / dropout are outside the accelerated path")
+        if self.dropout_rate > 0 and self.training:
+            raise NotImplementedError("dropout is outside the accelerated path")
         if self.att_norm.eps != self.ffn_norm.eps:
             raise NotImplementedError("att_norm and ffn_norm must share eps")
         a, m = self.attn, self.mlp
-        out = HF.BlockFn.apply(hidden_states, self.att_norm.weight, self.att_norm.bias, a.qkv.weight, a.qkv.bias,
-                               a.proj.weight, a.proj.bias, self.ffn_norm.weight, self.ffn_norm.bias,
-                               m.linear1.weight, m.linear1.bias, m.linear2.weight, m.linear2.bias,
+        lora = ((a.lora_q.lora_matrix_A, a.lora_q.lora_matrix_B, a.lora_v.lora_matrix_A, a.lora_v.lora_matrix_B)
+                if a.lora else (None, None, None, None))
+        out = HF.BlockFn.apply(hidden_states, self.att_norm.weight, getattr(self.att_norm, "bias", None),
+                               a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+                               self.ffn_norm.weight, getattr(self.ffn_norm, "bias", None),
+                               m.linear1.weight, m.linear1.bias, m.linear2.weight, m.linear2.bias, *lora,
                                self.num_heads, self.att_norm.eps)
         return out, residual

@@ -126,7 +126,7 @@ class MaskedAutoencoderViT(nn.Module):
             residual = None
             for blk in self.blocks:
                 t, residual = blk(t, residual)
-            t = HF.LayerNormFn.apply(t, self.norm.weight, self.norm.bias, self.norm.eps, False)
+            t = HF.LayerNormFn.apply(t, self.norm.weight, getattr(self.norm, "bias", None), self.norm.eps, False)
         return t, mask, ids_restore
 
     # ---- decoder (mae.py:244-275)
@@ -137,7 +137,7 @@ class MaskedAutoencoderViT(nn.Module):
         residual = None
         for blk in self.decoder_blocks:
             t, residual = blk(t, residual)
-        h = HF.LayerNormFn.apply(t, self.decoder_norm.weight, self.decoder_norm.bias, self.decoder_norm.eps, True)
+        h = HF.LayerNormFn.apply(t, self.decoder_norm.weight, getattr(self.decoder_norm, "bias", None), self.decoder_norm.eps, True)
         return HF.LinearFn.apply(h, self.decoder_pred.weight, self.decoder_pred.bias, False, False)
 
     @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace

@@ -62,7 +62,7 @@ class ViT(nn.Module):
             for blk in self.blocks:
                 x, residual = blk(x, residual)
                 hidden_states_out.append(x)
-            x = HF.LayerNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.eps, False)
+            x = HF.LayerNormFn.apply(x, self.norm.weight, getattr(self.norm, "bias", None), self.norm.eps, False)
             if hasattr(self, "classification_head"):
                 x = self.classification_head(x[:, 0])       # tiny host-torch head (CLASSIFICATION: False in all configs)
         return x, hidden_states_out

@@ -1,5 +1,5 @@
-"""Hot-path helpers mirrored from `src/utils/misc.py`: MultiCropWrapper (:447-484) and the EMA teacher update
-(:386-397).  Everything else in the reference's misc.py (meters, checkpoint I/O, plotting) is host glue and out
+"""Hot-path helpers mirrored from `src/utils/misc.py`: MultiCropWrapper (:447-484), the EMA teacher update
+(:386-397) and the freeze rule of LoRA / linear-probe fine-tuning (:349-363).  Everything else in the reference's misc.py (meters, checkpoint I/O, plotting) is host glue and out
 of scope."""
 from __future__ import annotations
 
@@ -34,6 +34,15 @@ class MultiCropWrapper(nn.Module):
         output = outs[0] if len(outs) == 1 else torch.cat(outs)
         cls_feature = output[:, 0, :]
         return {"dino_output": self.head(cls_feature)}
+
+
+def set_requires_grad_false(*models, lora: bool = False) -> None:
+    """misc.py:349-363.  lora=True keeps the LoRA factors, every bias, the patch / position embeddings and the norms
+    trainable (a substring match on the parameter NAME, as the reference does); otherwise everything is frozen.
+    Frozen weights cost nothing in our backward: `BlockFn` skips their wgrad GEMMs."""
+    for model in models:
+        for name, param in model.named_parameters():
+            param.requires_grad = bool(lora) and ("lora" in name or "bias" in name or "embeddings" in name or "norm" in name)
 
 
 @torch.no_grad()

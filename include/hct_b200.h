@@ -93,14 +93,17 @@ int hct_gemm_trace(void* buf);
  * Row kernels (HBM-bound)
  * ------------------------------------------------------------------------------------------- */
 /* nn.LayerNorm forward: attentionblock.py:97-98, mae.py:240,271, vit.py:169.
- * x fp32 [rows, dim] -> y (bf16 if y_bf16 else fp32) ; mean/rstd fp32 [rows] (may be NULL). */
+ * x fp32 [rows, dim] -> y (bf16 if y_bf16 else fp32) ; mean/rstd fp32 [rows] (may be NULL).
+ * beta == NULL selects RMSNorm (src/models/layers.py:29-53, the NORM_LAYER: 'rmsnorm' option of
+ * main_downstream.py:111-116): y = x * rsqrt(mean(x^2) + eps) * gamma, rstd_out = that rsqrt, mean_out is not written. */
 int hct_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_bf16,
                       float* mean, float* rstd, int64_t rows, int32_t dim, float eps,
                       hct_stream_t stream);
 /* LayerNorm backward (autograd of the call sites above).  dy: bf16 (dy_bf16) or fp32 [rows, dim].
  * dx_out_f32 = (dres_in ? dres_in : 0) + dLN ; optional bf16 copy dx_out_bf16 ;
  * dgamma/dbeta fp32 [dim] are ACCUMULATED (+=) with atomics; dxsum (optional, fp32 [dim], +=) receives
- * the column sums of the bf16 dx output = the bias gradient of the Linear that consumes it. */
+ * the column sums of the bf16 dx output = the bias gradient of the Linear that consumes it.
+ * mean == NULL selects the RMSNorm backward (dbeta must then be NULL). */
 int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dres_in,
                       float* dx_out_f32, void* dx_out_bf16, float* dgamma, float* dbeta, float* dxsum,
@@ -276,6 +279,44 @@ int hct_grad_norms_multi(const int64_t* table, int32_t n, float* norms_ws, hct_s
 int hct_adamw_multi(const int64_t* table, int32_t n, const float* norms_ws, float clip, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int32_t step,
                     hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Downstream heads: LoRA q/v adapters, BatchNorm1d over token rows, attentive pooling.
+ * ------------------------------------------------------------------------------------------- */
+/* LoRA residuals of SelfAttention (src/models/attentionblock.py:57-59).  The reference reshapes -- it does not
+ * permute -- lora_q(x) [B,N,C] to [B,H,N,hd] before adding it to q, so flat element f = (h*N + n)*hd + d of a
+ * sample's LoRA output lands on q[b,h,n,d]; this call reproduces that on our qkv layout [B,N,3,H,hd] (bf16):
+ *   backward == 0:  qkv[b,n,0,h,d] += lq[b].flat[f],  qkv[b,n,2,h,d] += lv[b].flat[f]      (in place)
+ *   backward != 0:  lq[b].flat[f] = qkv[b,n,0,h,d],   lv[b].flat[f] = qkv[b,n,2,h,d]       (qkv = dqkv; the adjoint)
+ * lq, lv: bf16 [B, N*C]. */
+int hct_lora_shuffle(void* qkv, void* lq, void* lv, int64_t batch, int32_t seq, int32_t heads, int32_t head_dim,
+                     int32_t backward, hct_stream_t stream);
+/* nn.BatchNorm1d(dim, affine=False) applied to [B, dim, N] = per-column statistics of the token matrix
+ * x fp32 [rows = B*N, dim] (src/models/classifier.py:64-65,89,96; also :18,31 for the linear probe).
+ * stats (training): sums fp32 [2*dim] must be ZERO on entry and receives (sum x, sum x^2); mean / invstd fp32 [dim]
+ *   get the batch mean and 1/sqrt(biased var + eps); running_mean / running_var (may be NULL) are updated in place
+ *   with `momentum` and the unbiased variance, as torch does.
+ * apply: y = (x - mean) * invstd, bf16 or fp32; with is_var != 0 the third argument is a (running) variance and
+ *   invstd_scratch fp32 [dim] receives 1/sqrt(var + eps) first (eval mode).
+ * bwd: dx fp32 = invstd * (dy - mean_r(dy) - x_hat * mean_r(dy * x_hat)); sums fp32 [2*dim] ZERO on entry (workspace);
+ *   sums == NULL: eval-mode backward dx = invstd * dy. */
+int hct_colnorm_stats(const float* x, float* sums, int64_t rows, int32_t dim, float eps, float momentum,
+                      float* mean, float* invstd, float* running_mean, float* running_var, hct_stream_t stream);
+int hct_colnorm_apply(const float* x, const float* mean, const float* invstd_or_var, int32_t is_var, float eps,
+                      float* invstd_scratch, void* y, int32_t y_bf16, int64_t rows, int32_t dim, hct_stream_t stream);
+int hct_colnorm_bwd(const void* dy, int32_t dy_bf16, const float* x, const float* mean, const float* invstd,
+                    float* sums, float* dx, int64_t rows, int32_t dim, hct_stream_t stream);
+/* Attentive pooling of AttentionClassifier.forward (classifier.py:84-94): num_queries learned query tokens
+ * (cls fp32 [num_queries, H*hd], shared by the batch) attend over the N tokens of each sample.
+ * kv bf16 [B, N, 2, H, hd] = the wkv Linear's natural output.  scale_total multiplies q: the reference scales q by
+ * self.scale AND F.scaled_dot_product_attention applies 1/sqrt(hd) again, so callers pass self.scale / sqrt(hd).
+ * out fp32 [B, num_queries, H*hd]; probs fp32 [B, H, num_queries, N] (saved for backward).
+ * bwd: dout fp32 like out -> dkv bf16 like kv (fully written), dcls fp32 [num_queries, H*hd] ACCUMULATED (+=). */
+int hct_pool_attention_fwd(const float* cls, const void* kv, float* out, float* probs, int32_t batch, int32_t seq,
+                           int32_t heads, int32_t head_dim, int32_t num_queries, float scale_total, hct_stream_t stream);
+int hct_pool_attention_bwd(const float* cls, const void* kv, const float* out, const float* probs, const float* dout,
+                           float* dcls, void* dkv, int32_t batch, int32_t seq, int32_t heads, int32_t head_dim,
+                           int32_t num_queries, float scale_total, hct_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -119,7 +119,7 @@ def mae_case(ns, cfg, batch, x_seed, noise_seed, w_seed, name, full_outputs):
 
 def vit_case(ns, cfg, batch, x_seed, w_seed, name, full_outputs):
     torch.manual_seed(0)
-    model = ns.vit.ViT(**cfg)
+    model = ns.vit.ViT(**synth.resolve_norm(cfg, ns.layers.RMSNorm))
     sd = synth.vit_state_dict(cfg, seed=w_seed)
     assert list(model.state_dict().keys()) == list(sd.keys()), (list(model.state_dict().keys())[:6], list(sd.keys())[:6])
     model.load_state_dict(sd, strict=True)
@@ -237,6 +237,62 @@ def dino_head_full_case(ns, name):
                         center1_sum=np.float64(crit.center.double().sum().item()))
 
 
+def attention_classifier_case(ns, name):
+    """classifier.py:35-100 in train mode (batch statistics) and eval mode (running statistics), 1 and 3 queries."""
+    rec = {}
+    for tag, dim, heads, nq, bias, B, N in (("q1", 192, 3, 1, False, 4, 69), ("q3", 96, 2, 3, True, 3, 33)):
+        torch.manual_seed(0)
+        clf = ns.classifier.AttentionClassifier(dim, 2, num_heads=heads, qkv_bias=bias, num_queries=nq)
+        sd = synth.attention_classifier_state_dict(dim, 2, num_queries=nq, qkv_bias=bias, seed=51)
+        assert list(clf.state_dict().keys()) == list(sd.keys()), list(clf.state_dict().keys())
+        clf.load_state_dict(sd)
+        clf.train()
+        x = torch.from_numpy(np.random.default_rng(52).standard_normal((B, N, dim)).astype(np.float32)) * 1.5 + 0.3
+        xg = x.clone().requires_grad_(True)
+        logits = clf(xg)
+        # per-sample weights: a batch-constant weighting has zero gradient through train-mode bn2 (its outputs sum to 0)
+        wl = torch.from_numpy(np.random.default_rng(53).standard_normal((B, 2)).astype(np.float32))
+        (logits * wl).sum().backward()
+        _close(O.attention_classifier(sd, x, heads, training=True), logits.detach(), 1e-5, name + tag + ".train")
+        sd_after = {k: v.clone() for k, v in clf.state_dict().items()}
+        clf.eval()
+        with torch.no_grad():
+            logits_eval = clf(x)
+        _close(O.attention_classifier(sd_after, x, heads, training=False), logits_eval, 1e-5, name + tag + ".eval")
+        rec.update({f"{tag}_x": x.numpy(), f"{tag}_logits_train": logits.detach().numpy(), f"{tag}_logits_eval": logits_eval.numpy(),
+                    f"{tag}_wl": wl.numpy(), f"{tag}_dx": xg.grad.numpy(), f"{tag}_dcls": clf.cls_token.grad.numpy(), f"{tag}_dwkv": clf.wkv.weight.grad.numpy(),
+                    f"{tag}_bn1_mean": sd_after["bn1.running_mean"].numpy(), f"{tag}_bn1_var": sd_after["bn1.running_var"].numpy(),
+                    f"{tag}_cfg": json.dumps(dict(dim=dim, heads=heads, nq=nq, bias=bias))})
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(f"[{name}] written")
+    return clf
+
+
+def lora_grad_case(ns, name):
+    """LoRA fine-tuning (TRAIN.LORA, misc.py:349-359): gradients of the trainable subset through the reshape quirk."""
+    cfg = synth.VIT_SMALL_LORA
+    torch.manual_seed(0)
+    model = ns.vit.ViT(**cfg)
+    sd = synth.vit_state_dict(cfg, seed=6)
+    model.load_state_dict(sd, strict=True)
+    ns.misc.set_requires_grad_false(model, lora=True)
+    model.train()
+    x = synth.volume(2, cfg["in_chans"], cfg["img_size"], 5)
+    y, _ = model(x)
+    w = torch.from_numpy(np.random.default_rng(61).standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * w).sum().backward()
+    names = ["blocks.0.attn.lora_q.lora_matrix_A", "blocks.0.attn.lora_q.lora_matrix_B", "blocks.1.attn.lora_v.lora_matrix_A",
+             "blocks.1.attn.lora_v.lora_matrix_B", "blocks.0.attn.qkv.bias", "blocks.1.att_norm.weight", "norm.bias",
+             "patch_embedding.patch_embeddings.bias"]
+    params = dict(model.named_parameters())
+    rec = {"grad::" + n: params[n].grad.numpy() for n in names}
+    rec["trainable"] = json.dumps(sorted(n for n, p in params.items() if p.requires_grad))
+    rec["frozen_have_no_grad"] = np.bool_(all(p.grad is None for p in params.values() if not p.requires_grad))
+    rec["out_weight_seed"] = 61
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    print(f"[{name}] {len(names)} gradients written")
+
+
 def misc_cases(ns):
     # a3: sin-cos table (cubic full size + a non-cubic grid that exposes the h/w swap)
     t_full = ns.pos_embed.build_sincos_position_embedding((8, 8, 8), 768, 3).detach()
@@ -266,6 +322,9 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ns = ref_import.load()
+    if "--only-attention-classifier" in sys.argv:
+        attention_classifier_case(ns, "attention_classifier")
+        return
     layout = {}
     m = mae_case(ns, synth.MAE_SMALL, 3, 1, 7, 2, "mae_small", True)
     m = mae_case(ns, synth.MAE_FULL, 2, 3, 42, 4, "mae_full_b2", False)
@@ -275,6 +334,13 @@ def main():
     layout["vit_full_extract"] = _layout(v)
     v = vit_case(ns, synth.VIT_FULL_DINO, 1, 9, 10, "vit_full_dino_b1", False)
     layout["vit_full_dino"] = _layout(v)
+    v = vit_case(ns, synth.VIT_SMALL_LORA, 2, 5, 6, "vit_small_lora", True)
+    layout["vit_small_lora"] = _layout(v)
+    v = vit_case(ns, synth.VIT_SMALL_RMS, 2, 5, 6, "vit_small_rms", True)
+    layout["vit_small_rms"] = _layout(v)
+    lora_grad_case(ns, "vit_small_lora_grads")
+    c = attention_classifier_case(ns, "attention_classifier")
+    layout["attention_classifier"] = _layout(c)
     s = dino_case(ns, synth.VIT_SMALL, synth.DINO_HEAD_SMALL, 2, "dino_small")
     layout["dino_small_wrapper"] = _layout(s)
     dino_head_full_case(ns, "dino_head_full")

@@ -127,6 +127,18 @@ def random_masking(x: Tensor, noise: Tensor, mask_ratio: float):
 # ----------------------------------------------------------------------------------------
 # a6  transformer block  (src/models/attentionblock.py:51-66, :96-99; monai MLPBlock)
 # ----------------------------------------------------------------------------------------
+def _rms(x: Tensor, w: Tensor, eps: float) -> Tensor:
+    """RMSNorm, src/models/layers.py:29-53 (NORM_LAYER: 'rmsnorm', main_downstream.py:111-116)."""
+    return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * w
+
+
+def _norm(x: Tensor, sd: SD, name: str, eps: float) -> Tensor:
+    """nn.LayerNorm, or RMSNorm when the state_dict holds no bias for this norm."""
+    if (name + ".bias") in sd:
+        return _ln(x, sd[name + ".weight"], sd[name + ".bias"], eps)
+    return _rms(x, sd[name + ".weight"], eps)
+
+
 def _ln(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
@@ -146,16 +158,24 @@ def self_attention(x: Tensor, sd: SD, pre: str, heads: int) -> Tensor:
     # output channels ordered [3][heads][hd]  (attentionblock.py:54)
     qkv = qkv.reshape(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0], qkv[1], qkv[2]
+    if (pre + "lora_q.lora_matrix_A") in sd:
+        # LoRA residuals (attentionblock.py:19-22, :57-59): x (B A)^T, RESHAPED (not permuted) to [B, H, S, hd]
+        lq = x @ (sd[pre + "lora_q.lora_matrix_B"] @ sd[pre + "lora_q.lora_matrix_A"]).t()
+        lv = x @ (sd[pre + "lora_v.lora_matrix_B"] @ sd[pre + "lora_v.lora_matrix_A"]).t()
+        q = q + lq.reshape(B, heads, S, hd)
+        v = v + lv.reshape(B, heads, S, hd)
     att = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))  # SDPA default scale (:61)
     att = att.softmax(-1)
     y = (att @ v).transpose(1, 2).reshape(B, S, C)
     return y @ sd[pre + "proj.weight"].t() + sd[pre + "proj.bias"]
 
 
-def attention_block(x: Tensor, sd: SD, pre: str, heads: int, eps: float = 1e-5) -> Tensor:
-    h = _ln(x, sd[pre + "att_norm.weight"], sd[pre + "att_norm.bias"], eps)
+def attention_block(x: Tensor, sd: SD, pre: str, heads: int, eps: Optional[float] = None) -> Tensor:
+    if eps is None:      # constructor defaults: nn.LayerNorm 1e-5, RMSNorm 1e-6 (attentionblock.py:92-93, layers.py:12)
+        eps = 1e-5 if (pre + "att_norm.bias") in sd else 1e-6
+    h = _norm(x, sd, pre + "att_norm", eps)
     x = x + self_attention(h, sd, pre + "attn.", heads)
-    h = _ln(x, sd[pre + "ffn_norm.weight"], sd[pre + "ffn_norm.bias"], eps)
+    h = _norm(x, sd, pre + "ffn_norm", eps)
     h = _gelu_erf(h @ sd[pre + "mlp.linear1.weight"].t() + sd[pre + "mlp.linear1.bias"])
     h = h @ sd[pre + "mlp.linear2.weight"].t() + sd[pre + "mlp.linear2.bias"]
     return x + h
@@ -186,7 +206,7 @@ def mae_forward_encoder(sd: SD, x: Tensor, noise: Tensor, mask_ratio: float, enc
     t = torch.cat([sd["cls_token"].expand(t.shape[0], -1, -1), t], dim=1)
     for i in range(_depth(sd, "blocks.")):
         t = attention_block(t, sd, f"blocks.{i}.", enc_heads)
-    t = _ln(t, sd["norm.weight"], sd["norm.bias"], 1e-5)
+    t = _norm(t, sd, "norm", 1e-5 if "norm.bias" in sd else 1e-6)         # LayerNorm / RMSNorm default eps (mae.py:116)
     return t, mask, ids_restore, ids_keep
 
 
@@ -202,7 +222,7 @@ def mae_forward_decoder(sd: SD, latent: Tensor, ids_restore: Tensor, dec_heads: 
     y = y + pos
     for i in range(_depth(sd, "decoder_blocks.")):
         y = attention_block(y, sd, f"decoder_blocks.{i}.", dec_heads)
-    y = _ln(y, sd["decoder_norm.weight"], sd["decoder_norm.bias"], 1e-5)
+    y = _norm(y, sd, "decoder_norm", 1e-5 if "decoder_norm.bias" in sd else 1e-6)
     y = _linear(y, sd, "decoder_pred")
     return y[:, 1:]
 
@@ -251,7 +271,7 @@ def vit_forward(sd: SD, x: Tensor, heads: int):
     for i in range(_depth(sd, "blocks.")):
         t = attention_block(t, sd, f"blocks.{i}.", heads)
         hidden.append(t)
-    t = _ln(t, sd["norm.weight"], sd["norm.bias"], 1e-6)          # eps 1e-6 (vit.py:124)
+    t = _norm(t, sd, "norm", 1e-6)                                # eps 1e-6 (vit.py:124)
     return t, hidden
 
 
@@ -337,6 +357,35 @@ def linear_classifier(sd: SD, x: Tensor, training: bool = True) -> Tensor:
         mu, var = sd["bn.running_mean"], sd["bn.running_var"]
     x = (x - mu) / torch.sqrt(var + 1e-6)
     return x @ sd["linear.weight"].t() + sd["linear.bias"]
+
+
+def attention_classifier(sd: SD, x: Tensor, heads: int, training: bool = True, qk_scale: Optional[float] = None) -> Tensor:
+    """AttentionClassifier.forward, src/models/classifier.py:74-100.  x [B, N, C] tokens -> [B, classes]."""
+    B, N, C = x.shape
+    hd = C // heads
+    scale = qk_scale or hd ** -0.5
+    cls = sd["cls_token"]                                            # [1, nq, C]
+    nq = cls.shape[1]
+    q = cls.expand(B, -1, -1).reshape(B, nq, heads, hd).permute(0, 2, 1, 3) * scale          # :86-87
+    if training:                                                     # bn1 over (batch, tokens) per channel (:89)
+        mu, var = x.mean((0, 1)), x.var((0, 1), unbiased=False)
+    else:
+        mu, var = sd["bn1.running_mean"], sd["bn1.running_var"]
+    xh = (x - mu) / torch.sqrt(var + 1e-6)
+    kv = xh @ sd["wkv.weight"].t()
+    if "wkv.bias" in sd:
+        kv = kv + sd["wkv.bias"]
+    kv = kv.reshape(B, N, 2, heads, hd).permute(2, 0, 3, 1, 4)
+    k, v = kv[0], kv[1]
+    att = (q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(hd))          # SDPA scales AGAIN by 1/sqrt(hd) (:93)
+    out = att.softmax(-1) @ v                                        # [B, H, nq, hd]
+    x_cls = out.reshape(B, nq, C)                                    # :95 -- reshape of [B,H,nq,hd], no transpose
+    if training:                                                     # bn2 over (batch, queries) per channel (:96)
+        mu2, var2 = x_cls.mean((0, 1)), x_cls.var((0, 1), unbiased=False)
+    else:
+        mu2, var2 = sd["bn2.running_mean"], sd["bn2.running_var"]
+    x_cls = ((x_cls - mu2) / torch.sqrt(var2 + 1e-6)).mean(1)
+    return x_cls @ sd["linear.weight"].t() + sd["linear.bias"]
 
 
 # ----------------------------------------------------------------------------------------

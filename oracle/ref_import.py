@@ -159,6 +159,7 @@ def load():
     ns.attentionblock = importlib.import_module("src.models.attentionblock")
     ns.dino_head = importlib.import_module("src.models.dino_head")
     ns.classifier = importlib.import_module("src.models.classifier")
+    ns.layers = importlib.import_module("src.models.layers")
     ns.patch_embedding = importlib.import_module("src.utils.patch_embedding")
     ns.pos_embed = importlib.import_module("src.utils.pos_embed")
     ns.misc = importlib.import_module("src.utils.misc")

@@ -34,6 +34,10 @@ VIT_FULL_EXTRACT = dict(in_chans=3, img_size=96, patch_size=12, hidden_size=768,
                         qkv_bias=False)
 VIT_SMALL = dict(in_chans=3, img_size=48, patch_size=12, hidden_size=192, mlp_dim=384,
                  num_layers=2, num_heads=3, pos_embed="sincos", num_register_tokens=4, qkv_bias=True)
+# downstream variants: LoRA adapters on q/v (TRAIN.LORA) and NORM_LAYER: 'rmsnorm'.
+# "norm_layer" is kept as a string here (json-able); `resolve_norm` turns it into the class for a constructor.
+VIT_SMALL_LORA = dict(VIT_SMALL, lora=True)
+VIT_SMALL_RMS = dict(VIT_SMALL, norm_layer="rmsnorm", num_register_tokens=0, qkv_bias=False)
 DINO_HEAD_FULL = dict(in_dim=768, out_dim=65536, nlayers=3, hidden_dim=2048, bottleneck_dim=256)
 DINO_HEAD_SMALL = dict(in_dim=192, out_dim=1024, nlayers=3, hidden_dim=256, bottleneck_dim=64)
 
@@ -53,15 +57,28 @@ def _linear(sd, g: _Gen, name: str, out_f: int, in_f: int, bias: bool = True):
         sd[name + ".bias"] = g.normal((out_f,), std=0.02)
 
 
-def _block(sd, g: _Gen, pre: str, dim: int, mlp: int, qkv_bias: bool):
+def resolve_norm(cfg: Dict, rmsnorm_cls, layernorm_cls=torch.nn.LayerNorm) -> Dict:
+    """Constructor kwargs from a synth config: the "norm_layer" string becomes the class."""
+    out = dict(cfg)
+    if "norm_layer" in out:
+        out["norm_layer"] = rmsnorm_cls if out["norm_layer"] == "rmsnorm" else layernorm_cls
+    return out
+
+
+def _block(sd, g: _Gen, pre: str, dim: int, mlp: int, qkv_bias: bool, lora: bool = False, rms: bool = False):
     # child order mlp, att_norm, ffn_norm, attn (attentionblock.py:91-94)
     _linear(sd, g, pre + "mlp.linear1", mlp, dim)
     _linear(sd, g, pre + "mlp.linear2", dim, mlp)
     for n in ("att_norm", "ffn_norm"):
         sd[pre + n + ".weight"] = g.normal((dim,), std=0.1, mean=1.0)
-        sd[pre + n + ".bias"] = g.normal((dim,), std=0.05)
+        if not rms:
+            sd[pre + n + ".bias"] = g.normal((dim,), std=0.05)
     _linear(sd, g, pre + "attn.qkv", 3 * dim, dim, bias=qkv_bias)
     _linear(sd, g, pre + "attn.proj", dim, dim)
+    if lora:      # registration order B then A, r = 128 (attentionblock.py:18-19, :45-47); B made non-zero on purpose
+        for n in ("lora_q", "lora_v"):
+            sd[pre + f"attn.{n}.lora_matrix_B"] = g.normal((dim, 128), std=0.05)
+            sd[pre + f"attn.{n}.lora_matrix_A"] = g.normal((128, dim), std=dim ** -0.5)
 
 
 def _patch_embed(sd, g: _Gen, in_chans: int, size: int, patch: int, dim: int, pos_embed: str):
@@ -112,10 +129,12 @@ def vit_state_dict(cfg: Dict, seed: int = 0) -> "OrderedDict[str, torch.Tensor]"
     if cfg.get("num_register_tokens", 0):
         sd["register_tokens"] = g.normal((1, cfg["num_register_tokens"], H), std=0.02)
     _patch_embed(sd, g, cfg["in_chans"], cfg["img_size"], cfg["patch_size"], H, cfg["pos_embed"])
+    rms = cfg.get("norm_layer") == "rmsnorm"
     for i in range(cfg["num_layers"]):
-        _block(sd, g, f"blocks.{i}.", H, cfg["mlp_dim"], cfg["qkv_bias"])
+        _block(sd, g, f"blocks.{i}.", H, cfg["mlp_dim"], cfg["qkv_bias"], lora=cfg.get("lora", False), rms=rms)
     sd["norm.weight"] = g.normal((H,), std=0.1, mean=1.0)
-    sd["norm.bias"] = g.normal((H,), std=0.05)
+    if not rms:
+        sd["norm.bias"] = g.normal((H,), std=0.05)
     return sd
 
 
@@ -136,6 +155,20 @@ def linear_classifier_state_dict(dim: int, num_classes: int, seed: int = 0):
     sd["bn.running_mean"] = torch.zeros(dim)
     sd["bn.running_var"] = torch.ones(dim)
     sd["bn.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    _linear(sd, g, "linear", num_classes, dim)
+    return sd
+
+
+def attention_classifier_state_dict(dim: int, num_classes: int, num_queries: int = 1, qkv_bias: bool = False, seed: int = 0):
+    """Registration order of src/models/classifier.py:64-71: bn1, bn2, wkv, linear modules; cls_token parameter first."""
+    g = _Gen(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    sd["cls_token"] = g.normal((1, num_queries, dim), std=0.5)
+    for n in ("bn1", "bn2"):
+        sd[n + ".running_mean"] = torch.zeros(dim)
+        sd[n + ".running_var"] = torch.ones(dim)
+        sd[n + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+    _linear(sd, g, "wkv", 2 * dim, dim, bias=qkv_bias)
     _linear(sd, g, "linear", num_classes, dim)
     return sd
 

@@ -48,6 +48,25 @@ def test_multicrop_and_classifier_layout():
     assert list(_lay(c)) == [LAYOUT["linear_classifier"][0], LAYOUT["linear_classifier"][1]]
 
 
+def test_downstream_variant_layouts():
+    """LoRA adapters, RMSNorm blocks and the attentive probe keep the reference's state_dict layout."""
+    import headct_foundation_b200 as H
+    from oracle import synth
+    m = H.ViT(**synth.VIT_SMALL_LORA)
+    assert list(_lay(m)) == [LAYOUT["vit_small_lora"][0], LAYOUT["vit_small_lora"][1]]
+    H.set_requires_grad_false(m, lora=True)                                  # misc.py:349-359
+    trainable = {n for n, p in m.named_parameters() if p.requires_grad}
+    assert "blocks.0.attn.lora_q.lora_matrix_A" in trainable and "blocks.0.attn.qkv.bias" in trainable
+    assert "patch_embedding.position_embeddings" in trainable and "norm.weight" in trainable
+    assert "blocks.0.attn.qkv.weight" not in trainable and "cls_token" not in trainable
+    m = H.ViT(**synth.resolve_norm(synth.VIT_SMALL_RMS, H.RMSNorm))
+    assert list(_lay(m)) == [LAYOUT["vit_small_rms"][0], LAYOUT["vit_small_rms"][1]]
+    c = H.AttentionClassifier(96, 2, num_heads=2, qkv_bias=True, num_queries=3)
+    assert list(_lay(c)) == [LAYOUT["attention_classifier"][0], LAYOUT["attention_classifier"][1]]
+    with pytest.raises(NotImplementedError):
+        H.AttentionBlock(64, 128, 2, norm_layer=torch.nn.BatchNorm1d)
+
+
 @pytest.mark.parametrize("name", ["mae_small", "vit_small", "dino_head_small"])
 def test_same_seed_same_init_as_reference(name):
     import headct_foundation_b200 as H

@@ -45,7 +45,7 @@ def test_mae_oracle(name):
             assert _close(sdg[k[6:]].grad, g[k], 3e-3), k
 
 
-@pytest.mark.parametrize("name", ["vit_small", "vit_full_extract_b2", "vit_full_dino_b1"])
+@pytest.mark.parametrize("name", ["vit_small", "vit_full_extract_b2", "vit_full_dino_b1", "vit_small_lora", "vit_small_rms"])
 def test_vit_oracle(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     cfg = json.loads(str(g["cfg"]))
@@ -111,3 +111,33 @@ def test_optimizer_helpers():
     gs = [torch.tensor([3.0, 4.0]), torch.tensor([0.1])]
     norms = O.clip_per_param(gs, 1.0)
     assert norms[0] == 5.0 and abs(gs[0].norm().item() - 1.0) < 1e-5 and gs[1].item() == pytest.approx(0.1)
+
+
+def test_lora_gradients_oracle():
+    """LoRA fine-tuning (reshape quirk of attentionblock.py:57-59 included): oracle autograd == reference gradients."""
+    g = np.load(os.path.join(GOLD, "vit_small_lora_grads.npz"))
+    cfg = synth.VIT_SMALL_LORA
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.vit_state_dict(cfg, seed=6).items()}
+    x = synth.volume(2, cfg["in_chans"], cfg["img_size"], 5)
+    y, _ = O.vit_forward(sd, x, cfg["num_heads"])
+    w = torch.from_numpy(np.random.default_rng(int(g["out_weight_seed"])).standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * w).sum().backward()
+    for k in g.files:
+        if k.startswith("grad::"):
+            assert _close(sd[k[6:]].grad, g[k], 2e-3), k
+    assert bool(g["frozen_have_no_grad"])
+
+
+def test_attention_classifier_oracle():
+    g = np.load(os.path.join(GOLD, "attention_classifier.npz"))
+    for tag in ("q1", "q3"):
+        c = json.loads(str(g[tag + "_cfg"]))
+        sd = synth.attention_classifier_state_dict(c["dim"], 2, num_queries=c["nq"], qkv_bias=c["bias"], seed=51)
+        x = torch.from_numpy(g[tag + "_x"])
+        assert _close(O.attention_classifier(sd, x, c["heads"], training=True), g[tag + "_logits_train"], 1e-4)
+        sd["bn1.running_mean"], sd["bn1.running_var"] = torch.from_numpy(g[tag + "_bn1_mean"]), torch.from_numpy(g[tag + "_bn1_var"])
+        # bn2's running statistics after one training step: restated from the train-mode pooled features
+        B, N, C = x.shape
+        mu, var = x.mean((0, 1)), x.var((0, 1), unbiased=False)
+        assert _close(0.9 * torch.zeros(C) + 0.1 * mu, g[tag + "_bn1_mean"], 1e-5)
+        assert _close(0.9 * torch.ones(C) + 0.1 * var * (B * N) / (B * N - 1), g[tag + "_bn1_var"], 1e-5)
