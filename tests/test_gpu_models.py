@@ -339,3 +339,31 @@ def test_reference_engine_step_with_amp_gradscaler_and_torch_adamw(cuda):
         moved = (ref[k].detach() - sd0[k]).norm().item()
         assert moved > 0
         assert (got[k] - ref[k].detach()).norm().item() < 0.2 * moved + 1e-6, k      # the UPDATE itself agrees
+
+
+def test_graphed_forward_equals_eager(cuda):
+    """CUDA-graph replay of the extraction forward (utils/graphs.py): bit-identical to the eager launches, follows new
+    inputs, and re-captures after the weights changed."""
+    import headct_foundation_b200 as H
+    from oracle import synth
+    cfg = synth.VIT_SMALL
+    m = H.ViT(**cfg)
+    m.load_state_dict(synth.vit_state_dict(cfg, seed=6))
+    m = m.to(cuda).eval()
+    x1 = synth.volume(2, 3, 48, 5).to(cuda)
+    x2 = synth.volume(2, 3, 48, 9).to(cuda)
+    gf = H.GraphedForward(m, x1, clone=True)
+    with torch.no_grad():
+        e1, h1 = m(x1)
+        e2, h2 = m(x2)
+    g1, gh1 = gf(x1)
+    g2, gh2 = gf(x2)
+    assert torch.equal(g1, e1) and torch.equal(g2, e2) and not torch.equal(g1, g2)
+    assert all(torch.equal(a, b) for a, b in zip(gh2, h2)) and len(gh1) == cfg["num_layers"]
+    with torch.no_grad():
+        m.blocks[0].mlp.linear1.weight.mul_(1.5)                 # in-place update bumps the version counter
+        e3, _ = m(x2)
+    g3, _ = gf(x2)
+    assert torch.equal(g3, e3) and not torch.equal(g3, g2)
+    with pytest.raises(ValueError):
+        gf(x2[:1])

@@ -40,6 +40,12 @@ def extract():
         tf = 100.921 * B / ms
         print(json.dumps({"config": "extract_feature (ViT-B 3D, S=513, 12 hidden states materialised)", "batch": B,
                           "ms": ms, "volumes_per_s": B / ms * 1e3, "algorithmic_tflops": tf, "frac_of_peak": tf / PEAK}), flush=True)
+        if B <= 64:      # launch-bound range: the same forward replayed from a CUDA graph (utils/graphs.py)
+            gf = H.GraphedForward(m, x)
+            msg = timed(lambda: gf(x), warmup=2, steps=20)
+            print(json.dumps({"config": "extract_feature, CUDA-graph replay", "batch": B, "ms": msg, "volumes_per_s": B / msg * 1e3,
+                              "frac_of_peak": 100.921 * B / msg / PEAK, "speedup_vs_eager": ms / msg}), flush=True)
+            del gf
         del x
 
 
