@@ -545,9 +545,15 @@ int launch_bwd(const bf16* qkv, const bf16* dout, const float* lse, const float*
 int hct_attn_tc_tiles(int S, int tail_on_mma_sync);
 int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles, cudaStream_t st);
 int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
-                         int H, int hd, cudaStream_t st);
-static int g_attn_tc = 2;     // 0: mma.sync kernels only; 1: tcgen05, forward tail rows (S % 128 <= 32) on mma.sync; 2: tcgen05 for every tile
-extern "C" int hct_attention_set_tcgen05(int mode) { g_attn_tc = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return HCT_OK; }
+                         int H, int hd, int n_tiles, cudaStream_t st);
+// row kernel for the one row behind the last full tile in the backward (S = 128 k + 1; hct_attention_tail.cu)
+bool hct_attention_bwd_tail_supported(int S, int hd, int r0);
+int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
+                           int H, int hd, int r0, cudaStream_t st);
+// 0: mma.sync kernels only; 1: tcgen05, forward tail rows (S % 128 <= 32) on mma.sync; 2 (default): tcgen05 for every
+// forward tile, a single backward tail row (S % 128 == 1) on the row kernel; 3: tcgen05 for every tile, backward included
+static int g_attn_tc = 2;
+extern "C" int hct_attention_set_tcgen05(int mode) { g_attn_tc = mode < 0 ? 0 : (mode > 3 ? 3 : mode); return HCT_OK; }
 
 extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H, int32_t hd,
                                  hct_stream_t s) {
@@ -558,7 +564,7 @@ extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t
   int q_start = 0;
   if (g_attn_tc && (hd == 64 || hd == 48)) {
     // full 128-row query tiles on tcgen05; the few rows behind them (the cls token makes S = 128 k + 1) on mma.sync
-    const int n_tiles = hct_attn_tc_tiles(S, g_attn_tc == 1);
+    const int n_tiles = hct_attn_tc_tiles(S, g_attn_tc == 1);   // modes 2 and 3: every forward tile on tcgen05
     int rc = hct_attention_fwd_tc(qkv, out, lse, B, S, H, hd, n_tiles, st);
     if (rc != HCT_OK) return rc;
     q_start = n_tiles * 128;
@@ -582,7 +588,15 @@ extern "C" int hct_attention_bwd(const void* qkv, const void* out, const void* d
       static_cast<const bf16*>(out), static_cast<const bf16*>(dout), delta_ws, S, H, hd, total);
   int rc = hct_check_launch("attn_delta_kernel");
   if (rc) return rc;
-  if (g_attn_tc && (hd == 64 || hd == 48)) return hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, st);
+  if (g_attn_tc && (hd == 64 || hd == 48)) {
+    const int full = S / 128, r0 = full * 128;
+    if (g_attn_tc != 3 && r0 < S && hct_attention_bwd_tail_supported(S, hd, r0)) {
+      rc = hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, full, st);
+      if (rc) return rc;
+      return hct_attention_bwd_tail(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, r0, st);
+    }
+    return hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, (S + 127) / 128, st);
+  }
   const bf16* q = static_cast<const bf16*>(qkv);
   const bf16* d = static_cast<const bf16*>(dout);
   bf16* dq = static_cast<bf16*>(dqkv);

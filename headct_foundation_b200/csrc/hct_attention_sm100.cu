@@ -791,7 +791,7 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
 
 template <int HD>
 static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorMap& do128, const CUtensorMap& do64,
-                         const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, cudaStream_t st) {
+                         const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, int n_tiles, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) {
     int rc = set_smem(attn_bwd_dkdv_tc_kernel<HD>, BWD_SMEM); if (rc) return rc;
@@ -799,7 +799,7 @@ static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const 
     cfg = true;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
-  dim3 grid((S + TILE - 1) / TILE, H, B);
+  dim3 grid(n_tiles, H, B);          // 128-row tiles of keys (dK/dV) resp. queries (dQ); rows behind them: hct_attention_tail.cu
   attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale);
   int rc = hct_check_launch("attn_bwd_dkdv_tc_kernel");
   if (rc) return rc;
@@ -808,13 +808,13 @@ static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const 
 }
 
 int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
-                         int H, int hd, cudaStream_t st) {
+                         int H, int hd, int n_tiles, cudaStream_t st) {
   CUtensorMap q128, q64, do128, do64;
   const long long D = static_cast<long long>(H) * hd, D3 = 3 * D, rows = static_cast<long long>(B) * S;
   int rc = hct_make_tmap_bf16_2d(&q128, qkv, D3, rows, D3, 64, TILE); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&q64, qkv, D3, rows, D3, 64, 64); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&do128, dout, D, rows, D, 64, TILE); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&do64, dout, D, rows, D, 64, 64); if (rc) return rc;
-  if (hd == 64) return launch_bwd_tc<64>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, st);
-  return launch_bwd_tc<48>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, st);
+  if (hd == 64) return launch_bwd_tc<64>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, n_tiles, st);
+  return launch_bwd_tc<48>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, n_tiles, st);
 }

@@ -193,8 +193,10 @@ int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, const float* im
  * ------------------------------------------------------------------------------------------- */
 int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H,
                       int32_t hd, hct_stream_t stream);
-/* hd 64/48 kernel choice.  2 (default): tcgen05/TMEM kernels for every tile; 1: tcgen05, but the forward's
- * S %% 128 <= 32 tail rows on the mma.sync kernel; 0: mma.sync kernels only */
+/* hd 64/48 kernel choice.  2 (default): tcgen05/TMEM kernels for every forward tile and every full 128-row backward
+ * tile, a single row behind the last full tile (S = 128 k + 1 with the cls token) of dQ/dK/dV on a CUDA-core row kernel;
+ * 3: tcgen05 for every tile, backward tail tile included; 1: tcgen05, but the forward's S %% 128 <= 32 tail rows on the
+ * mma.sync kernel; 0: mma.sync kernels only */
 int hct_attention_set_tcgen05(int mode);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
 /* Diagnostics: clock64 event timeline of one CTA of the dK/dV backward kernel.  buf = device buffer of >= 768 int64

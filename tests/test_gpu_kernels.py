@@ -159,15 +159,17 @@ def test_layernorm_fwd_bwd(cuda, HF, rows, dim, eps):
 
 
 # ------------------------------------------------------------------ attention
-@pytest.mark.parametrize("mode", [2, 1, 0])
+@pytest.mark.parametrize("mode", [2, 3, 1, 0])
 @pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (3, 65, 2, 48),
+                                      (2, 260, 2, 48), (1, 136, 3, 64),      # 4 / 8 rows behind the last full tile
                                       (3, 17, 3, 64), (2, 64, 4, 32), (1, 1, 2, 64),
                                       # ragged tails: 38 / 8 / 44 / exactly 16 valid keys in the last 64-key block,
                                       # query tiles with 1-4 live warps, and exact multiples of the tile sizes
                                       (2, 230, 4, 48), (2, 200, 3, 64), (1, 300, 2, 48), (2, 144, 2, 64),
                                       (1, 128, 2, 64), (2, 256, 2, 48), (1, 385, 1, 64)])
 def test_attention_fwd_bwd(cuda, HF, B, S, H, hd, mode):
-    """mode 2: tcgen05 kernels for every tile (default); 1: forward tail rows on mma.sync; 0: mma.sync kernels only."""
+    """mode 2 (default): tcgen05 kernels, backward rows behind the last full 128-row tile on the row kernel; 3: tcgen05 for
+    every tile; 1: forward tail rows on mma.sync; 0: mma.sync kernels only."""
     from headct_foundation_b200._cabi import call, stream_ptr, lib
     if mode != 2 and (hd == 32 or S < 64):
         pytest.skip("mode only matters for the tcgen05 shapes")
@@ -204,6 +206,11 @@ def _attention_case(cuda, B, S, H, hd):
     for i, name in enumerate("qkv"):
         err = (d[:, :, i] - dr[:, :, i]).double().norm().item()
         assert err < 1.5e-2 * dr[:, :, i].double().norm().item() + 1e-5, name   # S = 1: dq and dk are exactly zero
+    r0 = S // 128 * 128
+    if 0 < r0 < S:          # the rows behind the last full tile on their own (a sliver of the norms above)
+        for i, name in enumerate("qkv"):
+            err = (d[:, r0:, i] - dr[:, r0:, i]).double().norm().item()
+            assert err < 1.5e-2 * dr[:, r0:, i].double().norm().item() + 1e-5, ("tail", name)
 
 
 # ------------------------------------------------------------------ masking (bit exact)

@@ -5,8 +5,8 @@ import torch
 from headct_foundation_b200._cabi import call, stream_ptr, lib
 
 dev = torch.device("cuda")
-MODES = [int(m) for m in (sys.argv[1] if len(sys.argv) > 1 else "2,1").split(",")]
-NAMES = {2: "tcgen05", 1: "tcgen05+mma.sync tail", 0: "mma.sync"}
+MODES = [int(m) for m in (sys.argv[1] if len(sys.argv) > 1 else "2,3").split(",")]
+NAMES = {2: "tcgen05 + bwd row-kernel tail", 3: "tcgen05 every tile", 1: "tcgen05+mma.sync fwd tail", 0: "mma.sync"}
 
 
 def timeit(fn, iters=5):
