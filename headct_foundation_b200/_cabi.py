@@ -82,6 +82,7 @@ _SIGNATURES = {
     "hct_gemm_trace": [C.c_void_p],
     "hct_profile_collect": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
     "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
+    "hct_adamw_multi_dev": [_P, _I32, _P, _F, _P, _F, _F, _F, _P],
     "hct_lora_shuffle": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
     "hct_colnorm_stats": [_P, _P, _I64, _I32, _F, _F, _P, _P, _P, _P, _P],
     "hct_colnorm_apply": [_P, _P, _P, _I32, _F, _P, _P, _I32, _I64, _I32, _P],

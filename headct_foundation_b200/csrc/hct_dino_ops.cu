@@ -224,7 +224,11 @@ __global__ void grad_sqnorm_multi_kernel(const long long* __restrict__ table, fl
 }
 
 __global__ void adamw_multi_kernel(const long long* __restrict__ table, const float* __restrict__ sqnorms, float clip,
-                                   float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt) {
+                                   float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                                   const float* __restrict__ hyper) {
+  if (hyper != nullptr) {      // per-step scalars from device memory: the launch can live in a CUDA graph
+    lr = hyper[0]; wd = hyper[1]; bc1 = hyper[2]; bc2_sqrt = hyper[3];
+  }
   const long long* e = table + 6LL * blockIdx.y;
   float* p = reinterpret_cast<float*>(e[0]);
   const float* g = reinterpret_cast<const float*>(e[1]);
@@ -331,6 +335,16 @@ extern "C" int hct_adamw_multi(const int64_t* table, int32_t n, const float* nor
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adamw_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(s)>>>(
-      reinterpret_cast<const long long*>(table), norms_ws, clip, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+      reinterpret_cast<const long long*>(table), norms_ws, clip, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), nullptr);
+  return hct_check_launch("adamw_multi_kernel");
+}
+
+extern "C" int hct_adamw_multi_dev(const int64_t* table, int32_t n, const float* norms_ws, float clip, const float* hyper,
+                                   float beta1, float beta2, float eps, hct_stream_t s) {
+  if (n <= 0) return HCT_OK;
+  HCT_REQUIRE(n <= 65535 && hyper != nullptr, "adamw_multi_dev: n=%d hyper=%p", n, (const void*)hyper);
+  HCT_REQUIRE(clip <= 0.f || norms_ws != nullptr, "adamw_multi_dev: clip > 0 needs norms_ws");
+  adamw_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(s)>>>(
+      reinterpret_cast<const long long*>(table), norms_ws, clip, 0.f, beta1, beta2, eps, 0.f, 1.f, 1.f, hyper);
   return hct_check_launch("adamw_multi_kernel");
 }

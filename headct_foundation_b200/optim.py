@@ -21,6 +21,7 @@ class FusedAdamW(torch.optim.Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, clip_grad=clip_grad)
         super().__init__(params, defaults)
         self._tables = {}
+        self._graph_state = {}
 
     def _table(self, gi, group):
         ps = [p for p in group["params"] if p.grad is not None]
@@ -73,3 +74,74 @@ class FusedAdamW(torch.optim.Optimizer):
                  float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), step, st)
             mark_updated(ps, shadows)     # the kernel wrote parameters (and their bf16 copies) through raw pointers
         return loss
+
+    # ------------------------------------------------------------------ CUDA-graph support (utils/graphs.py)
+    def _hyper_values(self, group, step: int):
+        b1, b2 = group["betas"]
+        return [float(group["lr"]), float(group["weight_decay"]), 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5]
+
+    def prepare_capture(self):
+        """Allocate the buffers the captured update reads (pointer table, norm workspace, per-step scalars) OUTSIDE the
+        capture: memory allocated while capturing belongs to the graph's pool and its initialising fill would be replayed,
+        wiping the scalars staged by `advance()`."""
+        for gi, group in enumerate(self.param_groups):
+            n = len(group["params"])
+            dev = group["params"][0].device
+            self._graph_state[gi] = dict(table_host=torch.zeros((n, 6), dtype=torch.int64).pin_memory(),
+                                         table=torch.zeros((n, 6), dtype=torch.int64, device=dev),
+                                         norms=torch.zeros(n, dtype=torch.float32, device=dev),
+                                         hyper=torch.zeros(4, dtype=torch.float32, device=dev), params=[], shadows=[])
+
+    @torch.no_grad()
+    def step_captured(self):
+        """Enqueue the update with every per-step scalar read from device memory (`hct_adamw_multi_dev`): call it inside a
+        CUDA-graph capture (after `prepare_capture()`), then `advance()` before each replay.  The pointer table reaches
+        the device through a captured copy from pinned memory (the gradients' addresses are only known while capturing)."""
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            gs = self._graph_state.get(gi)
+            if gs is None:
+                raise RuntimeError("call FusedAdamW.prepare_capture() before capturing")
+            dev = ps[0].device
+            rows, shadows = [], []
+            for p in ps:
+                st = self.state[p]
+                if len(st) == 0:
+                    raise RuntimeError("run at least one eager step before capturing (optimizer state must exist)")
+                if not p.grad.is_contiguous():
+                    raise RuntimeError("FusedAdamW.step_captured needs contiguous gradients")
+                sh = shadow_of(p)
+                shadows.append(sh)
+                rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                             0 if sh is None else sh.data_ptr()))
+            n = len(rows)
+            gs["table_host"][:n].copy_(torch.tensor(rows, dtype=torch.int64))
+            gs["params"], gs["shadows"] = ps, shadows
+            gs["table"].copy_(gs["table_host"], non_blocking=True)        # captured H2D node from pinned memory
+            st = stream_ptr(dev)
+            clip = float(group.get("clip_grad", 0.0) or 0.0)
+            if clip > 0:
+                call("hct_grad_norms_multi", gs["table"].data_ptr(), n, gs["norms"].data_ptr(), st)
+            b1, b2 = group["betas"]
+            call("hct_adamw_multi_dev", gs["table"].data_ptr(), n, gs["norms"].data_ptr(), clip,
+                 gs["hyper"].data_ptr(), float(b1), float(b2), float(group["eps"]), st)
+
+    @torch.no_grad()
+    def advance(self):
+        """Host side of one replayed step: bump the step counters, stage lr / weight decay / bias corrections for the
+        captured launch (async copy on the current stream, ahead of the replay) and re-key the bf16 weight copies."""
+        for gi, group in enumerate(self.param_groups):
+            gs = self._graph_state.get(gi)
+            if gs is None or not gs["params"]:
+                continue
+            ps = gs["params"]
+            step = int(self.state[ps[0]]["step"].item()) + 1
+            for p in ps:
+                self.state[p]["step"] += 1
+            # a fresh pinned staging tensor per step: torch's host allocator keeps it alive until the copy has run, so the
+            # host may run ahead of the GPU by several steps without overwriting values still in flight
+            staged = torch.tensor(self._hyper_values(group, step), dtype=torch.float32).pin_memory()
+            gs["hyper"].copy_(staged, non_blocking=True)
+            mark_updated(ps, gs["shadows"])

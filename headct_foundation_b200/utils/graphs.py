@@ -1,4 +1,4 @@
-"""CUDA-graph replay of a launch-bound forward.
+"""CUDA-graph replay of launch-bound forwards and training steps.
 
 Feature extraction at small batch (`notebooks/extract_feature_sample.ipynb` cell 12: `model(x)` under no_grad; BASELINE
 config 5 sweeps batch 1-512) enqueues ~90 kernels of a few microseconds each through the C ABI, so below batch ~16 the
@@ -68,3 +68,72 @@ class GraphedForward:
         self.static_in.copy_(x, non_blocking=True)
         self.graph.replay()
         return _tree_map(torch.clone, self.static_out) if self.clone else self.static_out
+
+
+class GraphedTrainStep:
+    """One whole training step -- zero_grad, forward, loss, backward, per-parameter clip + AdamW -- as ONE graph launch.
+
+    Enqueueing the ~490 kernels of an MAE step through Python / ctypes costs the host ~13 ms, which caps small per-GPU
+    batches (13 ms of GPU work at batch 32); the reference pays the same kind of cost through eager PyTorch plus 254
+    `.item()` syncs (engine_pretrain_mae.py:52-86, misc.py:374-383).  Usage:
+
+        step = GraphedTrainStep(model, FusedAdamW(...), example_batch)     # `model(x)` must return the loss first
+        for x in loader:
+            optimizer.param_groups[0]["lr"] = schedule(it)                 # read at replay time (device-side scalars)
+            loss = step(x)                                                 # static loss tensor, read it before the next call
+
+    Everything the step needs per iteration lives in device memory (`FusedAdamW.step_captured` / `advance`); the mask
+    noise comes from torch's CUDA generator, which is graph-aware.  Single process only: under DDP the gradient
+    all-reduce has to sit between backward and the update, so multi-GPU runs keep the eager path.
+    """
+
+    def __init__(self, model: torch.nn.Module, optimizer, example: torch.Tensor, loss_of=None, warmup: int = 3):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs a CUDA example input (no CPU fallback)")
+        if not hasattr(optimizer, "step_captured"):
+            raise TypeError("GraphedTrainStep needs headct_foundation_b200.optim.FusedAdamW")
+        self.model, self.optimizer = model, optimizer
+        self.loss_of = loss_of or (lambda out: out[0] if isinstance(out, (tuple, list)) else out)
+        self.static_in = example.detach().clone()
+        dev = example.device
+        # eager warm-up (optimizer state, bf16 weight copies, allocator, lazy kernel attributes) on a side stream; the
+        # parameters and the optimizer state it touches are put back afterwards, so capturing does not train the model
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        saved_p = [p.detach().clone() for p in params]
+        saved_s = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in optimizer.state[p].items()} if p in optimizer.state
+                   and len(optimizer.state[p]) else None for p in params]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                optimizer.zero_grad(set_to_none=True)
+                self.loss_of(model(self.static_in)).backward()
+                optimizer.step()
+            with torch.no_grad():
+                for p, sp, ss in zip(params, saved_p, saved_s):
+                    p.copy_(sp)
+                    st = optimizer.state.get(p)
+                    if st:
+                        for k, v in st.items():
+                            if torch.is_tensor(v):
+                                v.copy_(ss[k]) if ss is not None else v.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        del saved_p, saved_s
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        optimizer.prepare_capture()
+        with torch.cuda.graph(self.graph):
+            loss = self.loss_of(model(self.static_in))
+            loss.backward()
+            optimizer.step_captured()
+        self.static_loss = loss.detach()
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if x.shape != self.static_in.shape or x.dtype != self.static_in.dtype:
+            raise ValueError(f"GraphedTrainStep was captured for {tuple(self.static_in.shape)} {self.static_in.dtype}, "
+                             f"got {tuple(x.shape)} {x.dtype}")
+        self.static_in.copy_(x, non_blocking=True)
+        self.optimizer.advance()
+        self.graph.replay()
+        return self.static_loss

@@ -281,6 +281,11 @@ int hct_grad_norms_multi(const int64_t* table, int32_t n, float* norms_ws, hct_s
 int hct_adamw_multi(const int64_t* table, int32_t n, const float* norms_ws, float clip, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int32_t step,
                     hct_stream_t stream);
+/* Same update with the per-step scalars read from DEVICE memory, so that the launch can be captured in a CUDA graph and
+ * replayed while the schedule moves: hyper fp32 [4] = {lr, weight_decay, 1 - beta1^step, sqrt(1 - beta2^step)}
+ * (lr_sched.py:18-55 changes lr every iteration; the bias corrections change with the step count). */
+int hct_adamw_multi_dev(const int64_t* table, int32_t n, const float* norms_ws, float clip, const float* hyper,
+                        float beta1, float beta2, float eps, hct_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Downstream heads: LoRA q/v adapters, BatchNorm1d over token rows, attentive pooling.

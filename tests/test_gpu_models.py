@@ -367,3 +367,56 @@ def test_graphed_forward_equals_eager(cuda):
     assert torch.equal(g3, e3) and not torch.equal(g3, g2)
     with pytest.raises(ValueError):
         gf(x2[:1])
+
+
+def test_graphed_train_step_follows_eager(cuda):
+    """One CUDA-graph launch per training step (utils/graphs.py) trains like the eager step: same losses and weights over
+    several steps with a moving learning rate (read from device memory at replay), and capturing leaves the model and
+    the optimizer state untouched."""
+    import headct_foundation_b200 as H
+    from headct_foundation_b200.optim import FusedAdamW
+    from oracle import synth
+    cfg = synth.MAE_SMALL
+    sd = synth.mae_state_dict(cfg, seed=2)
+    noise = synth.noise(2, (cfg["input_size"] // cfg["patch_size"]) ** 3, seed=3).to(cuda)
+    xs = [synth.volume(2, cfg["in_chans"], cfg["input_size"], 20 + i).to(cuda) for i in range(4)]
+
+    def build():
+        m = H.MaskedAutoencoderViT(**cfg)
+        m.load_state_dict(sd, strict=True)
+        m = m.to(cuda).train()
+        m.noise_override = noise
+        opt = FusedAdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05,
+                         clip_grad=3.0)
+        return m, opt
+
+    m1, o1 = build()
+    eager = []
+    for i, x in enumerate(xs):
+        o1.param_groups[0]["lr"] = 1e-3 * (i + 1)
+        o1.zero_grad(set_to_none=True)
+        loss = m1(x)[0]
+        loss.backward()
+        o1.step()
+        eager.append(loss.item())
+    m2, o2 = build()
+    step = H.GraphedTrainStep(m2, o2, xs[0])
+    for k, v in m2.state_dict().items():                          # the warm-up inside the capture was rolled back
+        assert torch.equal(v.cpu(), sd[k]), k
+    graphed = []
+    for i, x in enumerate(xs):
+        o2.param_groups[0]["lr"] = 1e-3 * (i + 1)
+        graphed.append(step(x).item())
+    assert all(abs(a - b) < 2e-3 * abs(a) for a, b in zip(eager, graphed)), (eager, graphed)
+    assert eager[0] != eager[-1]
+    p0 = next(iter(o2.state))
+    assert int(o2.state[p0]["step"].item()) == len(xs)
+    # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is at the noise level of the
+    # split-K atomics differ between ANY two runs, so the weights are compared by direction, the trajectory by its losses
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert _cos(a.detach().cpu(), b.detach().cpu()) > 0.99, k
+        assert _cos((a.detach().cpu() - sd[k]), (b.detach().cpu() - sd[k])) > 0.9 or (a.detach().cpu() - sd[k]).norm() < 1e-6, k
+    # eager use after replays sees the updated weights (bf16 copies re-keyed by advance())
+    with torch.no_grad():
+        l1, l2 = m1(xs[0])[0].item(), m2(xs[0])[0].item()
+    assert abs(l1 - l2) < 2e-3 * abs(l1)
