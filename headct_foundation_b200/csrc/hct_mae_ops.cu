@@ -440,6 +440,97 @@ __global__ void crop_resize_area_kernel(const void* __restrict__ src, const Crop
   }
 }
 
+// Row-staged version (source rows of <= 256 elements, 16-byte aligned).  One warp per OUTPUT row (j, all k) of one
+// output plane: the <= 3 x 3 source rows of its averaging window are fetched with one 16-byte (fp16) / 32-byte (fp32)
+// load per lane and summed element-wise in registers -- each source element is touched by ONE instruction instead of
+// once per overlapping output window -- then the summed row goes through a per-warp shared-memory line and every lane
+// adds up the <= 3 entries of its three output columns.  No CTA-wide synchronisation.
+constexpr int CROP_ROW_MAX = 256;
+constexpr int CROP_MAX_K = 4;                                 // output columns per lane: T2 <= 128
+template <bool IN_F16>
+__global__ void __launch_bounds__(256)
+crop_resize_area_rows_kernel(const void* __restrict__ src, const CropBox* __restrict__ boxes,
+                             const float* __restrict__ offsets, float* __restrict__ out,
+                             int C, int S0, int S1, int S2, int T0, int T1, int T2) {
+  __shared__ __align__(16) float rowbuf[8][CROP_ROW_MAX + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // ---- per plane (once per CTA): which crop / channel / output slice, its source planes
+  const int plane = blockIdx.x;                               // (crop * C + c) * T0 + i_out
+  const int i_out = plane % T0;
+  const int nc = plane / T0;
+  const int n = nc / C, c = nc - n * C;
+  const CropBox bx = boxes[n];
+  const float off = offsets != nullptr ? offsets[n] : 0.f;
+  const int i = (bx.flips & 1) ? T0 - 1 - i_out : i_out;
+  const long long vbase = (static_cast<long long>(bx.sample) * C + c) * S0;
+  const int a0 = static_cast<int>((static_cast<long long>(i) * bx.n0) / T0);
+  const int b0 = static_cast<int>((static_cast<long long>(i + 1) * bx.n0 + T0 - 1) / T0);
+  const int g0a = max(bx.s0 + a0, 0), g0b = min(bx.s0 + b0, S0);
+  // the columns this crop can touch, widened to whole 8-element groups
+  const int c_lo = max(bx.s2, 0) & ~7, c_hi = min(bx.s2 + bx.n2, S2);
+  const int e0 = c_lo + lane * 8;
+  const bool active = e0 < c_hi;
+  // ---- per lane (once): the column windows of its output columns k_out = lane + 32 m, as offsets into the row line
+  int w_lo[CROP_MAX_K], w_hi[CROP_MAX_K];
+  float w_inv[CROP_MAX_K];
+#pragma unroll
+  for (int m = 0; m < CROP_MAX_K; ++m) {
+    const int k_out = lane + 32 * m;
+    w_lo[m] = 0; w_hi[m] = 0; w_inv[m] = 0.f;
+    if (k_out < T2) {
+      const int k = (bx.flips & 4) ? T2 - 1 - k_out : k_out;
+      const int a2 = (k * bx.n2) / T2, b2 = ((k + 1) * bx.n2 + T2 - 1) / T2;
+      w_lo[m] = max(bx.s2 + a2, 0) - c_lo;
+      w_hi[m] = min(bx.s2 + b2, S2) - c_lo;
+      w_inv[m] = 1.f / static_cast<float>((b0 - a0) * (b2 - a2));
+    }
+  }
+  float* rb = rowbuf[warp];
+  float* dplane = out + static_cast<long long>(plane) * T1 * T2;
+  // ---- one output row per warp and iteration
+  for (int j_out = warp; j_out < T1; j_out += 8) {
+    const int j = (bx.flips & 2) ? T1 - 1 - j_out : j_out;
+    const int a1 = (j * bx.n1) / T1, b1 = ((j + 1) * bx.n1 + T1 - 1) / T1;
+    const int g1a = max(bx.s1 + a1, 0), g1b = min(bx.s1 + b1, S1);
+    float sum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (active) {
+      // (issuing the window's loads in predicated batches of eight was tried: the extra predication / conversion work
+      // cost more than the exposed latency it hid -- 6.5 ms against 5.05 ms for the 256-crop DINO batch)
+      for (int g0 = g0a; g0 < g0b; ++g0) {
+        const long long prow = ((vbase + g0) * S1) * S2 + e0;
+        for (int g1 = g1a; g1 < g1b; ++g1) {
+          const long long row = prow + static_cast<long long>(g1) * S2;
+          if (IN_F16) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + row));
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 f = __half22float2(h[q]); sum[2 * q] += f.x; sum[2 * q + 1] += f.y; }
+          } else {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + row));
+            const float4 y = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + row) + 1);
+            sum[0] += x.x; sum[1] += x.y; sum[2] += x.z; sum[3] += x.w; sum[4] += y.x; sum[5] += y.y; sum[6] += y.z; sum[7] += y.w;
+          }
+        }
+      }
+    }
+    __syncwarp();                                             // the previous row's readers are done with the line
+    *reinterpret_cast<float4*>(rb + lane * 8) = make_float4(sum[0], sum[1], sum[2], sum[3]);
+    *reinterpret_cast<float4*>(rb + lane * 8 + 4) = make_float4(sum[4], sum[5], sum[6], sum[7]);
+    __syncwarp();
+    const float inv1 = 1.f / static_cast<float>(b1 - a1);
+    float* dst = dplane + j_out * T2;
+#pragma unroll
+    for (int m = 0; m < CROP_MAX_K; ++m) {
+      const int k_out = lane + 32 * m;
+      if (k_out < T2) {
+        float acc = 0.f;
+        for (int g2 = w_lo[m]; g2 < w_hi[m]; ++g2) acc += rb[g2];
+        dst[k_out] = acc * w_inv[m] * inv1 + off;
+      }
+    }
+  }
+}
+
 // RandAdjustContrast (transforms.py:92): ((x - min) / (range + 1e-7))^gamma * range + min over the whole sample.
 // Pass 1: per-sample min / max (ordered-int atomics); pass 2: apply to the samples whose gamma is set (> 0).
 __device__ __forceinline__ int float_ordered(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -654,6 +745,9 @@ extern "C" int hct_gaussian_smooth_axis(const float* in, const int32_t* in_idx, 
   return hct_check_launch("gauss_axis_kernel");
 }
 
+static int g_crop_rows = 1;      // 0: per-voxel gather only (A/B comparison, tools/augment_bench.py)
+extern "C" int hct_crop_resize_set_rows(int enable) { g_crop_rows = enable != 0; return HCT_OK; }
+
 extern "C" int hct_crop_resize_area(const void* src, int32_t src_f16, const int32_t* boxes, const float* offsets, float* out, int64_t ncrops,
                                     int32_t C, int32_t S0, int32_t S1, int32_t S2, int32_t T0, int32_t T1, int32_t T2,
                                     hct_stream_t s) {
@@ -663,6 +757,14 @@ extern "C" int hct_crop_resize_area(const void* src, int32_t src_f16, const int3
   HCT_REQUIRE(planes <= 2147483647LL, "crop_resize_area: too many planes (%lld)", planes);
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const CropBox* bx = reinterpret_cast<const CropBox*>(boxes);
+  const size_t elt = src_f16 ? 2 : 4;
+  if (g_crop_rows && S2 % 8 == 0 && S2 <= CROP_ROW_MAX && (reinterpret_cast<uintptr_t>(src) % 16) == 0 && T2 <= 32 * CROP_MAX_K &&
+      (static_cast<size_t>(S2) * elt) % 16 == 0) {
+    dim3 grid(static_cast<unsigned>(planes));
+    if (src_f16) crop_resize_area_rows_kernel<true><<<grid, 256, 0, st>>>(src, bx, offsets, out, C, S0, S1, S2, T0, T1, T2);
+    else crop_resize_area_rows_kernel<false><<<grid, 256, 0, st>>>(src, bx, offsets, out, C, S0, S1, S2, T0, T1, T2);
+    return hct_check_launch("crop_resize_area_rows_kernel");
+  }
   if (src_f16) crop_resize_area_kernel<true><<<static_cast<unsigned>(planes), 256, 0, st>>>(src, bx, offsets, out, C, S0, S1, S2, T0, T1, T2);
   else crop_resize_area_kernel<false><<<static_cast<unsigned>(planes), 256, 0, st>>>(src, bx, offsets, out, C, S0, S1, S2, T0, T1, T2);
   return hct_check_launch("crop_resize_area_kernel");

@@ -262,6 +262,8 @@ int hct_gaussian_smooth_axis(const float* in, const int32_t* in_idx, float* out,
  * ResizeWithPadOrCrop); flip bit k reverses OUTPUT axis k; offsets fp32 [ncrops] or NULL is added last.
  * src fp16 / fp32 [B, C, S0, S1, S2]; out fp32 [ncrops, C, T0, T1, T2].
  * Area resize = adaptive average pooling, windows [floor(i n / T), ceil((i + 1) n / T)). */
+/* 1 (default): row-staged kernel when the source rows allow it (S2 %% 8 == 0, S2 <= 256); 0: per-voxel gather only */
+int hct_crop_resize_set_rows(int enable);
 int hct_crop_resize_area(const void* src, int32_t src_f16, const int32_t* boxes, const float* offsets, float* out, int64_t ncrops,
                          int32_t C, int32_t S0, int32_t S1, int32_t S2, int32_t T0, int32_t T1, int32_t T2,
                          hct_stream_t stream);

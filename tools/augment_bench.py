@@ -50,6 +50,11 @@ write_gb = 4 * Bd * 3 * 96 ** 3 * 4 / 1e9
 msc = timeit(lambda: HF.crop_resize_area(src, draws["boxes"], (96, 96, 96), draws["flips"], draws["offsets"]), n=5)
 print(f"DINO crop+area-resize+flip+shift, {4 * Bd} crops: {msc:.3f} ms  {(read_gb + write_gb) / msc * 1e3:.0f} GB/s "
       f"({(read_gb + write_gb) / msc * 1e3 / HBM:.2f} of HBM copy bandwidth); algorithmic {read_gb:.2f} GB read + {write_gb:.2f} GB written")
+from headct_foundation_b200._cabi import lib as _lib
+_lib().hct_crop_resize_set_rows(0)
+mso = timeit(lambda: HF.crop_resize_area(src, draws["boxes"], (96, 96, 96), draws["flips"], draws["offsets"]), n=5)
+_lib().hct_crop_resize_set_rows(1)
+print(f"  (per-voxel gather kernel, for comparison: {mso:.3f} ms)")
 msd = timeit(lambda: dino.apply(src, draws), n=5)
 print(f"DINO full multi-crop augment B={Bd}: {msd:.3f} ms per batch ({Bd / msd * 1e3:.0f} volumes/s), "
       f"{int((draws['sigma'][:, 0] > 0).sum())} smoothed, {int((draws['gamma'] > 0).sum())} contrast-adjusted")
