@@ -315,7 +315,7 @@ template <int HD>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                         const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
-                        const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+                        const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale, int merge_tail) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -334,6 +334,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   const int D = H * HD;
   const int nqb = (S + 63) / 64;
   const bool tail16 = S - (nqb - 1) * 64 <= 16;             // last query block is computed 16 columns wide
+  // merged tail: the 16-wide last block is computed TOGETHER with block 0 -- its S^T / dP^T park in the dV / dK
+  // accumulator columns, which are not live before block 0's second-stage MMAs -- so the MMA -> softmax -> MMA chain is
+  // one step shorter (9 -> 8 at S = 513, 3 -> 2 at S = 129).  Ring entries: 0 = block 0, 1 = tail block, e >= 2 = block e - 1.
+  const bool merge = merge_tail != 0 && tail16 && nqb >= 2;
+  const int nsteps = merge ? nqb - 1 : nqb;
   const float sl2 = scale * LOG2E;
 
   if (threadIdx.x == 0) {
@@ -359,15 +364,16 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
       tma_load_2d(smem_u32(sK), &tmQKV128, kv_full, D + h * HD, b * S + kt * TILE);
       tma_load_2d(smem_u32(sV), &tmQKV128, kv_full, 2 * D + h * HD, b * S + kt * TILE);
     }
-    for (int i = 0; i < nqb; ++i) {
+    for (int i = 0; i < nqb; ++i) {                   // i = ring entry
       const int st = i % BWD_STAGES;
+      const int blk = merge ? (i == 0 ? 0 : (i == 1 ? nqb - 1 : i - 1)) : i;
       TRACE(0 * 256 + i * 8 + 0);
       mbar_wait(&qdo_empty[st], ((i / BWD_STAGES) & 1) ^ 1u);
       TRACE(0 * 256 + i * 8 + 1);
       if (leader) {
         mbar_expect_tx(&qdo_full[st], 2 * HALF_BYTES);
-        tma_load_2d(smem_u32(sQ + st * HALF_BYTES), &tmQKV64, &qdo_full[st], h * HD, b * S + i * 64);
-        tma_load_2d(smem_u32(sdO + st * HALF_BYTES), &tmDO64, &qdo_full[st], h * HD, b * S + i * 64);
+        tma_load_2d(smem_u32(sQ + st * HALF_BYTES), &tmQKV64, &qdo_full[st], h * HD, b * S + blk * 64);
+        tma_load_2d(smem_u32(sdO + st * HALF_BYTES), &tmDO64, &qdo_full[st], h * HD, b * S + blk * 64);
       }
       __syncwarp();
       TRACE(0 * 256 + i * 8 + 2);
@@ -381,14 +387,16 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     const uint64_t dK_ = make_sdesc_sw128(smem_u32(sK), false, 0);
     const uint64_t dV_ = make_sdesc_sw128(smem_u32(sV), false, 0);
     mbar_wait(kv_full, 0);
-    auto issue_sdp = [&](int i) {          // S^T = K Q_i^T and dP^T = V dO_i^T into TMEM
-      const int st = i % BWD_STAGES;
+    auto issue_sdp = [&](int i) {          // step i: S^T = K Q_i^T and dP^T = V dO_i^T into TMEM
+      const int e = merge ? (i == 0 ? 0 : i + 1) : i;      // ring entry of the step's 64-wide block
+      const int st = e % BWD_STAGES;
       TRACE(1 * 256 + i * 8 + 0);
-      mbar_wait(&qdo_full[st], (i / BWD_STAGES) & 1);
+      mbar_wait(&qdo_full[st], (e / BWD_STAGES) & 1);
+      if (merge && i == 0) mbar_wait(&qdo_full[1], 0);     // the tail block's tiles (entry 1)
       TRACE(1 * 256 + i * 8 + 1);
       tc_fence_after();
       if (leader) {
-        const uint32_t id = (i == nqb - 1 && tail16) ? idesc_s16 : idesc_s;
+        const uint32_t id = (!merge && i == nqb - 1 && tail16) ? idesc_s16 : idesc_s;
         const uint64_t dQk = make_sdesc_sw128(smem_u32(sQ + st * HALF_BYTES), false, 0);
         const uint64_t dOk = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), false, 0);
 #pragma unroll
@@ -396,14 +404,24 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
           tc_mma(tmem_S, dK_ + ks * 2, dQk + ks * 2, id, ks > 0 ? 1u : 0u);
           tc_mma(tmem_dP, dV_ + ks * 2, dOk + ks * 2, id, ks > 0 ? 1u : 0u);
         }
+        if (merge && i == 0) {                      // tail block, 16 wide, parked in the (not yet live) dV / dK columns
+          const uint64_t dQt = make_sdesc_sw128(smem_u32(sQ + 1 * HALF_BYTES), false, 0);
+          const uint64_t dOt = make_sdesc_sw128(smem_u32(sdO + 1 * HALF_BYTES), false, 0);
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            tc_mma(tmem_dV, dK_ + ks * 2, dQt + ks * 2, idesc_s16, ks > 0 ? 1u : 0u);
+            tc_mma(tmem_dK, dV_ + ks * 2, dOt + ks * 2, idesc_s16, ks > 0 ? 1u : 0u);
+          }
+        }
         tc_commit(s_full);
       }
       __syncwarp();
       TRACE(1 * 256 + i * 8 + 2);
     };
     issue_sdp(0);
-    for (int i = 0; i < nqb; ++i) {
-      const int st = i % BWD_STAGES;
+    for (int i = 0; i < nsteps; ++i) {
+      const int e = merge ? (i == 0 ? 0 : i + 1) : i;
+      const int st = e % BWD_STAGES;
       TRACE(1 * 256 + i * 8 + 3);
       mbar_wait(p_full, i & 1);                       // P^T / dS^T of block i sit in TMEM (and every warp has read S^T / dP^T)
       TRACE(1 * 256 + i * 8 + 4);
@@ -413,7 +431,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         const uint64_t dOm = make_sdesc_sw128(smem_u32(sdO + st * HALF_BYTES), true, HALF_BYTES);
         const uint32_t acc = i > 0 ? 1u : 0u;
         // k-step ks covers queries [16 ks, 16 ks + 16): packed by warp group ks / 2 at column 32 (ks / 2) + 8 (ks % 2)
-        if (i == nqb - 1 && tail16) {
+        if (!merge && i == nqb - 1 && tail16) {
           tc_mma_ts(tmem_dV, tmem_S, dOm, idesc_g, acc);
           tc_mma_ts(tmem_dK, tmem_dP, dQm, idesc_g, acc);
         } else {
@@ -423,12 +441,19 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
             tc_mma_ts(tmem_dK, tmem_dP + (ks >> 1) * 32 + (ks & 1) * 8, dQm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
           }
         }
+        if (merge && i == 0) {      // the tail block's P^T / dS^T were packed into the free columns [16, 24) of each region
+          const uint64_t dQt = make_sdesc_sw128(smem_u32(sQ + 1 * HALF_BYTES), true, HALF_BYTES);
+          const uint64_t dOt = make_sdesc_sw128(smem_u32(sdO + 1 * HALF_BYTES), true, HALF_BYTES);
+          tc_mma_ts(tmem_dV, tmem_S + 16, dOt, idesc_g, 1u);
+          tc_mma_ts(tmem_dK, tmem_dP + 16, dQt, idesc_g, 1u);
+          tc_commit(&qdo_empty[1]);
+        }
         tc_commit(&qdo_empty[st]);
-        if (i == nqb - 1) tc_commit(done);
+        if (i == nsteps - 1) tc_commit(done);
       }
       __syncwarp();
       TRACE(1 * 256 + i * 8 + 5);
-      if (i + 1 < nqb) issue_sdp(i + 1);
+      if (i + 1 < nsteps) issue_sdp(i + 1);
     }
   } else if (warp < 8) {
     // ===================== softmax-backward threads: one KEY row per thread =====================
@@ -446,19 +471,24 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
     auto load_lse = [&](int i) { const int qr = i * 64 + wg * 32 + lane; return qr < S ? lse_g[qr] : 0.f; };
     auto load_delta = [&](int i) { const int qr = i * 64 + wg * 32 + lane; return qr < S ? delta_g[qr] : 0.f; };
     float ls_n = load_lse(0), dl_n = load_delta(0);
-    for (int i = 0; i < nqb; ++i) {
+    for (int i = 0; i < nsteps; ++i) {
       long long* tr = (warp == 0 && lane == 0) ? trace : nullptr;
       float* stat = wstat + (i & 1) * 64;
       stat[lane] = ls_n * LOG2E;
       stat[32 + lane] = dl_n;
+      if (merge && i == 0 && wg == 0) {               // statistics of the tail block's queries: the other (still unused) buffer
+        const int qr = (nqb - 1) * 64 + lane;
+        wstat[64 + lane] = (lane < 16 && qr < S) ? lse_g[qr] * LOG2E : 0.f;
+        wstat[96 + lane] = (lane < 16 && qr < S) ? delta_g[qr] : 0.f;
+      }
       __syncwarp();
-      if (i + 1 < nqb) { ls_n = load_lse(i + 1); dl_n = load_delta(i + 1); }
+      if (i + 1 < nsteps) { ls_n = load_lse(i + 1); dl_n = load_delta(i + 1); }
       if (tr) tr[2 * 256 + i * 8 + 0] = clock64();
       mbar_wait(s_full, i & 1);
       if (tr) tr[2 * 256 + i * 8 + 1] = clock64();
       tc_fence_after();
       const int ncol = min(64, S - i * 64);                    // valid query columns in this block
-      const bool t16 = (i == nqb - 1) && tail16;
+      const bool t16 = !merge && (i == nqb - 1) && tail16;
       if (warp_active && !(t16 && wg == 1)) {
         uint32_t pk[16], dk[16];
         if (t16) {
@@ -507,6 +537,29 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
         tmem_st16(tmem_dP + lane_off + wg * 32, dk);
         tmem_st_wait();
       }
+      if (merge && i == 0 && wg == 0 && warp_active) {
+        // tail block: 16 columns out of the dV / dK accumulator columns, packed into columns [16, 24) of S^T / dP^T
+        // (after the main block above: those columns held block 0's fp32 scores until this warp had loaded them)
+        const int ncol_t = S - (nqb - 1) * 64;
+        const float* tstat = wstat + 64;
+        uint32_t sv[16], dv[16], pk[16], dk[16];
+        tmem_ld16(tmem_dV + lane_off, sv);
+        tmem_ld16(tmem_dK + lane_off, dv);
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float2 ls = *reinterpret_cast<const float2*>(tstat + e);
+          const float2 dl = *reinterpret_cast<const float2*>(tstat + 32 + e);
+          const float p0 = e < ncol_t ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x)) : 0.f;
+          const float p1 = e + 1 < ncol_t ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y)) : 0.f;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+        }
+#pragma unroll
+        for (int e = 8; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
+        tmem_st16(tmem_S + lane_off + 16, pk);
+        tmem_st16(tmem_dP + lane_off + 16, dk);
+        tmem_st_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
@@ -551,7 +604,7 @@ template <int HD>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
                       const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
-                      const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+                      const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale, int merge_tail) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -569,6 +622,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
   const int D = H * HD;
   const int nkb = (S + 63) / 64;
   const bool tail16 = S - (nkb - 1) * 64 <= 16;             // last key block is computed 16 columns wide
+  // merged tail (see the dK/dV kernel): the 16-wide last key block rides along with block 0 -- its S / dP park in the dQ
+  // accumulator columns [128,144) / [144,160), its dS goes to operand buffer 1 -- one chain step less.
+  // Ring entries: 0 = block 0, 1 = tail block, e >= 2 = block e - 1.
+  const bool merge = merge_tail != 0 && tail16 && nkb >= 2;
+  const int nsteps = merge ? nkb - 1 : nkb;
   const float sl2 = scale * LOG2E;
 
   if (threadIdx.x == 0) {
@@ -593,13 +651,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
       tma_load_2d(smem_u32(sQ), &tmQKV128, qdo_full, h * HD, b * S + qt * TILE);
       tma_load_2d(smem_u32(sdO), &tmDO128, qdo_full, h * HD, b * S + qt * TILE);
     }
-    for (int j = 0; j < nkb; ++j) {
+    for (int j = 0; j < nkb; ++j) {                   // j = ring entry
       const int st = j % BWD_STAGES;
+      const int blk = merge ? (j == 0 ? 0 : (j == 1 ? nkb - 1 : j - 1)) : j;
       mbar_wait(&kv_empty[st], ((j / BWD_STAGES) & 1) ^ 1u);
       if (leader) {
         mbar_expect_tx(&kv_full[st], 2 * HALF_BYTES);
-        tma_load_2d(smem_u32(sK + st * HALF_BYTES), &tmQKV64, &kv_full[st], D + h * HD, b * S + j * 64);
-        tma_load_2d(smem_u32(sV + st * HALF_BYTES), &tmQKV64, &kv_full[st], 2 * D + h * HD, b * S + j * 64);
+        tma_load_2d(smem_u32(sK + st * HALF_BYTES), &tmQKV64, &kv_full[st], D + h * HD, b * S + blk * 64);
+        tma_load_2d(smem_u32(sV + st * HALF_BYTES), &tmQKV64, &kv_full[st], 2 * D + h * HD, b * S + blk * 64);
       }
       __syncwarp();
     }
@@ -611,13 +670,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const uint64_t dQ_ = make_sdesc_sw128(smem_u32(sQ), false, 0);
     const uint64_t dO_ = make_sdesc_sw128(smem_u32(sdO), false, 0);
     mbar_wait(qdo_full, 0);
-    auto issue_sdp = [&](int j) {
-      const int st = j % BWD_STAGES;
-      mbar_wait(&kv_full[st], (j / BWD_STAGES) & 1);
+    auto issue_sdp = [&](int j) {                   // step j
+      const int e = merge ? (j == 0 ? 0 : j + 1) : j;
+      const int st = e % BWD_STAGES;
+      mbar_wait(&kv_full[st], (e / BWD_STAGES) & 1);
+      if (merge && j == 0) mbar_wait(&kv_full[1], 0);
       if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
       tc_fence_after();
       if (leader) {
-        const uint32_t id = (j == nkb - 1 && tail16) ? idesc_s16 : idesc_s;
+        const uint32_t id = (!merge && j == nkb - 1 && tail16) ? idesc_s16 : idesc_s;
         const uint64_t dKk = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), false, 0);
         const uint64_t dVk = make_sdesc_sw128(smem_u32(sV + st * HALF_BYTES), false, 0);
 #pragma unroll
@@ -625,29 +686,45 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           tc_mma(tmem_S, dQ_ + ks * 2, dKk + ks * 2, id, ks > 0 ? 1u : 0u);
           tc_mma(tmem_dP, dO_ + ks * 2, dVk + ks * 2, id, ks > 0 ? 1u : 0u);
         }
+        if (merge && j == 0) {                      // tail block: S_t -> dQ columns [0,16), dP_t -> dQ columns [16,32)
+          const uint64_t dKt = make_sdesc_sw128(smem_u32(sK + 1 * HALF_BYTES), false, 0);
+          const uint64_t dVt = make_sdesc_sw128(smem_u32(sV + 1 * HALF_BYTES), false, 0);
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            tc_mma(tmem_dQ, dQ_ + ks * 2, dKt + ks * 2, idesc_s16, ks > 0 ? 1u : 0u);
+            tc_mma(tmem_dQ + 16, dO_ + ks * 2, dVt + ks * 2, idesc_s16, ks > 0 ? 1u : 0u);
+          }
+        }
         tc_commit(s_full);
       }
       __syncwarp();
     };
     issue_sdp(0);
-    for (int j = 0; j < nkb; ++j) {
-      const int st = j % BWD_STAGES;
-      if (j + 1 < nkb) issue_sdp(j + 1);            // runs underneath the softmax threads' work on block j
+    for (int j = 0; j < nsteps; ++j) {
+      const int e = merge ? (j == 0 ? 0 : j + 1) : j;
+      const int st = e % BWD_STAGES;
+      if (j + 1 < nsteps) issue_sdp(j + 1);         // runs underneath the softmax threads' work on block j
       mbar_wait(p_full, j & 1);
       tc_fence_after();
       if (leader) {
         const uint64_t dKm = make_sdesc_sw128(smem_u32(sK + st * HALF_BYTES), true, HALF_BYTES);
         const uint32_t a = tmem_dS + (j & 1) * 32;
         const uint32_t acc = j > 0 ? 1u : 0u;
-        if (j == nkb - 1 && tail16) {
+        if (!merge && j == nkb - 1 && tail16) {
           tc_mma_ts(tmem_dQ, a, dKm, idesc_g, acc);
         } else {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) tc_mma_ts(tmem_dQ, a + ks * 8, dKm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
         }
+        if (merge && j == 0) {                      // the tail block's dS sits in operand buffer 1
+          const uint64_t dKt = make_sdesc_sw128(smem_u32(sK + 1 * HALF_BYTES), true, HALF_BYTES);
+          tc_mma_ts(tmem_dQ, tmem_dS + 32, dKt, idesc_g, 1u);
+          tc_commit(&ds_free[1]);
+          tc_commit(&kv_empty[1]);
+        }
         tc_commit(&ds_free[j & 1]);
         tc_commit(&kv_empty[st]);
-        if (j == nkb - 1) tc_commit(done);
+        if (j == nsteps - 1) tc_commit(done);
       }
       __syncwarp();
     }
@@ -661,11 +738,26 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
     const long long sidx = (static_cast<long long>(b) * H + h) * S + row;
     const float lse_r = row_ok ? lse[sidx] * LOG2E : 0.f;
     const float delta_r = row_ok ? delta[sidx] : 0.f;
-    for (int j = 0; j < nkb; ++j) {
+    for (int j = 0; j < nsteps; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int ncol = min(64, S - j * 64);                    // valid key columns in this block
-      const bool t16 = (j == nkb - 1) && tail16;
+      const bool t16 = !merge && (j == nkb - 1) && tail16;
+      uint32_t dkt[16];
+      if (merge && j == 0 && wg == 0 && warp_active) {         // tail block out of the dQ columns (not live before p_full)
+        const int ncol_t = S - (nkb - 1) * 64;
+        uint32_t svt[16], dvt[16];
+        tmem_ld16(tmem_dQ + lane_off, svt);
+        tmem_ld16(tmem_dQ + 16 + lane_off, dvt);
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float p0 = e < ncol_t ? ex2f(fmaf(__uint_as_float(svt[e]), sl2, -lse_r)) : 0.f;
+          const float p1 = e + 1 < ncol_t ? ex2f(fmaf(__uint_as_float(svt[e + 1]), sl2, -lse_r)) : 0.f;
+          dkt[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dvt[e]) - delta_r), p1 * (__uint_as_float(dvt[e + 1]) - delta_r));
+        }
+#pragma unroll
+        for (int e = 8; e < 16; ++e) dkt[e] = 0u;
+      }
       const bool works = warp_active && !(t16 && wg == 1);
       uint32_t dk[16];
       if (!works) {
@@ -707,10 +799,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid
           dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - delta_r), p1 * (__uint_as_float(dv[e + 1]) - delta_r));
         }
       }
-      // operand buffer j & 1 is free once the dQ MMAs of block j - 2 have retired
-      if (j >= 2) { mbar_wait(&ds_free[j & 1], ((j >> 1) - 1) & 1); tc_fence_after(); }
+      // operand buffer j & 1 is free once the dQ MMAs of block j - 2 have retired (merged tail: buffer 1 is also used,
+      // and released, at step 0, so the odd steps wait one completion earlier)
+      if (merge && (j & 1)) { mbar_wait(&ds_free[1], (j >> 1) & 1); tc_fence_after(); }
+      else if (j >= 2) { mbar_wait(&ds_free[j & 1], ((j >> 1) - 1) & 1); tc_fence_after(); }
       if (works) {
         tmem_st16(tmem_dS + (j & 1) * 32 + lane_off + wg * 16, dk);
+        if (merge && j == 0 && wg == 0) tmem_st16(tmem_dS + 32 + lane_off, dkt);
         tmem_st_wait();
       }
       // a warp with nothing to compute could otherwise run two blocks ahead and arrive twice in one phase
@@ -754,6 +849,9 @@ int set_smem(K kernel, int bytes) {
 }
 
 }  // namespace
+
+static int g_merge_tail = 1;     // 0 = the 16-wide tail block as its own chain step (A/B comparison)
+extern "C" int hct_attention_set_merge_tail(int enable) { g_merge_tail = enable != 0; return HCT_OK; }
 
 extern "C" int hct_attention_trace(void* buf) {      // device buffer of >= 768 int64 (or null): dK/dV kernel event timeline
   long long* p = static_cast<long long*>(buf);
@@ -800,10 +898,10 @@ static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const 
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   dim3 grid(n_tiles, H, B);          // 128-row tiles of keys (dK/dV) resp. queries (dQ); rows behind them: hct_attention_tail.cu
-  attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale);
+  attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale, g_merge_tail);
   int rc = hct_check_launch("attn_bwd_dkdv_tc_kernel");
   if (rc) return rc;
-  attn_bwd_dq_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do128, lse, delta, dqkv, S, H, scale);
+  attn_bwd_dq_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do128, lse, delta, dqkv, S, H, scale, g_merge_tail);
   return hct_check_launch("attn_bwd_dq_tc_kernel");
 }
 

@@ -198,6 +198,9 @@ int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t
  * 3: tcgen05 for every tile, backward tail tile included; 1: tcgen05, but the forward's S %% 128 <= 32 tail rows on the
  * mma.sync kernel; 0: mma.sync kernels only */
 int hct_attention_set_tcgen05(int mode);
+/* 1 (default): when the last 64-wide block of the tcgen05 backward kernels holds <= 16 rows (S = 64 k + 1 with the cls
+ * token) it is computed together with block 0 -- one MMA -> softmax -> MMA chain step less; 0: as its own step */
+int hct_attention_set_merge_tail(int enable);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
 /* Diagnostics: clock64 event timeline of one CTA of the dK/dV backward kernel.  buf = device buffer of >= 768 int64
  * (layout: [producer | MMA | softmax warp 0][block][8 events], see tools/attn_dbg.py) or NULL to switch it off. */

@@ -180,6 +180,19 @@ def test_attention_fwd_bwd(cuda, HF, B, S, H, hd, mode):
         lib().hct_attention_set_tcgen05(2)
 
 
+@pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (2, 65, 2, 48), (1, 321, 2, 64),
+                                      (1, 200, 3, 64)])
+def test_attention_bwd_unmerged_tail_block(cuda, HF, B, S, H, hd):
+    """The default backward computes a <= 16-row last block together with block 0 (hct_attention_set_merge_tail(1));
+    the older schedule -- the tail block as its own chain step -- stays available for A/B timing and must agree too."""
+    from headct_foundation_b200._cabi import lib
+    lib().hct_attention_set_merge_tail(0)
+    try:
+        _attention_case(cuda, B, S, H, hd)
+    finally:
+        lib().hct_attention_set_merge_tail(1)
+
+
 def _attention_case(cuda, B, S, H, hd):
     from headct_foundation_b200._cabi import call, stream_ptr
     D = H * hd
