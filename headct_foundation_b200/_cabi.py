@@ -74,6 +74,7 @@ _SIGNATURES = {
     "hct_profile_enable": [_I32],
     "hct_gemm_set_cta_pair": [_I32],
     "hct_crop_resize_set_rows": [_I32],
+    "hct_layernorm_set_bulk": [_I32],
     "hct_attention_set_tcgen05": [_I32],
     "hct_attention_set_merge_tail": [_I32],
     "hct_attention_trace": [C.c_void_p],

@@ -2,6 +2,7 @@
 // Roofline for all of them is HBM bandwidth; they use 16-byte accesses and warp-per-row layouts.
 #include "../../include/hct_b200.h"
 #include "hct_common.cuh"
+#include "hct_tcgen05.cuh"
 
 namespace {
 
@@ -75,7 +76,15 @@ __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
                "l"(gsrc) : "memory");
 }
 
-template <int NV, bool DY_BF16, int LN_BWD_STAGES>
+// 1-D bulk copy global -> shared through the TMA unit, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(hct_tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(hct_tc::smem_u32(bar)) : "memory");
+}
+
+// USE_BULK: each row's x / dres / dy land through three cp.async.bulk copies issued by one lane (TMA unit, mbarrier
+// completion) instead of 18 per-lane cp.async instructions.
+template <int NV, bool DY_BF16, int LN_BWD_STAGES, bool USE_BULK>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres_in,
@@ -89,6 +98,14 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
   // a 2-deep ring (60 KiB per SM) sat right at the bandwidth-delay product of HBM under load.
   const int stage_floats = DY_BF16 ? 2 * dim + dim / 2 : 3 * dim;
   float* wbuf = sbuf + static_cast<size_t>(warp) * LN_BWD_STAGES * stage_floats;
+  __shared__ uint64_t bars[LN_WARPS][4];
+  if (USE_BULK) {
+    if (lane == 0) {
+      for (int k = 0; k < LN_BWD_STAGES; ++k) hct_tc::mbar_init(&bars[warp][k], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   float4 dg[NV], db[NV], ds[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = dg[i]; ds[i] = dg[i]; }
@@ -96,6 +113,20 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
   const long long row0 = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
   const long long rstride = static_cast<long long>(gridDim.x) * LN_WARPS;
   auto prefetch = [&](long long row, int stage) {          // always commits a group (possibly empty): uniform counting
+    if (USE_BULK) {
+      if (row < rows && lane == 0) {
+        float* sx = wbuf + stage * stage_floats;
+        const uint32_t bx = dim * 4u, bd = DY_BF16 ? dim * 2u : dim * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warp's generic reads of this stage precede the refill
+        hct_tc::mbar_expect_tx(&bars[warp][stage], bx + (dres_in ? bx : 0u) + bd);
+        bulk_load_1d(sx, x + row * dim, bx, &bars[warp][stage]);
+        if (dres_in) bulk_load_1d(sx + dim, dres_in + row * dim, bx, &bars[warp][stage]);
+        bulk_load_1d(sx + 2 * dim, DY_BF16 ? static_cast<const void*>(reinterpret_cast<const bf16*>(dy) + row * dim)
+                                           : static_cast<const void*>(reinterpret_cast<const float*>(dy) + row * dim),
+                     bd, &bars[warp][stage]);
+      }
+      return;
+    }
     if (row < rows) {
       float* sx = wbuf + stage * stage_floats;
       float* sr = sx + dim;
@@ -117,9 +148,14 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
 #pragma unroll
   for (int k = 0; k < LN_BWD_STAGES - 1; ++k) prefetch(row0 + k * rstride, k);
   int stage = 0;
-  for (long long row = row0; row < rows; row += rstride, stage = (stage + 1 == LN_BWD_STAGES ? 0 : stage + 1)) {
+  uint32_t it = 0;
+  for (long long row = row0; row < rows; row += rstride, stage = (stage + 1 == LN_BWD_STAGES ? 0 : stage + 1), ++it) {
     prefetch(row + (LN_BWD_STAGES - 1) * rstride, (stage + LN_BWD_STAGES - 1) % LN_BWD_STAGES);
-    asm volatile("cp.async.wait_group %0;" ::"n"(LN_BWD_STAGES - 1) : "memory");
+    if (USE_BULK) {
+      hct_tc::mbar_wait(&bars[warp][stage], (it / LN_BWD_STAGES) & 1u);
+    } else {
+      asm volatile("cp.async.wait_group %0;" ::"n"(LN_BWD_STAGES - 1) : "memory");
+    }
     __syncwarp();
     const float mu = mean ? mean[row] : 0.f, rs = rstd[row];      // mean == NULL: RMSNorm backward
     const float* sx = wbuf + stage * stage_floats;
@@ -353,6 +389,9 @@ extern "C" int hct_layernorm_fwd(const float* x, const float* gamma, const float
   return hct_check_launch("ln_fwd_kernel");
 }
 
+static int g_ln_bulk = 1;
+extern "C" int hct_layernorm_set_bulk(int enable) { g_ln_bulk = enable != 0; return HCT_OK; }
+
 extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* gamma, const float* mean,
                                  const float* rstd, const float* dres_in, float* dx_out_f32, void* dx_out_bf16,
                                  float* dgamma, float* dbeta, float* dxsum, int64_t rows, int32_t dim, hct_stream_t s) {
@@ -371,17 +410,21 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
   HCT_REQUIRE(smem <= 200 * 1024, "layernorm_bwd: dim=%d needs %zu bytes of shared memory", dim, smem);
   cudaStream_t st = static_cast<cudaStream_t>(s);
   bf16* dx16 = static_cast<bf16*>(dx_out_bf16);
-#define HCT_LN_BWD(NV, BF, ST)                                                                                 \
-  do {                                                                                                         \
-    static bool configured = false;                                                                            \
-    if (!configured) {                                                                                         \
-      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      configured = true;                                                                                       \
-    }                                                                                                          \
-    ln_bwd_kernel<NV, BF, ST><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32, \
-                                                                 dx16, dgamma, dbeta, dxsum, rows, dim);       \
+  // bulk (TMA) staging needs 16-byte aligned rows of a multiple of 16 bytes in every stream
+  const bool bulk = g_ln_bulk && dim % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dy) % 16) == 0 && (dres_in == nullptr || reinterpret_cast<uintptr_t>(dres_in) % 16 == 0);
+#define HCT_LN_BWD(NV, BF, ST, BULK)                                                                                 \
+  do {                                                                                                               \
+    static bool configured = false;                                                                                  \
+    if (!configured) {                                                                                               \
+      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF, ST, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      configured = true;                                                                                             \
+    }                                                                                                                \
+    ln_bwd_kernel<NV, BF, ST, BULK><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32, \
+                                                                       dx16, dgamma, dbeta, dxsum, rows, dim);       \
   } while (0)
-#define HCT_LN_BWD_S(NV, BF) do { if (stages == 3) HCT_LN_BWD(NV, BF, 3); else HCT_LN_BWD(NV, BF, 2); } while (0)
+#define HCT_LN_BWD_B(NV, BF, ST) do { if (bulk) HCT_LN_BWD(NV, BF, ST, true); else HCT_LN_BWD(NV, BF, ST, false); } while (0)
+#define HCT_LN_BWD_S(NV, BF) do { if (stages == 3) HCT_LN_BWD_B(NV, BF, 3); else HCT_LN_BWD_B(NV, BF, 2); } while (0)
 #define HCT_LN_BWD_D(BF)                                                                                        \
   do {                                                                                                         \
     if (dim <= 256) HCT_LN_BWD_S(2, BF); else if (dim <= 768) HCT_LN_BWD_S(6, BF);                              \
@@ -390,6 +433,7 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
   if (dy_bf16) HCT_LN_BWD_D(true); else HCT_LN_BWD_D(false);
 #undef HCT_LN_BWD_D
 #undef HCT_LN_BWD_S
+#undef HCT_LN_BWD_B
 #undef HCT_LN_BWD
   return hct_check_launch("ln_bwd_kernel");
 }

@@ -104,6 +104,8 @@ int hct_layernorm_fwd(const float* x, const float* gamma, const float* beta, voi
  * dgamma/dbeta fp32 [dim] are ACCUMULATED (+=) with atomics; dxsum (optional, fp32 [dim], +=) receives
  * the column sums of the bf16 dx output = the bias gradient of the Linear that consumes it.
  * mean == NULL selects the RMSNorm backward (dbeta must then be NULL). */
+/* 1 (default): rows are staged with cp.async.bulk (TMA unit, mbarrier completion); 0: per-lane cp.async */
+int hct_layernorm_set_bulk(int enable);
 int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, const float* gamma,
                       const float* mean, const float* rstd, const float* dres_in,
                       float* dx_out_f32, void* dx_out_bf16, float* dgamma, float* dbeta, float* dxsum,

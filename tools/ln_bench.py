@@ -24,6 +24,11 @@ for name, rows in (("dec", 256 * 513), ("enc", 256 * 129)):
     y, mean, rstd = HF.layernorm_fwd(x, w, b, 1e-5, True, True)
     f = timeit(lambda: HF.layernorm_fwd(x, w, b, 1e-5, True, True))
     g = timeit(lambda: HF.layernorm_bwd(dy, x, w, mean, rstd, dres, True, want_colsum=True))
+    from headct_foundation_b200._cabi import lib
+    lib().hct_layernorm_set_bulk(0)
+    g0 = timeit(lambda: HF.layernorm_bwd(dy, x, w, mean, rstd, dres, True, want_colsum=True))
+    lib().hct_layernorm_set_bulk(1)
+    print(f"   (ln_bwd with per-lane cp.async staging: {g0:.3f} ms)")
     bf, bb = rows * D * 6 / 1e9, rows * D * 16 / 1e9      # algorithmic GB: fwd 4+2 B/elem, bwd 2+4+4 in, 4+2 out
     print(f"{name} rows={rows}: ln_fwd {f:.3f} ms ({bf / f * 1e3:.0f} GB/s, {bf / f * 1e3 / HBM:.2f} of HBM)   "
           f"ln_bwd {g:.3f} ms ({bb / g * 1e3:.0f} GB/s, {bb / g * 1e3 / HBM:.2f} of HBM)")
