@@ -8,6 +8,7 @@ namespace {
 
 constexpr int LN_MAXV = 16;            // float4 per lane held in registers -> dim <= 2048
 constexpr int LN_WARPS = 8;
+constexpr int LN_SMEM_MAX = 226 * 1024;   // dynamic shared memory budget: the 227 KiB a CTA may opt in to on sm_100 minus the static part
 
 // ------------------------------------------------------------------ LayerNorm forward
 template <int NV>
@@ -84,8 +85,11 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 // USE_BULK: each row's x / dres / dy land through three cp.async.bulk copies issued by one lane (TMA unit, mbarrier
 // completion) instead of 18 per-lane cp.async instructions.
-template <int NV, bool DY_BF16, int LN_BWD_STAGES, bool USE_BULK>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// LN_BWD_WARPS: 12 warps x 2 stages where that fits (160 registers per thread cap an SM at 12 warps): the kernel is bound
+// by how much latency its few resident warps can hide, not by bytes in flight -- 8 warps x 3 stages ran at 0.73 of copy
+// bandwidth, 12 x 2 (the same bytes in flight) at 0.89.
+template <int NV, bool DY_BF16, int LN_BWD_STAGES, bool USE_BULK, int LN_BWD_WARPS>
+__global__ void __launch_bounds__(LN_BWD_WARPS * 32)
 ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres_in,
               float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
@@ -98,7 +102,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
   // a 2-deep ring (60 KiB per SM) sat right at the bandwidth-delay product of HBM under load.
   const int stage_floats = DY_BF16 ? 2 * dim + dim / 2 : 3 * dim;
   float* wbuf = sbuf + static_cast<size_t>(warp) * LN_BWD_STAGES * stage_floats;
-  __shared__ uint64_t bars[LN_WARPS][4];
+  __shared__ uint64_t bars[LN_BWD_WARPS][4];
   if (USE_BULK) {
     if (lane == 0) {
       for (int k = 0; k < LN_BWD_STAGES; ++k) hct_tc::mbar_init(&bars[warp][k], 1);
@@ -110,8 +114,8 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
 #pragma unroll
   for (int i = 0; i < NV; ++i) { dg[i] = make_float4(0, 0, 0, 0); db[i] = dg[i]; ds[i] = dg[i]; }
 
-  const long long row0 = static_cast<long long>(blockIdx.x) * LN_WARPS + warp;
-  const long long rstride = static_cast<long long>(gridDim.x) * LN_WARPS;
+  const long long row0 = static_cast<long long>(blockIdx.x) * LN_BWD_WARPS + warp;
+  const long long rstride = static_cast<long long>(gridDim.x) * LN_BWD_WARPS;
   auto prefetch = [&](long long row, int stage) {          // always commits a group (possibly empty): uniform counting
     if (USE_BULK) {
       if (row < rows && lane == 0) {
@@ -226,7 +230,7 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
     for (int c = threadIdx.x; c < 3 * dim; c += blockDim.x) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < LN_WARPS; ++w) s += sbuf[static_cast<size_t>(w) * 3 * dim + c];
+      for (int w = 0; w < LN_BWD_WARPS; ++w) s += sbuf[static_cast<size_t>(w) * 3 * dim + c];
       if (c < dim) { if (dgamma) atomicAdd(dgamma + c, s); }
       else if (c < 2 * dim) { if (dbeta) atomicAdd(dbeta + (c - dim), s); }
       else if (dxsum) atomicAdd(dxsum + (c - 2 * dim), s);
@@ -400,31 +404,38 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
   HCT_REQUIRE(mean != nullptr || dbeta == nullptr, "layernorm_bwd: RMSNorm (mean == NULL) has no beta gradient");
   HCT_REQUIRE(dxsum == nullptr || dx_out_bf16 != nullptr, "layernorm_bwd: dxsum needs the bf16 output");
   if (rows == 0) return HCT_OK;
-  const int grid = grid_for(rows, LN_WARPS, hct_num_sms());
-  const size_t stage_floats = dy_bf16 ? 2 * static_cast<size_t>(dim) + dim / 2 : 3 * static_cast<size_t>(dim);
-  const size_t scratch = static_cast<size_t>(LN_WARPS) * 3 * dim * sizeof(float);     // final cross-warp reduction
-  int stages = 3;                                                                      // deepest ring that fits
-  if (static_cast<size_t>(LN_WARPS) * 3 * stage_floats * sizeof(float) > 200 * 1024) stages = 2;
-  size_t smem = static_cast<size_t>(LN_WARPS) * stages * stage_floats * sizeof(float);
+  const size_t stage_bytes = (dy_bf16 ? 2 * static_cast<size_t>(dim) + dim / 2 : 3 * static_cast<size_t>(dim)) * sizeof(float);
+  // 12 warps with a 2-deep ring when that fits, else 8 warps with the deepest ring that fits
+  const int warps = 12 * 2 * stage_bytes <= static_cast<size_t>(LN_SMEM_MAX) ? 12 : 8;
+  int stages = 2;
+  if (warps == 8 && 8 * 3 * stage_bytes <= static_cast<size_t>(LN_SMEM_MAX)) stages = 3;
+  const int grid = grid_for(rows, warps, hct_num_sms());
+  const size_t scratch = static_cast<size_t>(warps) * 3 * dim * sizeof(float);        // final cross-warp reduction
+  size_t smem = static_cast<size_t>(warps) * stages * stage_bytes;
   if (smem < scratch) smem = scratch;
-  HCT_REQUIRE(smem <= 200 * 1024, "layernorm_bwd: dim=%d needs %zu bytes of shared memory", dim, smem);
+  HCT_REQUIRE(smem <= static_cast<size_t>(LN_SMEM_MAX), "layernorm_bwd: dim=%d needs %zu bytes of shared memory", dim, smem);
   cudaStream_t st = static_cast<cudaStream_t>(s);
   bf16* dx16 = static_cast<bf16*>(dx_out_bf16);
   // bulk (TMA) staging needs 16-byte aligned rows of a multiple of 16 bytes in every stream
   const bool bulk = g_ln_bulk && dim % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
                     (reinterpret_cast<uintptr_t>(dy) % 16) == 0 && (dres_in == nullptr || reinterpret_cast<uintptr_t>(dres_in) % 16 == 0);
-#define HCT_LN_BWD(NV, BF, ST, BULK)                                                                                 \
-  do {                                                                                                               \
-    static bool configured = false;                                                                                  \
-    if (!configured) {                                                                                               \
-      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF, ST, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-      configured = true;                                                                                             \
-    }                                                                                                                \
-    ln_bwd_kernel<NV, BF, ST, BULK><<<grid, LN_WARPS * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32, \
-                                                                       dx16, dgamma, dbeta, dxsum, rows, dim);       \
+#define HCT_LN_BWD(NV, BF, ST, BULK, NW)                                                                                  \
+  do {                                                                                                                    \
+    static bool configured = false;                                                                                       \
+    if (!configured) {                                                                                                    \
+      cudaFuncSetAttribute(ln_bwd_kernel<NV, BF, ST, BULK, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_MAX); \
+      configured = true;                                                                                                  \
+    }                                                                                                                     \
+    ln_bwd_kernel<NV, BF, ST, BULK, NW><<<grid, NW * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32,        \
+                                                                     dx16, dgamma, dbeta, dxsum, rows, dim);              \
   } while (0)
-#define HCT_LN_BWD_B(NV, BF, ST) do { if (bulk) HCT_LN_BWD(NV, BF, ST, true); else HCT_LN_BWD(NV, BF, ST, false); } while (0)
-#define HCT_LN_BWD_S(NV, BF) do { if (stages == 3) HCT_LN_BWD_B(NV, BF, 3); else HCT_LN_BWD_B(NV, BF, 2); } while (0)
+#define HCT_LN_BWD_B(NV, BF, ST, NW) do { if (bulk) HCT_LN_BWD(NV, BF, ST, true, NW); else HCT_LN_BWD(NV, BF, ST, false, NW); } while (0)
+#define HCT_LN_BWD_S(NV, BF)                                                                         \
+  do {                                                                                               \
+    if (warps == 12) HCT_LN_BWD_B(NV, BF, 2, 12);                                                    \
+    else if (stages == 3) HCT_LN_BWD_B(NV, BF, 3, 8);                                                \
+    else HCT_LN_BWD_B(NV, BF, 2, 8);                                                                 \
+  } while (0)
 #define HCT_LN_BWD_D(BF)                                                                                        \
   do {                                                                                                         \
     if (dim <= 256) HCT_LN_BWD_S(2, BF); else if (dim <= 768) HCT_LN_BWD_S(6, BF);                              \
