@@ -207,11 +207,15 @@ __global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dout, cons
 // One CTA per MASKED patch.  The target patch is staged into shared memory in the prediction's
 // (ph,pw,pd,c) order from the volume's (c,ph,pw,pd) runs, optionally normalised, then compared with
 // the bf16 prediction row using 16-byte loads.
-template <bool BWD>
+// PS: patch side as a compile-time constant (12 = every shipped yaml; 0 = generic).  The target gather computes four
+// quotients per 16-byte load; with a run-time divisor that arithmetic (ALU 50 %, issue slots 62 % busy under ncu) and not
+// DRAM bounded the kernel.
+template <bool BWD, int PS>
 __global__ void __launch_bounds__(256)
 mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, const float* __restrict__ mask,
                 float* __restrict__ per_patch, const float* __restrict__ dloss, const float* __restrict__ mask_sum,
-                bf16* __restrict__ dpred, int L, int C, int H, int W, int D, int p, int norm_pix, int prefix) {
+                bf16* __restrict__ dpred, int L, int C, int H, int W, int D, int p_arg, int norm_pix, int prefix) {
+  const int p = PS > 0 ? PS : p_arg;
   extern __shared__ __align__(16) float tgt[];     // [P]
   __shared__ float red[33];
   const long long patch = blockIdx.x;          // n * L + l
@@ -237,6 +241,20 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
   const int gw = W / p, gd = D / p;
   const int pd0 = (l % gd) * p, pw0 = ((l / gd) % gw) * p, ph0 = (l / (gd * gw)) * p;
   const int runs = C * p * p;
+  // the prediction row is fetched FIRST, into registers: its DRAM round trip overlaps the target gather below instead of
+  // following it behind the barrier (one exposed memory latency per CTA instead of two)
+  constexpr int PRE = 4;
+  const bf16* pr = pred + prow * P;
+  const int nvec = P >> 3;
+  const bool preload = nvec <= PRE * static_cast<int>(blockDim.x);
+  uint4 pu[PRE];
+  if (preload) {
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+      const int i = threadIdx.x + k * blockDim.x;
+      pu[k] = i < nvec ? __ldg(reinterpret_cast<const uint4*>(pr) + i) : make_uint4(0, 0, 0, 0);
+    }
+  }
   float lsum = 0.f;
   if ((p & 3) == 0 && (D & 3) == 0) {
     // a patch row along D is p contiguous floats, 16-byte aligned: fetch it as p/4 vectors (a quarter of the
@@ -268,11 +286,12 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
     const float var = block_sum(q, red) / (P - 1);     // unbiased (mae.py:292)
     inv_std = rsqrtf(var + 1e-6f);
   }
-  const bf16* pr = pred + prow * P;
   if (!BWD) {
     float s = 0.f;
-    for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) {
-      const uint4 u = reinterpret_cast<const uint4*>(pr)[i];
+    for (int i = threadIdx.x, k = 0; i < nvec; i += blockDim.x, ++k) {
+      uint4 u;
+      if (preload) { u = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3])); }
+      else u = reinterpret_cast<const uint4*>(pr)[i];
       const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
       const float pv[8] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d2.x, d2.y};
       const float4 t0 = *reinterpret_cast<const float4*>(tgt + i * 8), t1 = *reinterpret_cast<const float4*>(tgt + i * 8 + 4);
@@ -284,8 +303,10 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
     if (threadIdx.x == 0) per_patch[patch] = s / P;
   } else {
     const float scale = dloss[0] * m * 2.f / (static_cast<float>(P) * mask_sum[0]);
-    for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) {
-      const uint4 u = reinterpret_cast<const uint4*>(pr)[i];
+    for (int i = threadIdx.x, k = 0; i < nvec; i += blockDim.x, ++k) {
+      uint4 u;
+      if (preload) { u = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3])); }
+      else u = reinterpret_cast<const uint4*>(pr)[i];
       const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
       const float pv[8] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d2.x, d2.y};
       const float4 t0 = *reinterpret_cast<const float4*>(tgt + i * 8), t1 = *reinterpret_cast<const float4*>(tgt + i * 8 + 4);
@@ -685,14 +706,20 @@ extern "C" int hct_mae_loss_fwd(const void* pred, int32_t pred_prefix_rows, cons
   cudaStream_t st = static_cast<cudaStream_t>(s);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(mae_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(mae_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
   float* per_patch = loss_out + 4;
-  mae_loss_kernel<false><<<static_cast<unsigned>(static_cast<long long>(N) * L), 256, P * sizeof(float), st>>>(
-      static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr, nullptr, nullptr, L, C, H, W, D, p, norm_pix,
-      pred_prefix_rows);
+  const unsigned grid = static_cast<unsigned>(static_cast<long long>(N) * L);
+  if (p == 12)
+    mae_loss_kernel<false, 12><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr,
+                                                                      nullptr, nullptr, L, C, H, W, D, p, norm_pix, pred_prefix_rows);
+  else
+    mae_loss_kernel<false, 0><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr,
+                                                                     nullptr, nullptr, L, C, H, W, D, p, norm_pix, pred_prefix_rows);
   rc = hct_check_launch("mae_loss_kernel<fwd>");
   if (rc != HCT_OK) return rc;
   loss_reduce_kernel<<<1, 1024, 0, st>>>(per_patch, mask, loss_out, static_cast<long long>(N) * L);
@@ -709,13 +736,18 @@ extern "C" int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, cons
   const int P = C * p * p * p;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(mae_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mae_loss_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  mae_loss_kernel<true><<<static_cast<unsigned>(static_cast<long long>(N) * L), 256, P * sizeof(float),
-                          static_cast<cudaStream_t>(s)>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss,
-                                                          mask_sum, static_cast<bf16*>(dpred), L, C, H, W, D, p,
-                                                          norm_pix, pred_prefix_rows);
+  const unsigned grid = static_cast<unsigned>(static_cast<long long>(N) * L);
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  if (p == 12)
+    mae_loss_kernel<true, 12><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss, mask_sum,
+                                                                     static_cast<bf16*>(dpred), L, C, H, W, D, p, norm_pix, pred_prefix_rows);
+  else
+    mae_loss_kernel<true, 0><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss, mask_sum,
+                                                                    static_cast<bf16*>(dpred), L, C, H, W, D, p, norm_pix, pred_prefix_rows);
   return hct_check_launch("mae_loss_kernel<bwd>");
 }
 
