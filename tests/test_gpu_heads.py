@@ -205,3 +205,62 @@ def test_attention_classifier(cuda):
         with torch.no_grad():
             le = clf(x.detach())
         assert _rel(le.float().cpu(), torch.from_numpy(gold[tag + "_logits_eval"])) < 1e-2
+
+
+# ------------------------------------------------------------------ full shipped shapes
+def test_lora_zero_init_equals_base_model_full_size(cuda):
+    """vit_HeadCT_cq500.yaml shape with TRAIN.LORA: a freshly constructed adapter has lora_matrix_B == 0
+    (attentionblock.py:18), so the LoRA model must reproduce the base model BIT FOR BIT -- the low-rank GEMMs and the
+    reshape-add contribute exact zeros -- and its backward must leave the frozen weights without gradients."""
+    import headct_foundation_b200 as H
+    from headct_foundation_b200.configs import VIT_DOWNSTREAM
+    torch.manual_seed(3)
+    base = H.ViT(**VIT_DOWNSTREAM).to(cuda).eval()
+    lora = H.ViT(**dict(VIT_DOWNSTREAM, lora=True)).to(cuda).eval()
+    missing, unexpected = lora.load_state_dict(base.state_dict(), strict=False)
+    assert not unexpected and all("lora" in k for k in missing)
+    x = torch.rand(4, 3, 96, 96, 96, device=cuda)
+    with torch.no_grad():
+        yb, hb = base(x)
+        yl, hl = lora(x)
+    assert torch.equal(yb, yl) and all(torch.equal(a, b) for a, b in zip(hb, hl))
+    H.set_requires_grad_false(lora, lora=True)
+    lora.train()
+    y, _ = lora(x)
+    y[:, 0].square().mean().backward()
+    named = dict(lora.named_parameters())
+    assert all(p.grad is None for p in named.values() if not p.requires_grad)
+    gB = named["blocks.11.attn.lora_v.lora_matrix_B"].grad
+    assert gB is not None and torch.isfinite(gB).all() and gB.abs().max() > 0
+    gA = named["blocks.11.attn.lora_v.lora_matrix_A"].grad          # dA = B^T (...) = 0 while B == 0
+    assert gA is not None and gA.abs().max() == 0
+
+
+def test_attention_classifier_full_shape_vs_oracle(cuda):
+    """Attentive probe at the downstream shape (batch 64 x 513 tokens x 768, 12 heads): logits against the CPU oracle
+    (1e-2 relative, bf16 kv path), train and eval mode; gradients reach tokens, queries and wkv."""
+    import headct_foundation_b200 as H
+    from oracle import headct_oracle as O, synth
+    sd = synth.attention_classifier_state_dict(768, 2, num_queries=1, qkv_bias=False, seed=71)
+    clf = H.AttentionClassifier(768, 2, num_heads=12, num_queries=1)
+    clf.load_state_dict(sd)
+    clf = clf.to(cuda).train()
+    g = torch.Generator().manual_seed(72)
+    x = torch.randn(64, 513, 768, generator=g) * 1.3 + 0.2
+    xc = x.to(cuda).requires_grad_(True)
+    logits = clf(xc)
+    ref = O.attention_classifier(sd, x, 12, training=True)
+    assert _rel(logits.float().cpu(), ref) < 1e-2
+    w = torch.randn(64, 2, generator=g)
+    (logits.float() * w.to(cuda)).sum().backward()
+    xr = x.clone().requires_grad_(True)
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    (O.attention_classifier(sdr, xr, 12, training=True) * w).sum().backward()
+    assert _cos(xc.grad.cpu(), xr.grad) > 0.99
+    assert _cos(clf.cls_token.grad.cpu(), sdr["cls_token"].grad) > 0.99
+    assert _cos(clf.wkv.weight.grad.cpu(), sdr["wkv.weight"].grad) > 0.99
+    clf.eval()
+    sd_eval = {k: v.detach().cpu() for k, v in clf.state_dict().items()}
+    with torch.no_grad():
+        le = clf(xc.detach())
+    assert _rel(le.float().cpu(), O.attention_classifier(sd_eval, x, 12, training=False)) < 1e-2
