@@ -77,6 +77,7 @@ _SIGNATURES = {
     "hct_layernorm_set_bulk": [_I32],
     "hct_attention_set_tcgen05": [_I32],
     "hct_attention_set_merge_tail": [_I32],
+    "hct_attention_set_dkdv32": [_I32],
     "hct_attention_trace": [C.c_void_p],
     "hct_crop_resize_area": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     "hct_adjust_contrast": [_P, _P, _P, _I64, _I64, _P],

@@ -600,6 +600,223 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __gr
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, BWD_TMEM_COLS); }
 }
 
+// =====================================================================================================
+// dK/dV kernel, pipelined variant: 32-query blocks with TWO S^T / dP^T buffer pairs in tensor memory
+// (2 x (32 + 32) + dV + dK = 224..256 columns, still two CTAs per SM).  The MMA warp keeps S^T / dP^T of block i+1 in
+// flight while the softmax warps work on block i (the 64-wide single-buffered kernel above is a serial
+// MMA -> softmax -> MMA chain of ~2500 cycles per block, profiles/r01_attn_dkdv_timeline.txt).
+// MEASURED: no faster (dec bwd 1.98 vs 1.90 ms) -- a softmax warp needs ~800 cycles for a 16-column chunk against ~950
+// for 32 columns (tcgen05.ld round trip, dependent ex2 chain, tcgen05.st + wait, fence, arrive are mostly fixed cost), so
+// with the same eight warps serving both buffers the softmax warps become the serial resource.  Kept as the off-by-default
+// A/B variant (hct_attention_set_dkdv32) and as the starting point for a version with one warp group per buffer.  Buffer b = i & 1 is recycled by in-order issue: S^T / dP^T of block i+2 are
+// issued behind the dV / dK MMAs of block i that read P^T / dS^T from the same columns.
+// =====================================================================================================
+constexpr int QB = 32;                        // queries per block
+constexpr int QB_BYTES = QB * 128;            // [32 rows][64 bf16]
+constexpr int DK32_STAGES = 6;
+constexpr int DK32_SMEM = 2 * TILE_BYTES + DK32_STAGES * 2 * QB_BYTES + 8 * 256 + 1024 + 256;
+
+template <int HD>
+__global__ void __launch_bounds__(BWD_THREADS, 2)
+attn_bwd_dkdv32_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV32,
+                          const __grid_constant__ CUtensorMap tmDO32, const float* __restrict__ lse,
+                          const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sK = smem;                               // [128 keys][64]
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;              // DK32_STAGES x [32 queries][64]
+  uint8_t* sdO = sQ + DK32_STAGES * QB_BYTES;
+  float* sStat = reinterpret_cast<float*>(sdO + DK32_STAGES * QB_BYTES);    // [8 warps][2 buffers][lse 16 | delta 16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + 8 * 256);
+  uint64_t *kv_full = bars, *qdo_full = bars + 1 /*[6]*/, *qdo_empty = bars + 7 /*[6]*/, *s_full = bars + 13 /*[2]*/,
+           *p_full = bars + 15 /*[2]*/, *done = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
+  const int D = H * HD;
+  const int nqb = (S + QB - 1) / QB;
+  const bool tail16 = S - (nqb - 1) * QB <= 16;             // last query block is computed 16 columns wide
+  const float sl2 = scale * LOG2E;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < DK32_STAGES; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, BWD_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // S^T buffers: [0,32), [32,64)   dP^T buffers: [64,96), [96,128)   dV: [128, 128+HD)   dK: [192, 192+HD)
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 64, tmem_dV = tmem_base + 128, tmem_dK = tmem_base + 192;
+
+  if (warp == BWD_PRODUCER_WARP) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+      tma_load_2d(smem_u32(sK), &tmQKV128, kv_full, D + h * HD, b * S + kt * TILE);
+      tma_load_2d(smem_u32(sV), &tmQKV128, kv_full, 2 * D + h * HD, b * S + kt * TILE);
+    }
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i % DK32_STAGES;
+      mbar_wait(&qdo_empty[st], ((i / DK32_STAGES) & 1) ^ 1u);
+      if (leader) {
+        mbar_expect_tx(&qdo_full[st], 2 * QB_BYTES);
+        tma_load_2d(smem_u32(sQ + st * QB_BYTES), &tmQKV32, &qdo_full[st], h * HD, b * S + i * QB);
+        tma_load_2d(smem_u32(sdO + st * QB_BYTES), &tmDO32, &qdo_full[st], h * HD, b * S + i * QB);
+      }
+      __syncwarp();
+    }
+  } else if (warp == BWD_MMA_WARP) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = make_idesc_bf16(TILE, QB, false, false);
+    const uint32_t idesc_s16 = make_idesc_bf16(TILE, 16, false, false);
+    const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
+    const uint64_t dK_ = make_sdesc_sw128(smem_u32(sK), false, 0);
+    const uint64_t dV_ = make_sdesc_sw128(smem_u32(sV), false, 0);
+    mbar_wait(kv_full, 0);
+    auto issue_sdp = [&](int i) {          // S^T = K Q_i^T and dP^T = V dO_i^T into buffer i & 1
+      const int st = i % DK32_STAGES, bf = i & 1;
+      mbar_wait(&qdo_full[st], (i / DK32_STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t id = (i == nqb - 1 && tail16) ? idesc_s16 : idesc_s;
+        const uint64_t dQk = make_sdesc_sw128(smem_u32(sQ + st * QB_BYTES), false, 0);
+        const uint64_t dOk = make_sdesc_sw128(smem_u32(sdO + st * QB_BYTES), false, 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {      // the two accumulate chains interleaved: consecutive MMAs independent
+          tc_mma(tmem_S + bf * QB, dK_ + ks * 2, dQk + ks * 2, id, ks > 0 ? 1u : 0u);
+          tc_mma(tmem_dP + bf * QB, dV_ + ks * 2, dOk + ks * 2, id, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[bf]);
+      }
+      __syncwarp();
+    };
+    issue_sdp(0);
+    if (nqb > 1) issue_sdp(1);
+    for (int i = 0; i < nqb; ++i) {
+      const int st = i % DK32_STAGES, bf = i & 1;
+      mbar_wait(&p_full[bf], (i >> 1) & 1);           // P^T / dS^T of block i sit in TMEM (and every warp has read S^T / dP^T)
+      tc_fence_after();
+      if (leader) {
+        const uint64_t dQm = make_sdesc_sw128(smem_u32(sQ + st * QB_BYTES), true, QB_BYTES);
+        const uint64_t dOm = make_sdesc_sw128(smem_u32(sdO + st * QB_BYTES), true, QB_BYTES);
+        const uint32_t acc = i > 0 ? 1u : 0u;
+        // k-step ks covers queries [16 ks, 16 ks + 16): packed by column group ks into the first 8 of its 16 columns
+        if (i == nqb - 1 && tail16) {
+          tc_mma_ts(tmem_dV, tmem_S + bf * QB, dOm, idesc_g, acc);
+          tc_mma_ts(tmem_dK, tmem_dP + bf * QB, dQm, idesc_g, acc);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            tc_mma_ts(tmem_dV, tmem_S + bf * QB + ks * 16, dOm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+            tc_mma_ts(tmem_dK, tmem_dP + bf * QB + ks * 16, dQm + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+          }
+        }
+        tc_commit(&qdo_empty[st]);
+        if (i == nqb - 1) tc_commit(done);
+      }
+      __syncwarp();
+      if (i + 2 < nqb) issue_sdp(i + 2);              // into the buffer block i has just released (in-order tensor pipe)
+    }
+  } else if (warp < 8) {
+    // ===================== softmax-backward threads: one KEY row per thread, 16 query columns per warp =====================
+    const int q = warp & 3;
+    const int kvrow = kt * TILE + q * 32 + lane;
+    const bool row_ok = kvrow < S;
+    const bool warp_active = kt * TILE + q * 32 < S;          // warps without a valid key row only keep the barriers moving
+    const int wg = warp >> 2;                                 // which 16-column half of each block this warp owns
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float* lse_g = lse + (static_cast<long long>(b) * H + h) * S;
+    const float* delta_g = delta + (static_cast<long long>(b) * H + h) * S;
+    // per-query statistics of this warp's 16 columns: lanes 0-15 fetch lse (scaled by log2 e), lanes 16-31 delta, one
+    // block ahead, into a private double-buffered shared-memory slot
+    float* wstat = sStat + warp * 64;
+    auto load_stat = [&](int blk) {
+      const int qr = blk * QB + wg * 16 + (lane & 15);
+      if (qr >= S) return 0.f;
+      return lane < 16 ? lse_g[qr] * LOG2E : delta_g[qr];
+    };
+    float st_n = load_stat(0);
+    for (int i = 0; i < nqb; ++i) {
+      const int bf = i & 1;
+      float* stat = wstat + bf * 32;                           // [lse 16 | delta 16]
+      stat[lane] = st_n;
+      __syncwarp();
+      if (i + 1 < nqb) st_n = load_stat(i + 1);
+      mbar_wait(&s_full[bf], (i >> 1) & 1);
+      tc_fence_after();
+      const int ncol = min(QB, S - i * QB);                    // valid query columns in this block
+      const bool t16 = (i == nqb - 1) && tail16;               // 16-wide tail block: column group 0 only
+      if (warp_active && !(t16 && wg != 0)) {
+        uint32_t sv[16], dv[16], pk[8], dk[8];
+        tmem_ld16_issue(tmem_S + bf * QB + lane_off + wg * 16, sv);
+        tmem_ld16_issue(tmem_dP + bf * QB + lane_off + wg * 16, dv);
+        tmem_ld_wait();
+        const int lim = ncol - wg * 16;                        // valid query columns in this warp's chunk
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const float4 ls = *reinterpret_cast<const float4*>(stat + e);
+          const float4 dl = *reinterpret_cast<const float4*>(stat + 16 + e);
+          // P and dS vanish outside the problem
+          const float p0 = e < lim ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x)) : 0.f;
+          const float p1 = e + 1 < lim ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y)) : 0.f;
+          const float p2 = e + 2 < lim ? ex2f(fmaf(__uint_as_float(sv[e + 2]), sl2, -ls.z)) : 0.f;
+          const float p3 = e + 3 < lim ? ex2f(fmaf(__uint_as_float(sv[e + 3]), sl2, -ls.w)) : 0.f;
+          pk[e >> 1] = pack_bf16x2(p0, p1);
+          pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+          dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+          dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) - dl.z), p3 * (__uint_as_float(dv[e + 3]) - dl.w));
+        }
+        // in place: this thread's own lanes, the first 8 of the 16 fp32 columns it has just read
+        tmem_st8(tmem_S + bf * QB + lane_off + wg * 16, pk);
+        tmem_st8(tmem_dP + bf * QB + lane_off + wg * 16, dk);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[bf]);
+    }
+    // ---- epilogue: dV, dK rows
+    mbar_wait(done, 0);
+    tc_fence_after();
+    bf16* dkrow = dqkv + (static_cast<long long>(b) * S + kvrow) * (3LL * D) + D + h * HD;
+    bf16* dvrow = dkrow + D;
+    if (warp_active) {                       // both warp groups cover the same 128 rows: one writes dK, the other dV
+      const uint32_t src = wg == 0 ? tmem_dK : tmem_dV;
+      bf16* dst = wg == 0 ? dkrow : dvrow;
+      const float sc = wg == 0 ? scale : 1.0f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < HD; c0 += 16) {
+        uint32_t o[16];
+        tmem_ld16(src + lane_off + c0, o);
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * sc, __uint_as_float(o[8 * g + 1]) * sc);
+            u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * sc, __uint_as_float(o[8 * g + 3]) * sc);
+            u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * sc, __uint_as_float(o[8 * g + 5]) * sc);
+            u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * sc, __uint_as_float(o[8 * g + 7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c0 + 8 * g) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, BWD_TMEM_COLS); }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(BWD_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
@@ -850,6 +1067,8 @@ int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
+static int g_dkdv32 = 0;         // 1 = pipelined dK/dV kernel (32-query blocks, two buffer pairs); 0 (default) = 64-wide single-buffered
+extern "C" int hct_attention_set_dkdv32(int enable) { g_dkdv32 = enable != 0; return HCT_OK; }
 static int g_merge_tail = 1;     // 0 = the 16-wide tail block as its own chain step (A/B comparison)
 extern "C" int hct_attention_set_merge_tail(int enable) { g_merge_tail = enable != 0; return HCT_OK; }
 
@@ -889,16 +1108,21 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
 
 template <int HD>
 static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const CUtensorMap& do128, const CUtensorMap& do64,
+                         const CUtensorMap& q32, const CUtensorMap& do32,
                          const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, int n_tiles, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) {
     int rc = set_smem(attn_bwd_dkdv_tc_kernel<HD>, BWD_SMEM); if (rc) return rc;
+    rc = set_smem(attn_bwd_dkdv32_tc_kernel<HD>, DK32_SMEM); if (rc) return rc;
     rc = set_smem(attn_bwd_dq_tc_kernel<HD>, BWD_SMEM); if (rc) return rc;
     cfg = true;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   dim3 grid(n_tiles, H, B);          // 128-row tiles of keys (dK/dV) resp. queries (dQ); rows behind them: hct_attention_tail.cu
-  attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale, g_merge_tail);
+  if (g_dkdv32)
+    attn_bwd_dkdv32_tc_kernel<HD><<<grid, BWD_THREADS, DK32_SMEM, st>>>(q128, q32, do32, lse, delta, dqkv, S, H, scale);
+  else
+    attn_bwd_dkdv_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do64, lse, delta, dqkv, S, H, scale, g_merge_tail);
   int rc = hct_check_launch("attn_bwd_dkdv_tc_kernel");
   if (rc) return rc;
   attn_bwd_dq_tc_kernel<HD><<<grid, BWD_THREADS, BWD_SMEM, st>>>(q128, q64, do128, lse, delta, dqkv, S, H, scale, g_merge_tail);
@@ -907,12 +1131,14 @@ static int launch_bwd_tc(const CUtensorMap& q128, const CUtensorMap& q64, const 
 
 int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
                          int H, int hd, int n_tiles, cudaStream_t st) {
-  CUtensorMap q128, q64, do128, do64;
+  CUtensorMap q128, q64, do128, do64, q32, do32;
   const long long D = static_cast<long long>(H) * hd, D3 = 3 * D, rows = static_cast<long long>(B) * S;
   int rc = hct_make_tmap_bf16_2d(&q128, qkv, D3, rows, D3, 64, TILE); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&q64, qkv, D3, rows, D3, 64, 64); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&do128, dout, D, rows, D, 64, TILE); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&do64, dout, D, rows, D, 64, 64); if (rc) return rc;
-  if (hd == 64) return launch_bwd_tc<64>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, n_tiles, st);
-  return launch_bwd_tc<48>(q128, q64, do128, do64, lse, delta, static_cast<bf16*>(dqkv), B, S, H, n_tiles, st);
+  rc = hct_make_tmap_bf16_2d(&q32, qkv, D3, rows, D3, 64, QB); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&do32, dout, D, rows, D, 64, QB); if (rc) return rc;
+  if (hd == 64) return launch_bwd_tc<64>(q128, q64, do128, do64, q32, do32, lse, delta, static_cast<bf16*>(dqkv), B, S, H, n_tiles, st);
+  return launch_bwd_tc<48>(q128, q64, do128, do64, q32, do32, lse, delta, static_cast<bf16*>(dqkv), B, S, H, n_tiles, st);
 }

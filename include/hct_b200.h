@@ -203,6 +203,10 @@ int hct_attention_set_tcgen05(int mode);
 /* 1 (default): when the last 64-wide block of the tcgen05 backward kernels holds <= 16 rows (S = 64 k + 1 with the cls
  * token) it is computed together with block 0 -- one MMA -> softmax -> MMA chain step less; 0: as its own step */
 int hct_attention_set_merge_tail(int enable);
+/* 1: the dK/dV backward kernel works on 32-query blocks with two S^T / dP^T buffer pairs in tensor memory, so the MMAs
+ * of block i+1 overlap the softmax of block i (measured: not faster); 0 (default): 64-query blocks,
+ * single-buffered (the merge_tail switch applies) */
+int hct_attention_set_dkdv32(int enable);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
 /* Diagnostics: clock64 event timeline of one CTA of the dK/dV backward kernel.  buf = device buffer of >= 768 int64
  * (layout: [producer | MMA | softmax warp 0][block][8 events], see tools/attn_dbg.py) or NULL to switch it off. */

@@ -193,6 +193,18 @@ def test_attention_bwd_unmerged_tail_block(cuda, HF, B, S, H, hd):
         lib().hct_attention_set_merge_tail(1)
 
 
+@pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (2, 65, 2, 48), (1, 321, 2, 64),
+                                      (1, 200, 3, 64), (2, 230, 4, 48), (1, 128, 2, 64)])
+def test_attention_bwd_pipelined_dkdv_variant(cuda, HF, B, S, H, hd):
+    """The off-by-default dK/dV kernel with 32-query blocks and two S^T / dP^T buffer pairs (hct_attention_set_dkdv32)."""
+    from headct_foundation_b200._cabi import lib
+    lib().hct_attention_set_dkdv32(1)
+    try:
+        _attention_case(cuda, B, S, H, hd)
+    finally:
+        lib().hct_attention_set_dkdv32(0)
+
+
 def _attention_case(cuda, B, S, H, hd):
     from headct_foundation_b200._cabi import call, stream_ptr
     D = H * hd
