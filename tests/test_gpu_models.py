@@ -413,9 +413,11 @@ def test_graphed_train_step_follows_eager(cuda):
     assert int(o2.state[p0]["step"].item()) == len(xs)
     # Adam's first steps move every element by ~lr * sign(g): elements whose gradient is at the noise level of the
     # split-K atomics differ between ANY two runs, so the weights are compared by direction, the trajectory by its losses
+    ups1, ups2 = [], []
     for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         assert _cos(a.detach().cpu(), b.detach().cpu()) > 0.99, k
-        assert _cos((a.detach().cpu() - sd[k]), (b.detach().cpu() - sd[k])) > 0.9 or (a.detach().cpu() - sd[k]).norm() < 1e-6, k
+        ups1.append((a.detach().cpu() - sd[k]).flatten()); ups2.append((b.detach().cpu() - sd[k]).flatten())
+    assert _cos(torch.cat(ups1), torch.cat(ups2)) > 0.95            # the accumulated update of the whole model
     # eager use after replays sees the updated weights (bf16 copies re-keyed by advance())
     with torch.no_grad():
         l1, l2 = m1(xs[0])[0].item(), m2(xs[0])[0].item()
