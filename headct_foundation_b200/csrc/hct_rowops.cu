@@ -274,7 +274,23 @@ colsum_kernel(const void* __restrict__ x, int x_bf16, long long ld, float* __res
   const int col = (blockIdx.x * 32 + cg) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < cols) {
-    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+    const long long rstep = static_cast<long long>(gridDim.y) * 8;
+    long long r = static_cast<long long>(blockIdx.y) * 8 + rl;
+    if (x_bf16) {
+      // four independent 16-byte loads in flight per thread (one load per iteration left the kernel latency-bound)
+      const bf16* xb = reinterpret_cast<const bf16*>(x) + col;
+      for (; r + 3 * rstep < rows; r += 4 * rstep) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + k * rstep) * ld);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(u[k].x), b = unpack_bf16x2(u[k].y), c = unpack_bf16x2(u[k].z), d = unpack_bf16x2(u[k].w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+        }
+      }
+    }
+    for (; r < rows; r += rstep) {
       if (x_bf16) {
         const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x) + r * ld + col);
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
