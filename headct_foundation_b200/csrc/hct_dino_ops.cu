@@ -243,8 +243,39 @@ __global__ void adamw_multi_kernel(const long long* __restrict__ table, const fl
     if (c < 1.f) coef = c;
   }
   const float step_size = lr / bc1;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  // 16-byte accesses on the four fp32 streams (8-byte on the bf16 copy) where the tensor allows it; the scalar loop below
+  // takes the remainder (and everything, for a tensor that is not 16-byte aligned)
+  long long done4 = 0;
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+        reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(sh) & 7) == 0) {
+    const long long n4 = n >> 2;
+    const float decay = 1.f - lr * wd, ob1 = 1.f - beta1, ob2 = 1.f - beta2;     // same arithmetic as the scalar loop
+    for (long long i = tid; i < n4; i += nthreads) {
+      const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+      float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+      float pe[4] = {p4.x, p4.y, p4.z, p4.w}, me[4] = {m4.x, m4.y, m4.z, m4.w}, ve[4] = {v4.x, v4.y, v4.z, v4.w};
+      const float ge[4] = {g4.x * coef, g4.y * coef, g4.z * coef, g4.w * coef};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float pi = pe[k] * decay;
+        me[k] = beta1 * me[k] + ob1 * ge[k];
+        ve[k] = beta2 * ve[k] + ob2 * ge[k] * ge[k];
+        pi -= step_size * me[k] / (sqrtf(ve[k]) / bc2_sqrt + eps);
+        pe[k] = pi;
+      }
+      reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
+      reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+      reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+      if (sh != nullptr) {
+        uint2 u; u.x = pack_bf16x2(pe[0], pe[1]); u.y = pack_bf16x2(pe[2], pe[3]);
+        reinterpret_cast<uint2*>(sh)[i] = u;
+      }
+    }
+    done4 = n4 << 2;
+  }
+  for (long long i = done4 + tid; i < n; i += nthreads) {
     const float gi = g[i] * coef;
     float pi = p[i] * (1.f - lr * wd);
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
