@@ -72,6 +72,32 @@ def test_no_cpu_fallback():
         H.ViT(**synth.VIT_SMALL)(torch.zeros(1, 3, 48, 48, 48))
 
 
+def test_no_cpu_fallback_downstream_heads_and_graphs():
+    """The rows added after the core path (8(f) rank 4, CUDA-graph replay) fail loudly on CPU tensors as well."""
+    import headct_foundation_b200 as H
+    from headct_foundation_b200 import _cabi
+    from headct_foundation_b200.optim import FusedAdamW
+    with pytest.raises(RuntimeError):
+        H.AttentionClassifier(96, 2, num_heads=2)(torch.zeros(2, 9, 96))
+    with pytest.raises(RuntimeError):
+        H.RMSNorm(64)(torch.zeros(3, 64))
+    with pytest.raises(RuntimeError):
+        H.LoraLinear(64, 64, r=8)(torch.zeros(3, 64))
+    lin = torch.nn.Linear(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        H.GraphedForward(lin, torch.zeros(2, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        H.GraphedTrainStep(lin, FusedAdamW(lin.parameters()), torch.zeros(2, 4))
+    L = _cabi.lib()
+    assert L.hct_lora_shuffle(None, None, None, 2, 9, 2, 12, 0, None) == 1             # head dim not a multiple of 8
+    assert L.hct_pool_attention_fwd(None, None, None, None, 2, 9, 2, 48, 9, 1.0, None) == 1   # more than 8 queries
+    assert L.hct_colnorm_stats(None, None, 8, 6, 1e-6, 0.1, None, None, None, None, None) == 1  # dim % 4
+    assert L.hct_lora_shuffle(None, None, None, 0, 9, 2, 48, 0, None) == 0             # empty batch is a no-op
+    opt = FusedAdamW(lin.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
+    lr, wd, bc1, bc2s = opt._hyper_values(opt.param_groups[0], 3)                      # what the captured launch reads
+    assert (lr, wd) == (1e-3, 0.05) and abs(bc1 - (1 - 0.9 ** 3)) < 1e-12 and abs(bc2s - (1 - 0.95 ** 3) ** 0.5) < 1e-12
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "headct_foundation_b200")
     for dirpath, _, files in os.walk(pkg):
