@@ -154,6 +154,151 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# Secondary workloads of BASELINE.json (configs[2..4]) measured in the same run, and per-class roofline fractions
+# ------------------------------------------------------------------------------------------------------------------
+DINO_GFLOP, FINETUNE_GFLOP, EXTRACT_GFLOP = 1408.9, 298.687, 100.921        # per volume, SURVEY.md 8(d)
+
+
+def _timed_steps(torch, dist, world, fn, warmup, steps):
+    """ms per step: CUDA events bracketed by barrier + synchronize, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return ms
+
+
+def secondary_dino(torch, dist, H, FusedAdamW, dev, world, local_rank, peak, B=64, steps=4, warmup=3):
+    """configs[2]: DINO step as engine_pretrain_dino.py:60-125 -- teacher forward on the 2 global crops, student forward on
+    all 4, DINOLoss (+ center all-reduce over NCCL, losses.py:97), backward, per-parameter clip + AdamW, EMA teacher --
+    with student AND teacher wrapped in DDP as main_pretrain_dino.py:188-199 does."""
+    from headct_foundation_b200 import configs as C
+    student = H.MultiCropWrapper(H.ViT(**C.VIT_DINO), H.DINOHead(**C.DINO_HEAD)).to(dev).train()
+    teacher = H.MultiCropWrapper(H.ViT(**C.VIT_DINO), H.DINOHead(**C.DINO_HEAD)).to(dev).train()
+    teacher.load_state_dict(student.state_dict())
+    s_mod, t_mod = student, teacher
+    if world > 1:
+        ddp = torch.nn.parallel.DistributedDataParallel
+        s_mod = ddp(student, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True,
+                    gradient_as_bucket_view=True, bucket_cap_mb=64)
+        t_mod = ddp(teacher, device_ids=[local_rank], broadcast_buffers=False, find_unused_parameters=True)
+    H.set_requires_grad_false(teacher)                                         # main_pretrain_dino.py:202
+    crit = H.DINOLoss(**C.DINO_LOSS).to(dev)
+    opt = FusedAdamW([p for p in student.parameters() if p.requires_grad], lr=5e-4 * B * world / 256, betas=(0.9, 0.999),
+                     weight_decay=0.04, clip_grad=3.0)
+    crops = [torch.rand(B, 3, 96, 96, 96, device=dev) for _ in range(4)]
+    last = []
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.no_grad():
+            t = t_mod(crops[:2])["dino_output"]
+        s_out = s_mod(crops)["dino_output"]
+        loss = crit(s_out, t, 0)
+        loss.backward()
+        opt.step()
+        H.update_momentum_encoder(student, teacher, 0.999)
+        last[:] = [loss.detach()]
+    ms = _timed_steps(torch, dist, world, step, warmup, steps)
+    loss = float(last[0])
+    if not (loss == loss and abs(loss) < 1e4):
+        raise RuntimeError(f"DINO loss {loss}")
+    tf = DINO_GFLOP * B / ms
+    return {"volumes_per_s": B * world / ms * 1e3, "ms_per_step": ms, "batch_per_gpu": B, "step_frac_of_peak": tf / peak,
+            "step_algorithmic_tflops_per_gpu": tf, "loss": loss,
+            "workload": "DINO ViT-B 3D step: 4 student crops fwd+bwd, 2 teacher crops fwd, 65536-way head, DINOLoss + center "
+                        "all-reduce, per-param clip + AdamW, EMA teacher; student and teacher under DDP"}
+
+
+def secondary_finetune(torch, dist, H, FusedAdamW, dev, world, local_rank, peak, B=64, steps=6, warmup=3):
+    """configs[3]: ViT-B + LinearClassifier + cross-entropy (engine_downstream.py:80-111), batch 64.  The reference does
+    not DDP-wrap downstream training (main_downstream.py:162): every rank trains its own replica."""
+    from headct_foundation_b200 import configs as C
+    m = H.ViT(**C.VIT_DOWNSTREAM).to(dev).train()
+    clf = H.LinearClassifier(768, 2).to(dev).train()
+    opt = FusedAdamW(list(m.parameters()), lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05)
+    opt2 = torch.optim.AdamW(clf.parameters(), lr=1e-2)
+    x = torch.rand(B, 3, 96, 96, 96, device=dev)
+    y = torch.randint(0, 2, (B,), device=dev)
+    ce = torch.nn.CrossEntropyLoss()
+
+    def step():
+        opt.zero_grad(set_to_none=True); opt2.zero_grad(set_to_none=True)
+        out, _ = m(x)
+        loss = ce(clf(out[:, :1, :].squeeze(1)), y)
+        loss.backward()
+        opt.step(); opt2.step()
+    ms = _timed_steps(torch, dist, world, step, warmup, steps)
+    tf = FINETUNE_GFLOP * B / ms
+    return {"volumes_per_s": B * world / ms * 1e3, "ms_per_step": ms, "batch_per_gpu": B, "step_frac_of_peak": tf / peak,
+            "workload": "fine-tune step ViT-B + LinearClassifier + CE (vit_HeadCT_cq500 shape), replicas (not DDP, as the reference)"}
+
+
+def secondary_extract(torch, dist, H, dev, world, peak, batches=(1, 8, 64, 256)):
+    """configs[4]: encoder-only feature extraction, ViT.eval() under no_grad, 12 hidden states materialised."""
+    from headct_foundation_b200 import configs as C
+    m = H.ViT(**C.VIT_EXTRACT).to(dev).eval()
+    rows = {}
+    for B in batches:
+        x = torch.rand(B, 3, 96, 96, 96, device=dev)
+        with torch.no_grad():
+            ms = _timed_steps(torch, dist, world, lambda: m(x), 2, 4)
+        rows[str(B)] = {"volumes_per_s": B * world / ms * 1e3, "ms": ms, "frac_of_peak": EXTRACT_GFLOP * B / ms / peak}
+        if B <= 8:          # launch-bound range: the same forward replayed from a CUDA graph (utils/graphs.py)
+            gf = H.GraphedForward(m, x)
+            msg = _timed_steps(torch, dist, world, lambda: gf(x), 2, 10)
+            rows[str(B)]["graph_replay_volumes_per_s"] = B * world / msg * 1e3
+            del gf
+        del x
+    return {"by_batch": rows, "workload": "extract_feature: ViT-B 3D eval forward (S = 513), per-GPU batch as keyed, replicas"}
+
+
+def class_rooflines(torch, _cabi, train_step, resident, peaks, steps=2):
+    """roofline_secondary: every kernel class above ~1 % of the step, timed launch by launch with CUDA events in an extra
+    (untimed for the headline) pass of `steps` steps.  Tensor classes vs the bf16 peak, the others vs HBM copy bandwidth."""
+    names = ["attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "mae_loss", "clip_adamw", "patchify"]
+    _cabi.profile_enable(*names)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        train_step(resident)
+    b.record()
+    torch.cuda.synchronize()
+    total_ms = a.elapsed_time(b)
+    out = {}
+    for n in names:
+        ms, work, cnt = _cabi.profile_collect(n)
+        if cnt == 0 or ms <= 0:
+            continue
+        tensor = n.startswith("attention")
+        if n == "clip_adamw":       # bytes counted on the host: (4 read for the norm) + (4 x 4 read + 3 x 4 + 2 written) per parameter
+            work = steps * class_rooflines.adamw_bytes
+        ach = work / 1e12 / (ms / 1e3) if tensor else work / 1e9 / (ms / 1e3)
+        peak = peaks["tflops"] if tensor else peaks["hbm"]
+        out[n] = {"bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak, "unit": "TFLOP/s" if tensor else "GB/s",
+                  "frac": ach / peak, "launches_per_step": cnt / steps, "ms_per_step": ms / steps,
+                  "share_of_step": ms / total_ms}
+    _cabi.profile_enable()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -214,7 +359,7 @@ def run_ours(args):
 
     # ---- timed region 1: inputs resident in HBM
     lib = _cabi.lib()
-    lib.hct_profile_enable(1)
+    lib.hct_profile_enable(1)          # class 0: the GEMM kernel
     n0 = _cabi.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
@@ -285,6 +430,28 @@ def run_ours(args):
     if not all(v == v and abs(v) < 1e6 for v in losses):
         raise RuntimeError(f"non-finite loss in the e2e region: {losses}")
 
+    # ---- per-class roofline fractions (extra pass, rank-local) and the secondary workloads (every rank takes part)
+    peaks = _peaks()
+    class_rooflines.adamw_bytes = sum(p.numel() for p in params) * (4 + 16 + 12 + 2)
+    roof2 = class_rooflines(torch, _cabi, train_step, resident, peaks) if not args.no_secondary else None
+    h2d_bytes = int(host_hu[0].numel() * 2)
+    secondary = None
+    if not args.no_secondary:
+        del resident, dev_hu, host_hu, x, loss, opt, step_model, model, params
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+        secondary = {}
+        for name, fn in (("dino", lambda: secondary_dino(torch, dist, H, FusedAdamW, dev, world, local_rank, peaks["tflops"])),
+                         ("finetune", lambda: secondary_finetune(torch, dist, H, FusedAdamW, dev, world, local_rank, peaks["tflops"])),
+                         ("extract", lambda: secondary_extract(torch, dist, H, dev, world, peaks["tflops"]))):
+            try:
+                secondary[name] = fn()
+            except Exception as e:                      # the headline line must survive a secondary failure; say what broke
+                if world > 1:
+                    raise
+                secondary[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            gc.collect(); torch.cuda.empty_cache()
+
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -297,7 +464,6 @@ def run_ours(args):
         launches_all = launches
 
     if rank == 0:
-        peaks = _peaks()
         traffic = _gemm_traffic() if B == 256 else None
         value = B * world * args.steps / (ms / 1e3)
         e2e_value = B * world * e2e_steps / (e2e_ms / 1e3)
@@ -305,7 +471,7 @@ def run_ours(args):
         step_tflops = value / world * MAE_FWD_BWD_GFLOP / 1e3
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference_arm(5, 1)
+            cpu = cpu_reference_arm(8, 2)          # the same sample as the --impl reference arm
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -313,8 +479,11 @@ def run_ours(args):
             "config": {"workload": WORKLOAD + (", DDP grad all-reduce" if world > 1 else ""),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no explicit flush"
-                                    % (resident.numel() * 4 / 1e6),
-                       "final_loss": final_loss, "host_issue_ms_per_step": host_issue_ms},
+                                    % (B * 3 * 96 ** 3 * 4 / 1e6),
+                       "final_loss": final_loss,
+                       # CPU time to enqueue one step; only meaningful while the host leads the GPU (otherwise the launch
+                       # queue back-pressures the host and this just equals ms_per_step)
+                       "host_issue_ms_per_step": (host_issue_ms if host_issue_ms < 0.8 * ms / args.steps else None)},
             "roofline": {"bound": "tensor", "kernel": "hct_gemm_tcgen05_kernel (all epilogues)", "achieved": achieved,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                          "traffic": (traffic["bytes_per_launch"] if traffic else None),
@@ -328,13 +497,17 @@ def run_ours(args):
                          "step_algorithmic_tflops_per_gpu": step_tflops,
                          "step_frac_of_peak": step_tflops / peaks["tflops"]},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
-                    "h2d_bytes_per_step": int(host_hu[0].numel() * 2), "d2h_bytes_per_step": 4,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "h2d_link_gbps_measured": h2d_gbps,
                     "path": "pinned int16 HU -> H2D (copy stream, double buffered) -> MultipleWindowScaleStack (GPU) -> "
                             "MaskedAutoencoderViT.forward/backward -> FusedAdamW -> async D2H of the loss into pinned memory"},
             "gpu_launches": launches_all,
             "clocks": clocks.summary(),
         }
+        if roof2 is not None:
+            line["roofline_secondary"] = roof2
+        if secondary is not None:
+            line["secondary"] = secondary
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu")}
         print(json.dumps(line), flush=True)
@@ -351,6 +524,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="volumes per GPU per step (DATA.BATCH_SIZE semantics)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip roofline_secondary and the DINO / fine-tune / extraction runs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -66,7 +66,7 @@ _SIGNATURES = {
     "hct_l2norm_fwd": [_P, _I32, _P, _P, _I64, _I32, _P],
     "hct_l2norm_bwd": [_P, _P, _P, _P, _I64, _I32, _P],
     "hct_weightnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _P],
-    "hct_weightnorm_bwd": [_P, _P, _P, _P, _P, _I64, _I32, _P],
+    "hct_weightnorm_bwd": [_P, _P, _P, _P, _P, _P, _I64, _I32, _P],
     "hct_dino_loss": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _F, _P],
     "hct_center_ema": [_P, _P, _F, _F, _I32, _P],
     "hct_ema_multi": [_P, _I32, _F, _P],
@@ -85,6 +85,7 @@ _SIGNATURES = {
     "hct_gaussian_smooth_axis": [_P, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _I32, _I32, _I32, _P],
     "hct_gemm_trace": [C.c_void_p],
     "hct_profile_collect": [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
+    "hct_profile_collect_class": [_I32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)],
     "hct_adamw_multi": [_P, _I32, _P, _F, _F, _F, _F, _F, _F, _I32, _P],
     "hct_adamw_multi_dev": [_P, _I32, _P, _F, _P, _F, _F, _F, _P],
     "hct_lora_shuffle": [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P],
@@ -124,6 +125,25 @@ def lib() -> C.CDLL:
             L.hct_attention_set_tcgen05(0)
         _lib = L
     return _lib
+
+
+PROF_CLASSES = {"gemm": 0, "attention_fwd": 1, "attention_bwd": 2, "layernorm_fwd": 3, "layernorm_bwd": 4, "mae_loss": 5,
+                "clip_adamw": 6, "window": 7, "patchify": 8}
+
+
+def profile_enable(*classes: str) -> None:
+    """Bracket every launch of the named kernel classes with CUDA events (measurement aid, see hct_b200.h)."""
+    mask = 0
+    for c in classes:
+        mask |= 1 << PROF_CLASSES[c]
+    lib().hct_profile_enable(mask)
+
+
+def profile_collect(cls: str):
+    """(total_ms, total_work, launches) of a class since its last collect; work = flops (tensor classes) or bytes."""
+    ms, wk, n = C.c_double(), C.c_double(), C.c_longlong()
+    check(lib().hct_profile_collect_class(PROF_CLASSES[cls], C.byref(ms), C.byref(wk), C.byref(n)), "hct_profile_collect_class")
+    return ms.value, wk.value, int(n.value)
 
 
 def launch_count() -> int:

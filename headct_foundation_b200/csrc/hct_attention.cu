@@ -578,6 +578,7 @@ extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t
                                  hct_stream_t s) {
   HCT_REQUIRE(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attention_fwd: bad B=%d S=%d H=%d", B, S, H);
   cudaStream_t st = static_cast<cudaStream_t>(s);
+  HctProfScope prof(st, HCT_PROF_ATTN_FWD, 4.0 * B * static_cast<double>(S) * S * H * hd);
   const bf16* q = static_cast<const bf16*>(qkv);
   bf16* o = static_cast<bf16*>(out);
   int q_start = 0;
@@ -602,6 +603,7 @@ extern "C" int hct_attention_bwd(const void* qkv, const void* out, const void* d
   HCT_REQUIRE(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attention_bwd: bad B=%d S=%d H=%d", B, S, H);
   HCT_REQUIRE(hd == 64 || hd == 48 || hd == 32, "attention_bwd: head dim %d unsupported (32/48/64)", hd);
   cudaStream_t st = static_cast<cudaStream_t>(s);
+  HctProfScope prof(st, HCT_PROF_ATTN_BWD, 8.0 * B * static_cast<double>(S) * S * H * hd);   // 2 x forward
   const long long total = static_cast<long long>(B) * S * H;
   HCT_REQUIRE(hd % 8 == 0 && hd <= 64, "attention_bwd: head dim %d unsupported by the delta pre-pass", hd);
   attn_delta_kernel<<<dim3((S + DELTA_TOK - 1) / DELTA_TOK, B), 256, H * (DELTA_TOK + 1) * sizeof(float), st>>>(

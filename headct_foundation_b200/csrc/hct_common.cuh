@@ -12,9 +12,18 @@
 void hct_set_error(const char* fmt, ...);
 int hct_check_launch(const char* what);   // cudaGetLastError -> HCT_ERR_CUDA + message
 int hct_num_sms();
-bool hct_prof_enabled();
+// per-launch timing classes of the measurement aid (hct_profile_enable takes a bit mask of 1 << class)
+enum { HCT_PROF_GEMM = 0, HCT_PROF_ATTN_FWD = 1, HCT_PROF_ATTN_BWD = 2, HCT_PROF_LN_FWD = 3, HCT_PROF_LN_BWD = 4,
+       HCT_PROF_LOSS = 5, HCT_PROF_ADAMW = 6, HCT_PROF_WINDOW = 7, HCT_PROF_PATCHIFY = 8, HCT_PROF_CLASSES = 9 };
+bool hct_prof_enabled(int cls = HCT_PROF_GEMM);
 void* hct_prof_begin(cudaStream_t st);
-void hct_prof_end(void* begin_event, cudaStream_t st, double flops);
+void hct_prof_end(void* begin_event, cudaStream_t st, double work, int cls = HCT_PROF_GEMM);   // work: flops or bytes
+// RAII bracket for an entry point: records the event pair only when the class is enabled
+struct HctProfScope {
+  void* begin; cudaStream_t st; double work; int cls;
+  HctProfScope(cudaStream_t s, int c, double w) : begin(hct_prof_enabled(c) ? hct_prof_begin(s) : nullptr), st(s), work(w), cls(c) {}
+  ~HctProfScope() { if (begin != nullptr) hct_prof_end(begin, st, work, cls); }
+};
 
 #define HCT_REQUIRE(cond, ...)                \
   do {                                        \

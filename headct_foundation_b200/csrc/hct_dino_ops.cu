@@ -65,7 +65,8 @@ __global__ void weightnorm_fwd_kernel(const float* __restrict__ v, const float* 
   for (int c = lane; c < dim; c += 32) w[row * dim + c] = __float2bfloat16_rn(v[row * dim + c] * sc);
 }
 __global__ void weightnorm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
-                                      const float* __restrict__ inv_norm, float* __restrict__ dv, long long rows, int dim) {
+                                      const float* __restrict__ inv_norm, float* __restrict__ dv, float* __restrict__ dg,
+                                      long long rows, int dim) {
   const int lane = threadIdx.x & 31;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -73,6 +74,8 @@ __global__ void weightnorm_bwd_kernel(const float* __restrict__ dw, const float*
   float dot = 0.f;
   for (int c = lane; c < dim; c += 32) dot += dw[row * dim + c] * v[row * dim + c] * inv;
   dot = warp_sum(dot);
+  if (dg != nullptr && lane == 0) dg[row] = dot;          // d/dg of g * v / ||v||  (norm_last_layer=False trains the gain)
+  if (dv == nullptr) return;
   const float sc = g[row] * inv;
   for (int c = lane; c < dim; c += 32) dv[row * dim + c] = sc * (dw[row * dim + c] - dot * v[row * dim + c] * inv);
 }
@@ -213,7 +216,7 @@ __global__ void ema_multi_kernel(const long long* __restrict__ table, float m) {
 
 __global__ void grad_sqnorm_multi_kernel(const long long* __restrict__ table, float* __restrict__ norms) {
   __shared__ float red[33];
-  const long long* e = table + 6LL * blockIdx.y;
+  const long long* e = table + 7LL * blockIdx.y;
   const float* g = reinterpret_cast<const float*>(e[1]);
   const long long n = e[4];
   float s = 0.f;
@@ -225,11 +228,20 @@ __global__ void grad_sqnorm_multi_kernel(const long long* __restrict__ table, fl
 
 __global__ void adamw_multi_kernel(const long long* __restrict__ table, const float* __restrict__ sqnorms, float clip,
                                    float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                   const float* __restrict__ hyper) {
+                                   float step, const float* __restrict__ hyper) {
   if (hyper != nullptr) {      // per-step scalars from device memory: the launch can live in a CUDA graph
-    lr = hyper[0]; wd = hyper[1]; bc1 = hyper[2]; bc2_sqrt = hyper[3];
+    lr = hyper[0]; wd = hyper[1]; bc1 = hyper[2]; bc2_sqrt = hyper[3]; step = hyper[4];
   }
-  const long long* e = table + 6LL * blockIdx.y;
+  const long long* e = table + 7LL * blockIdx.y;
+  // torch.optim.AdamW bias-corrects every parameter with ITS OWN step count.  Column 6 holds how many steps this tensor
+  // is behind the table's first tensor (a tensor whose gradient was None for a while -- cancel_gradients_last_layer,
+  // misc.py:366-371 -- joins late with zero moments): bc1 / bc2_sqrt above are the first tensor's, recomputed here otherwise.
+  const long long behind = e[6];
+  if (behind != 0) {
+    const float s = step - static_cast<float>(behind);
+    bc1 = 1.f - powf(beta1, s);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, s));
+  }
   float* p = reinterpret_cast<float*>(e[0]);
   const float* g = reinterpret_cast<const float*>(e[1]);
   float* m = reinterpret_cast<float*>(e[2]);
@@ -310,10 +322,10 @@ extern "C" int hct_weightnorm_fwd(const float* v, const float* g, void* w, float
   return hct_check_launch("weightnorm_fwd_kernel");
 }
 extern "C" int hct_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm, float* dv,
-                                  int64_t rows, int32_t dim, hct_stream_t s) {
+                                  float* dg, int64_t rows, int32_t dim, hct_stream_t s) {
   if (rows <= 0) return HCT_OK;
   weightnorm_bwd_kernel<<<static_cast<unsigned>((rows * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(s)>>>(
-      dw, v, g, inv_norm, dv, rows, dim);
+      dw, v, g, inv_norm, dv, dg, rows, dim);
   return hct_check_launch("weightnorm_bwd_kernel");
 }
 
@@ -352,6 +364,7 @@ extern "C" int hct_grad_norms_multi(const int64_t* table, int32_t n, float* norm
   if (n <= 0) return HCT_OK;
   HCT_REQUIRE(n <= 65535, "grad_norms_multi: too many tensors (%d)", n);
   cudaStream_t st = static_cast<cudaStream_t>(s);
+  HctProfScope prof(st, HCT_PROF_ADAMW, 0.0);            // bytes are unknown here (the table lives on the device): the host adds them
   cudaError_t e = cudaMemsetAsync(norms_ws, 0, sizeof(float) * n, st);
   if (e != cudaSuccess) { hct_set_error("grad_norms_multi memset: %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
   grad_sqnorm_multi_kernel<<<dim3(32, n), 256, 0, st>>>(reinterpret_cast<const long long*>(table), norms_ws);
@@ -365,8 +378,10 @@ extern "C" int hct_adamw_multi(const int64_t* table, int32_t n, const float* nor
   HCT_REQUIRE(clip <= 0.f || norms_ws != nullptr, "adamw_multi: clip > 0 needs norms_ws");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  HctProfScope prof(static_cast<cudaStream_t>(s), HCT_PROF_ADAMW, 0.0);
   adamw_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(s)>>>(
-      reinterpret_cast<const long long*>(table), norms_ws, clip, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), nullptr);
+      reinterpret_cast<const long long*>(table), norms_ws, clip, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2),
+      static_cast<float>(step), nullptr);
   return hct_check_launch("adamw_multi_kernel");
 }
 
@@ -376,6 +391,6 @@ extern "C" int hct_adamw_multi_dev(const int64_t* table, int32_t n, const float*
   HCT_REQUIRE(n <= 65535 && hyper != nullptr, "adamw_multi_dev: n=%d hyper=%p", n, (const void*)hyper);
   HCT_REQUIRE(clip <= 0.f || norms_ws != nullptr, "adamw_multi_dev: clip > 0 needs norms_ws");
   adamw_multi_kernel<<<dim3(64, n), 256, 0, static_cast<cudaStream_t>(s)>>>(
-      reinterpret_cast<const long long*>(table), norms_ws, clip, 0.f, beta1, beta2, eps, 0.f, 1.f, 1.f, hyper);
+      reinterpret_cast<const long long*>(table), norms_ws, clip, 0.f, beta1, beta2, eps, 0.f, 1.f, 1.f, 1.f, hyper);
   return hct_check_launch("adamw_multi_kernel");
 }

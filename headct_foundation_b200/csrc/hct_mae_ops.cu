@@ -604,6 +604,7 @@ extern "C" int hct_window_scale_stack(const void* hu, int hu_i16, void* out, int
   for (int i = 0; i < nwin; ++i) { wp.a_min[i] = a_min[i]; wp.inv_w[i] = a_max[i] - a_min[i]; }
   const int grid = grid_for(nvol * (vox / 4), 256, hct_num_sms() * 16);
   cudaStream_t st = static_cast<cudaStream_t>(s);
+  HctProfScope prof(st, HCT_PROF_WINDOW, static_cast<double>(nvol) * vox * ((hu_i16 ? 2.0 : 4.0) + nwin * (out_bf16 ? 2.0 : 4.0)));
   if (hu_i16) {
     if (out_bf16) window_kernel<true, true><<<grid, 256, 0, st>>>(hu, out, nvol, vox, wp);
     else window_kernel<true, false><<<grid, 256, 0, st>>>(hu, out, nvol, vox, wp);
@@ -620,6 +621,8 @@ extern "C" int hct_patchify(const float* x, void* cols, const int64_t* patch_ids
   HCT_REQUIRE(p > 0 && H % p == 0 && W % p == 0 && D % p == 0, "patchify: volume %dx%dx%d not divisible by patch %d", H, W, D, p);
   HCT_REQUIRE(rows_per_vol > 0 && rows_per_vol <= (H / p) * (W / p) * (D / p), "patchify: rows_per_vol=%d", rows_per_vol);
   if (B <= 0) return HCT_OK;
+  HctProfScope prof(static_cast<cudaStream_t>(s), HCT_PROF_PATCHIFY,
+                    static_cast<double>(B) * rows_per_vol * C * p * p * p * (4.0 + 2.0));
   patchify_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows_per_vol), 128, 0, static_cast<cudaStream_t>(s)>>>(
       x, static_cast<bf16*>(cols), reinterpret_cast<const long long*>(patch_ids), pos_idx_out, C, H, W, D, p, rows_per_vol);
   return hct_check_launch("patchify_kernel");
@@ -714,6 +717,8 @@ extern "C" int hct_mae_loss_fwd(const void* pred, int32_t pred_prefix_rows, cons
   }
   float* per_patch = loss_out + 4;
   const unsigned grid = static_cast<unsigned>(static_cast<long long>(N) * L);
+  // algorithmic bytes as in SURVEY 8(d): pred (bf16) + target (fp32) of every patch row (an upper bound: unmasked rows are skipped)
+  HctProfScope prof(st, HCT_PROF_LOSS, static_cast<double>(N) * L * P * (2.0 + 4.0));
   if (p == 12)
     mae_loss_kernel<false, 12><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr,
                                                                       nullptr, nullptr, L, C, H, W, D, p, norm_pix, pred_prefix_rows);
@@ -742,6 +747,7 @@ extern "C" int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, cons
   }
   const unsigned grid = static_cast<unsigned>(static_cast<long long>(N) * L);
   cudaStream_t st = static_cast<cudaStream_t>(s);
+  HctProfScope prof(st, HCT_PROF_LOSS, static_cast<double>(N) * L * P * (2.0 + 4.0 + 2.0));      // + dpred out
   if (p == 12)
     mae_loss_kernel<true, 12><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss, mask_sum,
                                                                      static_cast<bf16*>(dpred), L, C, H, W, D, p, norm_pix, pred_prefix_rows);

@@ -401,6 +401,9 @@ extern "C" int hct_layernorm_fwd(const float* x, const float* gamma, const float
                                  float* mean, float* rstd, int64_t rows, int32_t dim, float eps, hct_stream_t s) {
   HCT_REQUIRE(rows >= 0 && dim > 0 && dim % 4 == 0 && dim <= LN_MAXV * 128, "layernorm_fwd: dim=%d unsupported", dim);
   if (rows == 0) return HCT_OK;
+  // algorithmic bytes: x fp32 in, y out, statistics out
+  HctProfScope prof(static_cast<cudaStream_t>(s), HCT_PROF_LN_FWD,
+                    static_cast<double>(rows) * (dim * (4.0 + (y_bf16 ? 2.0 : 4.0)) + (mean ? 4.0 : 0.0) + (rstd ? 4.0 : 0.0)));
   const int grid = grid_for(rows, LN_WARPS, hct_num_sms() * 8);
 #define HCT_LN_FWD(NV) \
   ln_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(s)>>>(x, gamma, beta, y, y_bf16, mean, rstd, rows, dim, eps)
@@ -432,6 +435,9 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
   HCT_REQUIRE(smem <= static_cast<size_t>(LN_SMEM_MAX), "layernorm_bwd: dim=%d needs %zu bytes of shared memory", dim, smem);
   cudaStream_t st = static_cast<cudaStream_t>(s);
   bf16* dx16 = static_cast<bf16*>(dx_out_bf16);
+  // algorithmic bytes: dy + x + (residual gradient) in, dx fp32 (+ bf16 copy) out
+  HctProfScope prof(st, HCT_PROF_LN_BWD,
+                    static_cast<double>(rows) * dim * ((dy_bf16 ? 2.0 : 4.0) + 4.0 + (dres_in ? 4.0 : 0.0) + 4.0 + (dx16 ? 2.0 : 0.0)));
   // bulk (TMA) staging needs 16-byte aligned rows of a multiple of 16 bytes in every stream
   const bool bulk = g_ln_bulk && dim % 8 == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
                     (reinterpret_cast<uintptr_t>(dy) % 16) == 0 && (dres_in == nullptr || reinterpret_cast<uintptr_t>(dres_in) % 16 == 0);

@@ -41,11 +41,11 @@ int hct_num_sms() {
   return sms[dev];
 }
 
-// ---- optional per-launch timing of the GEMM kernel (bench.py's roofline numbers) ----
+// ---- optional per-launch timing by kernel class (bench.py's roofline / roofline_secondary numbers) ----
 namespace {
-struct ProfRec { cudaEvent_t a, b; double flops; };
-bool g_prof_on = false;
-std::vector<ProfRec> g_prof;
+struct ProfRec { cudaEvent_t a, b; double work; };
+unsigned g_prof_mask = 0;
+std::vector<ProfRec> g_prof[HCT_PROF_CLASSES];
 std::vector<cudaEvent_t> g_event_pool;
 cudaEvent_t get_event() {
   if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
@@ -53,33 +53,39 @@ cudaEvent_t get_event() {
 }
 }  // namespace
 
-bool hct_prof_enabled() { return g_prof_on; }
+bool hct_prof_enabled(int cls) { return (g_prof_mask >> cls) & 1u; }
 void* hct_prof_begin(cudaStream_t st) {
   cudaEvent_t e = get_event();
   cudaEventRecord(e, st);
   return e;
 }
-void hct_prof_end(void* begin_event, cudaStream_t st, double flops) {
+void hct_prof_end(void* begin_event, cudaStream_t st, double work, int cls) {
   cudaEvent_t e = get_event();
   cudaEventRecord(e, st);
-  g_prof.push_back(ProfRec{static_cast<cudaEvent_t>(begin_event), e, flops});
+  g_prof[cls].push_back(ProfRec{static_cast<cudaEvent_t>(begin_event), e, work});
 }
 
-extern "C" int hct_profile_enable(int on) { g_prof_on = on != 0; return HCT_OK; }
-// Sums elapsed time / flops over all GEMM launches recorded since the last collect (synchronises on their events).
-extern "C" int hct_profile_collect(double* total_ms, double* total_flops, long long* launches) {
-  double ms = 0, fl = 0;
-  for (auto& r : g_prof) {
+// `on`: bit mask of 1 << class (1 = the GEMM kernel only, as in round 1; 0 = off)
+extern "C" int hct_profile_enable(int on) { g_prof_mask = static_cast<unsigned>(on); return HCT_OK; }
+// Sums elapsed time / work (flops or bytes) over all launches of a class recorded since its last collect (synchronises on
+// their events).
+extern "C" int hct_profile_collect_class(int cls, double* total_ms, double* total_work, long long* launches) {
+  HCT_REQUIRE(cls >= 0 && cls < HCT_PROF_CLASSES, "profile_collect_class: bad class %d", cls);
+  double ms = 0, wk = 0;
+  for (auto& r : g_prof[cls]) {
     float t = 0.f;
     cudaEventSynchronize(r.b);
-    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; fl += r.flops; }
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; wk += r.work; }
     g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
   }
   if (total_ms) *total_ms = ms;
-  if (total_flops) *total_flops = fl;
-  if (launches) *launches = static_cast<long long>(g_prof.size());
-  g_prof.clear();
+  if (total_work) *total_work = wk;
+  if (launches) *launches = static_cast<long long>(g_prof[cls].size());
+  g_prof[cls].clear();
   return HCT_OK;
+}
+extern "C" int hct_profile_collect(double* total_ms, double* total_flops, long long* launches) {
+  return hct_profile_collect_class(HCT_PROF_GEMM, total_ms, total_flops, launches);
 }
 
 extern "C" const char* hct_last_error(void) { return g_err; }

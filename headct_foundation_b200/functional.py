@@ -26,6 +26,19 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
                            "(no CPU fallback)")
 
 
+def _f32_stream(x: torch.Tensor, what: str) -> torch.Tensor:
+    """The kernels read the residual stream through raw fp32 pointers: a bf16 / fp16 hidden state (a caller inside
+    autocast, a half-precision model) is converted here instead of being misread; other dtypes are refused."""
+    _require_cuda(x, what)
+    if x.dtype == F32:
+        return x.contiguous()
+    if x.dtype == BF16:
+        return cast_f32(x)
+    if x.dtype == torch.float16:
+        return x.float().contiguous()
+    raise TypeError(f"{what}: expected a float32 / bfloat16 / float16 tensor, got {x.dtype}")
+
+
 # --------------------------------------------------------------------------------------------
 # bf16 shadow copies of fp32 parameters (what autocast would cast on every call), refreshed only
 # when the parameter's version counter changes (i.e. after an optimizer step / load_state_dict).
@@ -248,11 +261,11 @@ class BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b,
                 lqA, lqB, lvA, lvB, heads, eps):
-        _require_cuda(x, "AttentionBlock input")
+        xdtype = x.dtype
+        x = _f32_stream(x, "AttentionBlock input")
         B, S, D = x.shape
         M = B * S
         hd = D // heads
-        x = x.contiguous()
         dev = x.device
         need_grad = any(ctx.needs_input_grad[:17])
         st = stream_ptr(dev)
@@ -285,6 +298,7 @@ class BlockFn(torch.autograd.Function):
             ctx.save_for_backward(x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2,
                                   mean2, rstd2, a, g, lqA, lqB, lvA, lvB, tq, tv)
             ctx.heads = heads
+            ctx.xdtype = xdtype
         return x3
 
     @staticmethod
@@ -300,7 +314,7 @@ class BlockFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         (N1W, N1B, QKVW, QKVB, PROJW, PROJB, N2W, N2B, FC1W, FC1B, FC2W, FC2B, LQA, LQB, LVA, LVB) = range(1, 17)
         lora = lqA is not None
-        dout = dout.contiguous()
+        dout = _f32_stream(dout, "AttentionBlock output gradient")
         d3, dfc2_b = take_bf16_shadow(dout, with_colsum=True)
         if d3 is None:
             d3 = rows_to_bf16(dout, groups=1, src_rows_per_group=M, src_row_off=0, rows_per_group=M, dim=D)
@@ -361,7 +375,10 @@ class BlockFn(torch.autograd.Function):
         del dqkv
         dx, dx16, dn1w, dn1b, dxs = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, True, want_colsum=True,
                                                   zeros=(zs.take("n1w", D), zs.take("n1b", D), zs.take("dxs", D)))
-        put_bf16_shadow(dx, dx16, dxs)
+        if ctx.xdtype == F32:
+            put_bf16_shadow(dx, dx16, dxs)
+        else:
+            dx = dx.to(ctx.xdtype)
 
         def opt(i, t):
             return t if need[i] else None
@@ -521,24 +538,40 @@ class PoolAttentionFn(torch.autograd.Function):
 
 # A block's backward produces both the fp32 residual-stream gradient and its bf16 copy (the next GEMM
 # operand).  autograd only carries the fp32 tensor between nodes, so the bf16 copy rides in this
-# side table keyed by the fp32 tensor's storage; the consumer pops it (and falls back to a cast).
-_SHADOW: Dict[int, Tuple[Tuple[int, ...], torch.Tensor, Optional[torch.Tensor]]] = {}
+# side table; the consumer pops it (and falls back to a cast).
+# The entry is keyed by address but holds a STRONG reference to the fp32 tensor plus its autograd version: as long as
+# the table holds it the allocator cannot hand its address to another tensor, autograd's InputBuffer sees a second
+# owner and accumulates a second incoming gradient OUT of place (a new tensor at a new address -> miss -> cast), and
+# an in-place edit by a hook bumps the version (-> miss -> cast).  A stale copy can therefore never be served; `shadow_stats()` lets a bench assert that
+# the fast path is the one that ran.
+_SHADOW: Dict[int, Tuple[torch.Tensor, int, torch.Tensor, Optional[torch.Tensor]]] = {}
+_SHADOW_STATS = {"hit": 0, "miss": 0}
+
+
+def shadow_stats(reset: bool = False) -> Dict[str, int]:
+    """{'hit': n, 'miss': n}: how often a consumer found / did not find the producer's bf16 gradient copy."""
+    out = dict(_SHADOW_STATS)
+    if reset:
+        _SHADOW_STATS["hit"] = _SHADOW_STATS["miss"] = 0
+    return out
 
 
 def put_bf16_shadow(t32: torch.Tensor, t16: Optional[torch.Tensor], colsum16: Optional[torch.Tensor] = None) -> None:
     """Register the bf16 copy (and optionally its column sums) of an fp32 gradient about to be handed to autograd."""
     _SHADOW.clear()
     if t16 is not None:
-        _SHADOW[t32.data_ptr()] = (tuple(t32.shape), t16, colsum16)
+        _SHADOW[t32.data_ptr()] = (t32, t32._version, t16, colsum16)
 
 
 def take_bf16_shadow(t32: torch.Tensor, with_colsum: bool = False):
     hit = _SHADOW.pop(t32.data_ptr(), None)
     _SHADOW.clear()
-    if hit is None or hit[0] != tuple(t32.shape):
+    if hit is None or hit[0].shape != t32.shape or hit[1] != t32._version or hit[0]._version != hit[1]:
+        _SHADOW_STATS["miss"] += 1
         return (None, None) if with_colsum else None
-    t16 = hit[1].view(-1, t32.shape[-1])
-    return (t16, hit[2]) if with_colsum else t16
+    _SHADOW_STATS["hit"] += 1
+    t16 = hit[2].view(-1, t32.shape[-1])
+    return (t16, hit[3]) if with_colsum else t16
 
 
 # --------------------------------------------------------------------------------------------
@@ -653,8 +686,8 @@ class GatherTokensFn(torch.autograd.Function):
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps, out_bf16):
-        _require_cuda(x, "LayerNorm input")
-        x = x.contiguous()
+        ctx.xdtype = x.dtype
+        x = _f32_stream(x, "LayerNorm input")
         need = any(ctx.needs_input_grad[:3])
         y, mean, rstd = layernorm_fwd(x, w, b, eps, out_bf16, need)
         if need:
@@ -665,8 +698,13 @@ class LayerNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
+        if dy.dtype not in (F32, BF16):
+            dy = dy.float()
         dx, dx16, dg, db = layernorm_bwd(dy, x, w, mean, rstd, None, True)
-        put_bf16_shadow(dx, dx16)
+        if ctx.xdtype == F32:
+            put_bf16_shadow(dx, dx16)
+        else:
+            dx = dx.to(ctx.xdtype)
         return dx, dg, db, None, None
 
 
@@ -854,22 +892,28 @@ class WeightNormLinearFn(torch.autograd.Function):
             d16 = cast_bf16(dlogits.contiguous())
         dx = torch.empty((n, dim), dtype=BF16, device=dev)
         gemm(d16, w, M=n, N=dim, K=K, lda=K, ldb=dim, b_mn=True, out=dx, ldo=dim, epi=EPI_BF16)
-        dv = None
-        if ctx.needs_input_grad[2]:
+        dv = dg = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dw = linear_wgrad(d16, x16)                                                 # [K, dim] fp32
-            dv = torch.empty_like(weight_v)
+            dv = torch.empty_like(weight_v) if ctx.needs_input_grad[2] else None
+            # weight_g is frozen when norm_last_layer=True (dino_head.py:28-29); DINO.NORM_LAST_LAYER=False trains it
+            dg = torch.empty_like(weight_g) if ctx.needs_input_grad[1] else None
             call("hct_weightnorm_bwd", dw.data_ptr(), weight_v.data_ptr(), weight_g.data_ptr(), inv.data_ptr(),
-                 dv.data_ptr(), K, dim, stream_ptr(dev))
-        return dx, None, dv     # weight_g is frozen (norm_last_layer=True, dino_head.py:28-29)
+                 ptr(dv), ptr(dg), K, dim, stream_ptr(dev))
+        return dx, dg, dv
 
 
-_GRAD16: Dict[int, torch.Tensor] = {}
+_GRAD16: Dict[int, Tuple[torch.Tensor, int, torch.Tensor]] = {}     # same ownership rules as _SHADOW
 
 
 def take_grad16(t32: torch.Tensor) -> Optional[torch.Tensor]:
     hit = _GRAD16.pop(t32.data_ptr(), None)
     _GRAD16.clear()
-    return hit
+    if hit is None or hit[0].shape != t32.shape or hit[1] != t32._version or hit[0]._version != hit[1]:
+        _SHADOW_STATS["miss"] += 1
+        return None
+    _SHADOW_STATS["hit"] += 1
+    return hit[2]
 
 
 class DinoLossFn(torch.autograd.Function):
@@ -901,7 +945,7 @@ class DinoLossFn(torch.autograd.Function):
              d16.data_ptr(), dloss.data_ptr(), B, ncrops, K, ts, tt, stream_ptr(dev))
         d32 = cast_f32(d16)
         _GRAD16.clear()
-        _GRAD16[d32.data_ptr()] = d16       # the prototype layer's backward consumes the bf16 copy directly
+        _GRAD16[d32.data_ptr()] = (d32, d32._version, d16)       # the prototype layer's backward consumes the bf16 copy directly
         return d32, None, None, None, None, None
 
 

@@ -23,6 +23,10 @@ class FusedAdamW(torch.optim.Optimizer):
         self._tables = {}
         self._graph_state = {}
 
+    def _steps(self, ps):
+        """Per-parameter step counts BEFORE this update (state['step'] is a CPU tensor, as in torch.optim.AdamW)."""
+        return [int(self.state[p]["step"]) for p in ps]
+
     def _table(self, gi, group):
         ps = [p for p in group["params"] if p.grad is not None]
         rows = []
@@ -40,9 +44,15 @@ class FusedAdamW(torch.optim.Optimizer):
                 p.grad = g
             sh = shadow_of(p)        # bf16 GEMM-operand copy, rewritten by the AdamW launch itself
             shadows.append(sh)
-            rows.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
-                         0 if sh is None else sh.data_ptr()))
-        sig = tuple(rows)
+            rows.append([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                         0 if sh is None else sh.data_ptr(), 0])
+        # column 6: how many steps each tensor is behind the first one (torch bias-corrects per parameter; a tensor whose
+        # grad was None for a while -- cancel_gradients_last_layer -- lags).  Part of the signature: the table is rebuilt
+        # whenever the set of participating tensors or their relative step counts change.
+        steps = self._steps(ps)
+        for row, s in zip(rows, steps):
+            row[6] = steps[0] - s
+        sig = tuple(tuple(r) for r in rows)
         hit = self._tables.get(gi)
         if hit is None or hit[0] != sig:
             dev = ps[0].device
@@ -50,7 +60,7 @@ class FusedAdamW(torch.optim.Optimizer):
             norms = torch.empty(len(rows), dtype=torch.float32, device=dev)
             hit = (sig, table, norms)
             self._tables[gi] = hit
-        return ps, hit[1], hit[2], shadows
+        return ps, hit[1], hit[2], shadows, steps[0] + 1
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -61,8 +71,7 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             if not any(p.grad is not None for p in group["params"]):
                 continue
-            ps, table, norms, shadows = self._table(gi, group)
-            step = int(self.state[ps[0]]["step"].item()) + 1
+            ps, table, norms, shadows, step = self._table(gi, group)
             for p in ps:
                 self.state[p]["step"] += 1
             st = stream_ptr(ps[0].device)
@@ -78,7 +87,7 @@ class FusedAdamW(torch.optim.Optimizer):
     # ------------------------------------------------------------------ CUDA-graph support (utils/graphs.py)
     def _hyper_values(self, group, step: int):
         b1, b2 = group["betas"]
-        return [float(group["lr"]), float(group["weight_decay"]), 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5]
+        return [float(group["lr"]), float(group["weight_decay"]), 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5, float(step)]
 
     def prepare_capture(self):
         """Allocate the buffers the captured update reads (pointer table, norm workspace, per-step scalars) OUTSIDE the
@@ -87,10 +96,10 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, group in enumerate(self.param_groups):
             n = len(group["params"])
             dev = group["params"][0].device
-            self._graph_state[gi] = dict(table_host=torch.zeros((n, 6), dtype=torch.int64).pin_memory(),
-                                         table=torch.zeros((n, 6), dtype=torch.int64, device=dev),
+            self._graph_state[gi] = dict(table_host=torch.zeros((n, 7), dtype=torch.int64).pin_memory(),
+                                         table=torch.zeros((n, 7), dtype=torch.int64, device=dev),
                                          norms=torch.zeros(n, dtype=torch.float32, device=dev),
-                                         hyper=torch.zeros(4, dtype=torch.float32, device=dev), params=[], shadows=[])
+                                         hyper=torch.zeros(5, dtype=torch.float32, device=dev), params=[], shadows=[])
 
     @torch.no_grad()
     def step_captured(self):
@@ -114,8 +123,11 @@ class FusedAdamW(torch.optim.Optimizer):
                     raise RuntimeError("FusedAdamW.step_captured needs contiguous gradients")
                 sh = shadow_of(p)
                 shadows.append(sh)
-                rows.append((p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
-                             0 if sh is None else sh.data_ptr()))
+                rows.append([p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(),
+                             0 if sh is None else sh.data_ptr(), 0])
+            steps = self._steps(ps)          # the lags are constant across replays: every captured tensor steps together
+            for row, s in zip(rows, steps):
+                row[6] = steps[0] - s
             n = len(rows)
             gs["table_host"][:n].copy_(torch.tensor(rows, dtype=torch.int64))
             gs["params"], gs["shadows"] = ps, shadows

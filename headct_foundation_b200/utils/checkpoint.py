@@ -72,16 +72,37 @@ def _pretrained_path(config_or_path) -> Optional[str]:
     return config_or_path.MODEL.PRETRAINED            # yacs-style config, misc.py:74
 
 
+def _read_checkpoint(path, trust_pickle: bool = False):
+    """misc.py:73-76: the reference allow-lists numpy's scalar constructor (checkpoints carry `best_loss` as a numpy
+    scalar) and loads with torch's safe unpickler.  Same here: `weights_only=True` with numpy scalar / dtype globals
+    allow-listed, so a crafted .pt cannot execute code on load.  `trust_pickle=True` is the explicit opt-in for legacy
+    files that hold arbitrary Python objects."""
+    if trust_pickle:
+        return torch.load(path, map_location=torch.device("cpu"), weights_only=False)
+    import numpy as np
+    safe = [np.dtype, np.ndarray]
+    for mod in ("numpy.core.multiarray", "numpy._core.multiarray"):
+        try:
+            m = __import__(mod, fromlist=["scalar", "_reconstruct"])
+            safe += [m.scalar, m._reconstruct]
+        except Exception:          # module path differs between numpy 1.x and 2.x
+            pass
+    safe += [type(np.dtype(t)) for t in ("float64", "float32", "int64", "int32", "bool")]
+    with torch.serialization.safe_globals(safe):
+        return torch.load(path, map_location=torch.device("cpu"), weights_only=True)
+
+
 def load_model(config_or_path, model, momentum_model=None, logger=None, model_name: str = "dino",
-               interpolate_position_embeddings: bool = False):
+               interpolate_position_embeddings: bool = False, trust_pickle: bool = False):
     """misc.py:72-95.  `config_or_path`: the reference's config object (uses .MODEL.PRETRAINED) or a file path.
     Returns the whole checkpoint dict (for `load_optimizer`) or None when no checkpoint is configured.
     The reference keeps position-embedding interpolation commented out (misc.py:80-81); it is available here behind
-    a flag because downstream runs at another resolution need it."""
+    a flag because downstream runs at another resolution need it.  Files are read with torch's safe unpickler
+    (`_read_checkpoint`); pass trust_pickle=True only for trusted legacy pickles."""
     path = _pretrained_path(config_or_path)
     if path is None:
         return None
-    ckpt = torch.load(path, map_location=torch.device("cpu"), weights_only=False)
+    ckpt = _read_checkpoint(path, trust_pickle)
     sd = strip_wrapper_prefixes(ckpt["state_dict"])
     if interpolate_position_embeddings:
         interpolate_pos_embed(_unwrap(model), sd)

@@ -35,8 +35,12 @@ long long hct_launch_count(void);
 /* Measurement aid (bench.py roofline): when enabled every hct_gemm_bf16 launch is bracketed by CUDA
  * events on its own stream; collect() returns the summed kernel time, 2*M*N*K flops and launch count
  * since the previous collect (it waits for those events). */
-int hct_profile_enable(int on);
+int hct_profile_enable(int on);     /* bit mask of (1 << class); 1 = GEMM only, 0 = off */
 int hct_profile_collect(double* total_ms, double* total_flops, long long* launches);
+/* The same per kernel class (bench.py roofline_secondary).  class: 0 GEMM (flops), 1 attention forward (flops = 4 S^2 D per
+ * (batch, layer)), 2 attention backward (flops = 2 x forward, delta / tail launches included in the time), 3 LayerNorm
+ * forward, 4 LayerNorm backward, 5 masked-MSE loss, 6 clip + AdamW, 7 HU windowing, 8 patchify (3..8: algorithmic bytes). */
+int hct_profile_collect_class(int cls, double* total_ms, double* total_work, long long* launches);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM core (tcgen05 / TMEM / TMA):  C[M,N] = epilogue( A[M,K] * B[N,K]^T )
@@ -226,9 +230,10 @@ int hct_l2norm_bwd(const void* dy_bf16, const void* y_bf16, const float* inv_nor
 /* weight_norm (dino_head.py:26-29): w_bf16[r,:] = g[r] * v[r,:] / ||v[r,:]|| ; inv_norm fp32[rows] */
 int hct_weightnorm_fwd(const float* v, const float* g, void* w_bf16, float* inv_norm, int64_t rows,
                        int32_t dim, hct_stream_t stream);
-/* dv = g*inv*(dw - (dw . vhat) vhat)  (g frozen: norm_last_layer=True, dino_head.py:28-29) */
+/* dv = g*inv*(dw - (dw . vhat) vhat); dg[r] = dw[r,:] . vhat[r,:].  dv / dg may be NULL (g is frozen when
+ * norm_last_layer=True, dino_head.py:28-29; with norm_last_layer=False the gain trains). */
 int hct_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* inv_norm,
-                       float* dv, int64_t rows, int32_t dim, hct_stream_t stream);
+                       float* dv, float* dg, int64_t rows, int32_t dim, hct_stream_t stream);
 /* DINOLoss.forward (losses.py:63-89).  student fp32 [ncrops*B, K], teacher fp32 [2*B, K],
  * center fp32 [K].  loss_out fp32[1] (may be NULL) is ACCUMULATED into (zero it first).
  * stats_ws: fp32 [2*(ncrops+2)*B] (row max / log-sum-exp; recomputed on every call).
@@ -284,8 +289,11 @@ int hct_adjust_contrast(float* x, const float* gamma, int32_t* minmax_ws, int64_
 /* ---------------------------------------------------------------------------------------------
  * Train-step glue: per-parameter clip (misc.py:374-383) + AdamW
  * (optimizers.py:354-360) as one multi-tensor launch each.
- * table: int64 [n, 6] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel, param_bf16_shadow_ptr or 0};
- * the AdamW launch also refreshes the bf16 copy of every updated parameter that has one.
+ * table: int64 [n, 7] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel, param_bf16_shadow_ptr or 0,
+ * steps_behind}; the AdamW launch also refreshes the bf16 copy of every updated parameter that has one.
+ * steps_behind = (step count of row 0) - (step count of this row): torch.optim.AdamW bias-corrects each parameter with
+ * its own state['step'], and a tensor whose gradient was None for some steps (cancel_gradients_last_layer,
+ * misc.py:366-371 / engine_pretrain_dino.py:95) lags the others; `step` below is row 0's count for this update.
  * norms_ws: fp32 [n] workspace receiving each gradient's SQUARED L2 norm.
  * ------------------------------------------------------------------------------------------- */
 int hct_grad_norms_multi(const int64_t* table, int32_t n, float* norms_ws, hct_stream_t stream);
@@ -293,7 +301,7 @@ int hct_adamw_multi(const int64_t* table, int32_t n, const float* norms_ws, floa
                     float beta1, float beta2, float eps, float weight_decay, int32_t step,
                     hct_stream_t stream);
 /* Same update with the per-step scalars read from DEVICE memory, so that the launch can be captured in a CUDA graph and
- * replayed while the schedule moves: hyper fp32 [4] = {lr, weight_decay, 1 - beta1^step, sqrt(1 - beta2^step)}
+ * replayed while the schedule moves: hyper fp32 [5] = {lr, weight_decay, 1 - beta1^step, sqrt(1 - beta2^step), step}
  * (lr_sched.py:18-55 changes lr every iteration; the bias corrections change with the step count). */
 int hct_adamw_multi_dev(const int64_t* table, int32_t n, const float* norms_ws, float clip, const float* hyper,
                         float beta1, float beta2, float eps, hct_stream_t stream);

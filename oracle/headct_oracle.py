@@ -111,7 +111,7 @@ def masking_indices(noise: Tensor, mask_ratio: float) -> Tuple[Tensor, Tensor, T
     len_keep = int(L * (1 - mask_ratio))
     ids_shuffle = torch.argsort(noise, dim=1, stable=True)
     ids_restore = torch.empty_like(ids_shuffle)
-    ar = torch.arange(L, dtype=ids_shuffle.dtype).expand(N, L)
+    ar = torch.arange(L, dtype=ids_shuffle.dtype, device=noise.device).expand(N, L)
     ids_restore.scatter_(1, ids_shuffle, ar)
     ids_keep = ids_shuffle[:, :len_keep]
     mask = (ids_restore >= len_keep).to(torch.float32)  # == gather([0]*keep+[1]*rest, ids_restore)

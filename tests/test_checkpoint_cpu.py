@@ -145,3 +145,27 @@ def test_checkpoint_matches_the_reference_loader(tmp_path):
     ck.interpolate_pos_embed(big_ours, sd_a)
     ref.pos_embed.interpolate_pos_embed(big_ours, sd_b)
     assert torch.allclose(sd_a["patch_embedding.position_embeddings"], sd_b["patch_embedding.position_embeddings"], atol=1e-6)
+
+
+def test_load_model_uses_the_safe_unpickler(tmp_path):
+    """misc.py:73-76 loads with torch's default (safe) unpickler + a numpy-scalar allow-list.  A file that smuggles an
+    arbitrary callable must be refused unless the caller opts in with trust_pickle=True; a checkpoint that carries
+    `best_loss` as a numpy scalar (what the reference writes) must load."""
+    import numpy as np
+    from headct_foundation_b200.utils.checkpoint import load_model
+
+    class Boom:
+        def __reduce__(self):
+            return (eval, ("__import__('os').environ.__setitem__('HCT_PWNED', '1')",))
+
+    model = _vit()
+    bad = tmp_path / "bad.pt"
+    torch.save({"state_dict": model.state_dict(), "extra": Boom()}, bad)
+    os.environ.pop("HCT_PWNED", None)
+    with pytest.raises(Exception):
+        load_model(str(bad), model)
+    assert "HCT_PWNED" not in os.environ
+    good = tmp_path / "good.pt"
+    torch.save({"state_dict": model.state_dict(), "best_loss": np.float64(0.25), "epoch": 3}, good)
+    ckpt = load_model(str(good), model)
+    assert float(ckpt["best_loss"]) == 0.25 and ckpt["epoch"] == 3

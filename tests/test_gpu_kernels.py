@@ -387,17 +387,23 @@ def test_l2norm_weightnorm(cuda, HF):
     go = torch.randn(10, 256, generator=g)
     yr.backward(go); y.backward(go.to(cuda).bfloat16())
     assert _rel(xc.grad.cpu(), xr.grad) < 1.5e-2
-    v = torch.randn(512, 64, generator=g) * 0.02; gg = torch.ones(512, 1)
-    vr = v.clone().requires_grad_(True)
-    w = vr * (gg / vr.norm(dim=1, keepdim=True))
+    # weight_norm with a TRAINABLE gain (DINOHead(norm_last_layer=False), dino_head.py:28-29): dv and dg
+    v = torch.randn(512, 64, generator=g) * 0.02; gg = 0.5 + torch.rand(512, 1, generator=g)
+    vr = v.clone().requires_grad_(True); gr = gg.clone().requires_grad_(True)
+    w = vr * (gr / vr.norm(dim=1, keepdim=True))
     xin = torch.randn(6, 64, generator=g).bfloat16()
     logits_r = xin.float() @ w.t()
-    vc = v.to(cuda).requires_grad_(True); gc = gg.to(cuda)
+    vc = v.to(cuda).requires_grad_(True); gc = gg.to(cuda).requires_grad_(True)
     logits = HF.WeightNormLinearFn.apply(xin.to(cuda), gc, vc)
     assert _rel(logits.cpu(), logits_r.detach()) < 5e-3
     gl = torch.randn(6, 512, generator=g)
     logits_r.backward(gl); logits.backward(gl.to(cuda))
     assert _rel(vc.grad.cpu(), vr.grad) < 1.5e-2
+    assert gc.grad is not None and _rel(gc.grad.cpu(), gr.grad) < 1.5e-2
+    # frozen gain (norm_last_layer=True): no dg is produced
+    gc2 = gg.to(cuda); vc2 = v.to(cuda).requires_grad_(True)
+    HF.WeightNormLinearFn.apply(xin.to(cuda), gc2, vc2).backward(gl.to(cuda))
+    assert _rel(vc2.grad.cpu(), vr.grad) < 1.5e-2 and gc2.grad is None
 
 
 def test_ema_and_adamw_multi(cuda, HF):
@@ -425,7 +431,7 @@ def test_ema_and_adamw_multi(cuda, HF):
     mc = [torch.zeros_like(p) for p in pc]; vc = [torch.zeros_like(p) for p in pc]
     # bf16 shadows (the GEMM operand copies) for every second tensor: the AdamW launch must keep them current
     sh = [torch.zeros(p.shape, dtype=torch.bfloat16, device=cuda) if i % 2 == 0 else None for i, p in enumerate(pc)]
-    table = torch.tensor([[p.data_ptr(), x.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 0 if h is None else h.data_ptr()]
+    table = torch.tensor([[p.data_ptr(), x.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 0 if h is None else h.data_ptr(), 0]
                           for p, x, m, v, h in zip(pc, gc, mc, vc, sh)], dtype=torch.int64, device=cuda)
     norms = torch.empty(len(pc), device=cuda)
     for step in (1, 2):
@@ -441,3 +447,44 @@ def test_ema_and_adamw_multi(cuda, HF):
     for a, h in zip(pc, sh):
         if h is not None:
             assert torch.equal(h, a.bfloat16())
+
+
+def test_fused_adamw_per_parameter_step_matches_torch(cuda, HF):
+    """torch.optim.AdamW bias-corrects every parameter with its own step count.  DINO's cancel_gradients_last_layer
+    (misc.py:366-371, engine_pretrain_dino.py:95) sets last_layer grads to None during the first epoch, so that tensor
+    joins later with zero moments and step 0: FusedAdamW must give it ITS bias correction (round 1 used the group's),
+    and a tensor that drops out for a few steps must resume with its own count.  Compared with stock AdamW every step."""
+    from headct_foundation_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(11)
+    shapes = [(64, 32), (32,), (128, 16), (7,)]
+    init = [torch.randn(*s, generator=g) for s in shapes]
+    ours = [torch.nn.Parameter(t.clone().to(cuda)) for t in init]
+    ref = [torch.nn.Parameter(t.clone().to(cuda)) for t in init]
+    kw = dict(lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.04)
+    fo = FusedAdamW(ours, clip_grad=0.0, **kw)
+    ro = torch.optim.AdamW(ref, **kw)
+    frozen_until = {2: 6}                 # tensor 2 ("last_layer") has no gradient for the first 6 steps
+    pause = {1: range(9, 12)}             # tensor 1 drops out for steps 9..11 and comes back
+    for step in range(16):
+        for i, (po, pr) in enumerate(zip(ours, ref)):
+            gr = torch.randn(*shapes[i], generator=g).to(cuda)
+            off = step < frozen_until.get(i, 0) or step in pause.get(i, ())
+            po.grad = None if off else gr.clone()
+            pr.grad = None if off else gr.clone()
+        fo.step(); ro.step()
+        for i, (po, pr) in enumerate(zip(ours, ref)):
+            assert _rel(po.detach().cpu(), pr.detach().cpu()) < 2e-6, (step, i)
+    assert int(fo.state[ours[2]]["step"]) == 10 and int(fo.state[ours[1]]["step"]) == 13 and int(fo.state[ours[0]]["step"]) == 16
+    # the first tensor of the table may itself be the late one (table keyed on "params with a grad")
+    ours2 = [torch.nn.Parameter(t.clone().to(cuda)) for t in init[:2]]
+    ref2 = [torch.nn.Parameter(t.clone().to(cuda)) for t in init[:2]]
+    fo2, ro2 = FusedAdamW(ours2, **kw), torch.optim.AdamW(ref2, **kw)
+    for step in range(8):
+        for i, (po, pr) in enumerate(zip(ours2, ref2)):
+            gr = torch.randn(*shapes[i], generator=g).to(cuda)
+            off = i == 0 and step < 4
+            po.grad = None if off else gr.clone()
+            pr.grad = None if off else gr.clone()
+        fo2.step(); ro2.step()
+        for po, pr in zip(ours2, ref2):
+            assert _rel(po.detach().cpu(), pr.detach().cpu()) < 2e-6, step
