@@ -60,7 +60,9 @@ def test_mae_full_config_batch16_against_oracle_on_cuda(cuda, batch):
     assert rel < 1e-2, (loss.item(), ref["loss"].item())
     assert _cos(latent, ref["latent"]) > 0.9995
     grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
-    assert set(grads) == set(rgrads), set(grads) ^ set(rgrads)
+    frozen = {k for k, p in model.named_parameters() if not p.requires_grad}          # decoder_pos_embed (mae.py:92)
+    assert frozen == {"decoder_pos_embed"}
+    assert set(grads) == set(rgrads) - frozen, set(grads) ^ set(rgrads)
     bad = {}
     for k, g in grads.items():
         r = rgrads[k]
