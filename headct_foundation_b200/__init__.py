@@ -17,10 +17,11 @@ from .utils.checkpoint import save_checkpoint, load_model, load_optimizer, inter
 from .utils.graphs import GraphedForward, GraphedTrainStep
 from .utils.metrics import DownstreamMetrics, multiclass_accuracy, multiclass_auroc
 from .losses.losses import DINOLoss
+from .functional import set_precision, get_precision, precision
 from .data.transforms import MultipleWindowScaleStack, MAE3DTrainAugment, ViTTrainAugment, DataAugmentationDINO3D
 
 __all__ = ["MaskedAutoencoderViT", "ViT", "AttentionBlock", "SelfAttention", "MLPBlock", "DINOHead",
            "LinearClassifier", "AttentionClassifier", "RMSNorm", "LoraLinear", "PatchEmbeddingBlock", "build_sincos_position_embedding", "MultiCropWrapper",
            "update_momentum_encoder", "set_requires_grad_false", "GraphedForward", "GraphedTrainStep", "DownstreamMetrics", "multiclass_accuracy", "multiclass_auroc", "DINOLoss", "MultipleWindowScaleStack", "save_checkpoint", "load_model",
            "load_optimizer", "interpolate_pos_embed", "strip_wrapper_prefixes", "MAE3DTrainAugment", "ViTTrainAugment",
-           "DataAugmentationDINO3D"]
+           "DataAugmentationDINO3D", "set_precision", "get_precision", "precision"]

@@ -94,6 +94,19 @@ _SIGNATURES = {
     "hct_colnorm_bwd": [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _P],
     "hct_pool_attention_fwd": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _P],
     "hct_pool_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _P],
+    # fp32 mode
+    "hct_split3_bf16": [_P, _I64, _I64, _I32, _I32, _P, _I64, _I32, _I32, _I32, _P],
+    "hct_gelu_f32": [_P, _P, _I64, _P],
+    "hct_gelu_bwd_f32": [_P, _P, _P, _I64, _P],
+    "hct_copy_rows_f32": [_P, _I64, _I64, _I32, _P, _I64, _I32, _I32, _P],
+    "hct_scatter_add_rows_f32": [_P, _P, _P, _I64, _I32, _P],
+    "hct_attention_f32_fwd": [_P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_attention_f32_bwd": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_patchify_f32": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "hct_decoder_assemble_f32": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_decoder_assemble_bwd_f32": [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_mae_loss_fwd_f32": [_P, _I32, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
+    "hct_mae_loss_bwd_f32": [_P, _I32, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("hct_last_error", "hct_abi_version", "hct_launch_count")
 

@@ -51,9 +51,11 @@ __global__ void window_kernel(const void* __restrict__ hu, void* __restrict__ ou
 
 // ------------------------------------------------------------------ a2: patchify (im2col, K order c,ph,pw,pd)
 // one CTA per output row; thread t copies run t = (c, ph, pw): p contiguous floats along D.
+template <bool OUT_F32>
 __global__ void __launch_bounds__(128)
-patchify_kernel(const float* __restrict__ x, bf16* __restrict__ cols, const long long* __restrict__ patch_ids,
+patchify_kernel(const float* __restrict__ x, void* __restrict__ cols_, const long long* __restrict__ patch_ids,
                 int* __restrict__ pos_idx_out, int C, int H, int W, int D, int p, int rows_per_vol) {
+  bf16* cols = static_cast<bf16*>(cols_);
   const long long row = blockIdx.x;
   const int b = static_cast<int>(row / rows_per_vol), j = static_cast<int>(row % rows_per_vol);
   const int gw = W / p, gd = D / p;
@@ -66,6 +68,11 @@ patchify_kernel(const float* __restrict__ x, bf16* __restrict__ cols, const long
   for (int r = threadIdx.x; r < runs; r += blockDim.x) {
     const int c = r / (p * p), ph = (r / p) % p, pw = r % p;
     const float* src = x + (((static_cast<long long>(b) * C + c) * H + ph0 + ph) * W + pw0 + pw) * D + pd0;
+    if (OUT_F32) {                                   // fp32 mode: the patch rows stay fp32 (split into bf16 terms later)
+      float* d32 = static_cast<float*>(cols_) + row * K + static_cast<long long>(r) * p;
+      for (int k = 0; k < p; ++k) d32[k] = src[k];
+      continue;
+    }
     bf16* d = dst + static_cast<long long>(r) * p;
     if ((p & 3) == 0 && (D & 3) == 0) {
       for (int k = 0; k < p; k += 4) {
@@ -134,7 +141,15 @@ __global__ void scatter_tokens_kernel(const float* __restrict__ ddst, const long
 }
 
 // ------------------------------------------------------------------ a7: decoder input assembly
-__global__ void decoder_assemble_kernel(const bf16* __restrict__ y, const long long* __restrict__ ids_restore,
+template <bool Y_F32>
+__device__ __forceinline__ float4 load_row4(const void* base, long long row, int dim, int c) {
+  if (Y_F32) return reinterpret_cast<const float4*>(static_cast<const float*>(base) + row * dim)[c];
+  const uint2 u = reinterpret_cast<const uint2*>(static_cast<const bf16*>(base) + row * dim)[c];
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <bool Y_F32>
+__global__ void decoder_assemble_kernel(const void* __restrict__ y, const long long* __restrict__ ids_restore,
                                         const float* __restrict__ mask_token, const float* __restrict__ dec_cls,
                                         const float* __restrict__ dec_pos, float* __restrict__ out, int L, int keep,
                                         int dim, long long total_rows) {
@@ -147,16 +162,12 @@ __global__ void decoder_assemble_kernel(const bf16* __restrict__ y, const long l
     const int t = static_cast<int>(r % (L + 1));
     float4 v, add;
     if (t == 0) {
-      const uint2 u = reinterpret_cast<const uint2*>(y + (n * (keep + 1)) * dim)[c];
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-      v = make_float4(a.x, a.y, b.x, b.y);
+      v = load_row4<Y_F32>(y, n * (keep + 1), dim, c);
       add = __ldg(reinterpret_cast<const float4*>(dec_cls) + c);
     } else {
       const long long src = ids_restore[n * L + (t - 1)];
       if (src < keep) {
-        const uint2 u = reinterpret_cast<const uint2*>(y + (n * (keep + 1) + 1 + src) * dim)[c];
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-        v = make_float4(a.x, a.y, b.x, b.y);
+        v = load_row4<Y_F32>(y, n * (keep + 1) + 1 + src, dim, c);
       } else {
         v = __ldg(reinterpret_cast<const float4*>(mask_token) + c);
       }
@@ -167,8 +178,9 @@ __global__ void decoder_assemble_kernel(const bf16* __restrict__ y, const long l
 }
 
 // block (dim/4 threads, <= 512) walks rows; masked rows accumulate into dmask_token, row 0 into ddec_cls
+template <bool Y_F32>
 __global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dout, const long long* __restrict__ ids_restore,
-                                            bf16* __restrict__ dy, float* __restrict__ dmask_token,
+                                            void* __restrict__ dy, float* __restrict__ dmask_token,
                                             float* __restrict__ ddec_cls, int L, int keep, int dim,
                                             long long total_rows) {
   const int nv = dim >> 2;
@@ -188,8 +200,12 @@ __global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dout, cons
         else { am.x += g.x; am.y += g.y; am.z += g.z; am.w += g.w; }
       }
       if (dst_row >= 0) {
-        uint2 u; u.x = pack_bf16x2(g.x, g.y); u.y = pack_bf16x2(g.z, g.w);
-        reinterpret_cast<uint2*>(dy + dst_row * dim)[c] = u;
+        if (Y_F32) {
+          reinterpret_cast<float4*>(static_cast<float*>(dy) + dst_row * dim)[c] = g;
+        } else {
+          uint2 u; u.x = pack_bf16x2(g.x, g.y); u.y = pack_bf16x2(g.z, g.w);
+          reinterpret_cast<uint2*>(static_cast<bf16*>(dy) + dst_row * dim)[c] = u;
+        }
       }
     }
     if (dmask_token) {
@@ -210,11 +226,16 @@ __global__ void decoder_assemble_bwd_kernel(const float* __restrict__ dout, cons
 // PS: patch side as a compile-time constant (12 = every shipped yaml; 0 = generic).  The target gather computes four
 // quotients per 16-byte load; with a run-time divisor that arithmetic (ALU 50 %, issue slots 62 % busy under ncu) and not
 // DRAM bounded the kernel.
-template <bool BWD, int PS>
+// PF32: prediction (and its gradient) are fp32 rows instead of bf16 (fp32 mode)
+template <bool BWD, int PS, bool PF32 = false>
 __global__ void __launch_bounds__(256)
-mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, const float* __restrict__ mask,
+mae_loss_kernel(const void* __restrict__ pred_, const float* __restrict__ imgs, const float* __restrict__ mask,
                 float* __restrict__ per_patch, const float* __restrict__ dloss, const float* __restrict__ mask_sum,
-                bf16* __restrict__ dpred, int L, int C, int H, int W, int D, int p_arg, int norm_pix, int prefix) {
+                void* __restrict__ dpred_, int L, int C, int H, int W, int D, int p_arg, int norm_pix, int prefix) {
+  const bf16* pred = static_cast<const bf16*>(pred_);
+  bf16* dpred = static_cast<bf16*>(dpred_);
+  const float* pred32 = static_cast<const float*>(pred_);
+  float* dpred32 = static_cast<float*>(dpred_);
   const int p = PS > 0 ? PS : p_arg;
   extern __shared__ __align__(16) float tgt[];     // [P]
   __shared__ float red[33];
@@ -226,13 +247,19 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
   const long long prow = static_cast<long long>(n) * (L + prefix) + prefix + l;
   if (BWD && l == 0 && prefix > 0) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < prefix * (P >> 3); i += blockDim.x)
-      reinterpret_cast<uint4*>(dpred + static_cast<long long>(n) * (L + prefix) * P)[i] = z;
+    if (PF32) {
+      for (int i = threadIdx.x; i < prefix * (P >> 2); i += blockDim.x)
+        reinterpret_cast<uint4*>(dpred32 + static_cast<long long>(n) * (L + prefix) * P)[i] = z;
+    } else {
+      for (int i = threadIdx.x; i < prefix * (P >> 3); i += blockDim.x)
+        reinterpret_cast<uint4*>(dpred + static_cast<long long>(n) * (L + prefix) * P)[i] = z;
+    }
   }
   if (m == 0.f) {
     if (BWD) {
       const uint4 z = make_uint4(0, 0, 0, 0);
-      for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) reinterpret_cast<uint4*>(dpred + prow * P)[i] = z;
+      if (PF32) { for (int i = threadIdx.x; i < (P >> 2); i += blockDim.x) reinterpret_cast<uint4*>(dpred32 + prow * P)[i] = z; }
+      else { for (int i = threadIdx.x; i < (P >> 3); i += blockDim.x) reinterpret_cast<uint4*>(dpred + prow * P)[i] = z; }
     } else if (threadIdx.x == 0) {
       per_patch[patch] = 0.f;
     }
@@ -246,7 +273,7 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
   constexpr int PRE = 4;
   const bf16* pr = pred + prow * P;
   const int nvec = P >> 3;
-  const bool preload = nvec <= PRE * static_cast<int>(blockDim.x);
+  const bool preload = !PF32 && nvec <= PRE * static_cast<int>(blockDim.x);
   uint4 pu[PRE];
   if (preload) {
 #pragma unroll
@@ -289,11 +316,17 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
   if (!BWD) {
     float s = 0.f;
     for (int i = threadIdx.x, k = 0; i < nvec; i += blockDim.x, ++k) {
-      uint4 u;
-      if (preload) { u = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3])); }
-      else u = reinterpret_cast<const uint4*>(pr)[i];
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
-      const float pv[8] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d2.x, d2.y};
+      float pv[8];
+      if (PF32) {
+        const float4 a = reinterpret_cast<const float4*>(pred32 + prow * P)[2 * i], b = reinterpret_cast<const float4*>(pred32 + prow * P)[2 * i + 1];
+        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
+      } else {
+        uint4 u;
+        if (preload) { u = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3])); }
+        else u = reinterpret_cast<const uint4*>(pr)[i];
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
+        pv[0] = a.x; pv[1] = a.y; pv[2] = b.x; pv[3] = b.y; pv[4] = c2.x; pv[5] = c2.y; pv[6] = d2.x; pv[7] = d2.y;
+      }
       const float4 t0 = *reinterpret_cast<const float4*>(tgt + i * 8), t1 = *reinterpret_cast<const float4*>(tgt + i * 8 + 4);
       const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
@@ -304,19 +337,30 @@ mae_loss_kernel(const bf16* __restrict__ pred, const float* __restrict__ imgs, c
   } else {
     const float scale = dloss[0] * m * 2.f / (static_cast<float>(P) * mask_sum[0]);
     for (int i = threadIdx.x, k = 0; i < nvec; i += blockDim.x, ++k) {
-      uint4 u;
-      if (preload) { u = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3])); }
-      else u = reinterpret_cast<const uint4*>(pr)[i];
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
-      const float pv[8] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d2.x, d2.y};
+      float pv[8];
+      if (PF32) {
+        const float4 a = reinterpret_cast<const float4*>(pred32 + prow * P)[2 * i], b = reinterpret_cast<const float4*>(pred32 + prow * P)[2 * i + 1];
+        pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; pv[4] = b.x; pv[5] = b.y; pv[6] = b.z; pv[7] = b.w;
+      } else {
+        uint4 u;
+        if (preload) { u = k == 0 ? pu[0] : (k == 1 ? pu[1] : (k == 2 ? pu[2] : pu[3])); }
+        else u = reinterpret_cast<const uint4*>(pr)[i];
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d2 = unpack_bf16x2(u.w);
+        pv[0] = a.x; pv[1] = a.y; pv[2] = b.x; pv[3] = b.y; pv[4] = c2.x; pv[5] = c2.y; pv[6] = d2.x; pv[7] = d2.y;
+      }
       const float4 t0 = *reinterpret_cast<const float4*>(tgt + i * 8), t1 = *reinterpret_cast<const float4*>(tgt + i * 8 + 4);
       const float tv[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
       float g[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) g[k] = scale * (pv[k] - (tv[k] - mean) * inv_std);
-      uint4 o;
-      o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]); o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
-      reinterpret_cast<uint4*>(dpred + prow * P)[i] = o;
+      if (PF32) {
+        reinterpret_cast<float4*>(dpred32 + prow * P)[2 * i] = make_float4(g[0], g[1], g[2], g[3]);
+        reinterpret_cast<float4*>(dpred32 + prow * P)[2 * i + 1] = make_float4(g[4], g[5], g[6], g[7]);
+      } else {
+        uint4 o;
+        o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]); o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+        reinterpret_cast<uint4*>(dpred + prow * P)[i] = o;
+      }
     }
   }
 }
@@ -623,9 +667,19 @@ extern "C" int hct_patchify(const float* x, void* cols, const int64_t* patch_ids
   if (B <= 0) return HCT_OK;
   HctProfScope prof(static_cast<cudaStream_t>(s), HCT_PROF_PATCHIFY,
                     static_cast<double>(B) * rows_per_vol * C * p * p * p * (4.0 + 2.0));
-  patchify_kernel<<<static_cast<unsigned>(static_cast<long long>(B) * rows_per_vol), 128, 0, static_cast<cudaStream_t>(s)>>>(
-      x, static_cast<bf16*>(cols), reinterpret_cast<const long long*>(patch_ids), pos_idx_out, C, H, W, D, p, rows_per_vol);
+  patchify_kernel<false><<<static_cast<unsigned>(static_cast<long long>(B) * rows_per_vol), 128, 0, static_cast<cudaStream_t>(s)>>>(
+      x, cols, reinterpret_cast<const long long*>(patch_ids), pos_idx_out, C, H, W, D, p, rows_per_vol);
   return hct_check_launch("patchify_kernel");
+}
+
+extern "C" int hct_patchify_f32(const float* x, float* cols, const int64_t* patch_ids, int32_t* pos_idx_out, int32_t B,
+                                int32_t C, int32_t H, int32_t W, int32_t D, int32_t p, int32_t rows_per_vol, hct_stream_t s) {
+  HCT_REQUIRE(p > 0 && H % p == 0 && W % p == 0 && D % p == 0, "patchify_f32: volume %dx%dx%d not divisible by patch %d", H, W, D, p);
+  HCT_REQUIRE(rows_per_vol > 0 && rows_per_vol <= (H / p) * (W / p) * (D / p), "patchify_f32: rows_per_vol=%d", rows_per_vol);
+  if (B <= 0) return HCT_OK;
+  patchify_kernel<true><<<static_cast<unsigned>(static_cast<long long>(B) * rows_per_vol), 128, 0, static_cast<cudaStream_t>(s)>>>(
+      x, cols, reinterpret_cast<const long long*>(patch_ids), pos_idx_out, C, H, W, D, p, rows_per_vol);
+  return hct_check_launch("patchify_kernel<f32>");
 }
 
 extern "C" int hct_mask_indices(const float* noise, int64_t* ids_restore, int64_t* ids_keep, float* mask, int32_t N,
@@ -669,10 +723,19 @@ extern "C" int hct_decoder_assemble(const void* y, const int64_t* ids_restore, c
   HCT_REQUIRE(dim % 4 == 0, "decoder_assemble: dim %% 4");
   if (N <= 0) return HCT_OK;
   const long long rows = static_cast<long long>(N) * (L + 1);
-  decoder_assemble_kernel<<<grid_for(rows * (dim / 4), 256, hct_num_sms() * 8), 256, 0, static_cast<cudaStream_t>(s)>>>(
-      static_cast<const bf16*>(y), reinterpret_cast<const long long*>(ids_restore), mask_token, dec_cls, dec_pos, out, L,
-      keep, dim, rows);
+  decoder_assemble_kernel<false><<<grid_for(rows * (dim / 4), 256, hct_num_sms() * 8), 256, 0, static_cast<cudaStream_t>(s)>>>(
+      y, reinterpret_cast<const long long*>(ids_restore), mask_token, dec_cls, dec_pos, out, L, keep, dim, rows);
   return hct_check_launch("decoder_assemble_kernel");
+}
+extern "C" int hct_decoder_assemble_f32(const float* y, const int64_t* ids_restore, const float* mask_token,
+                                        const float* dec_cls, const float* dec_pos, float* out, int32_t N, int32_t L,
+                                        int32_t keep, int32_t dim, hct_stream_t s) {
+  HCT_REQUIRE(dim % 4 == 0, "decoder_assemble_f32: dim %% 4");
+  if (N <= 0) return HCT_OK;
+  const long long rows = static_cast<long long>(N) * (L + 1);
+  decoder_assemble_kernel<true><<<grid_for(rows * (dim / 4), 256, hct_num_sms() * 8), 256, 0, static_cast<cudaStream_t>(s)>>>(
+      y, reinterpret_cast<const long long*>(ids_restore), mask_token, dec_cls, dec_pos, out, L, keep, dim, rows);
+  return hct_check_launch("decoder_assemble_kernel<f32>");
 }
 
 extern "C" int hct_decoder_assemble_bwd(const float* dout, const int64_t* ids_restore, void* dy, float* dmask_token,
@@ -684,10 +747,21 @@ extern "C" int hct_decoder_assemble_bwd(const float* dout, const int64_t* ids_re
   int threads = ((dim / 4 + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   long long grid = rows < 4LL * hct_num_sms() ? rows : 4LL * hct_num_sms();
-  decoder_assemble_bwd_kernel<<<static_cast<int>(grid), threads, 0, static_cast<cudaStream_t>(s)>>>(
-      dout, reinterpret_cast<const long long*>(ids_restore), static_cast<bf16*>(dy), dmask_token, ddec_cls, L, keep, dim,
-      rows);
+  decoder_assemble_bwd_kernel<false><<<static_cast<int>(grid), threads, 0, static_cast<cudaStream_t>(s)>>>(
+      dout, reinterpret_cast<const long long*>(ids_restore), dy, dmask_token, ddec_cls, L, keep, dim, rows);
   return hct_check_launch("decoder_assemble_bwd_kernel");
+}
+extern "C" int hct_decoder_assemble_bwd_f32(const float* dout, const int64_t* ids_restore, float* dy, float* dmask_token,
+                                            float* ddec_cls, int32_t N, int32_t L, int32_t keep, int32_t dim, hct_stream_t s) {
+  HCT_REQUIRE(dim % 4 == 0, "decoder_assemble_bwd_f32: dim %% 4");
+  if (N <= 0) return HCT_OK;
+  const long long rows = static_cast<long long>(N) * (L + 1);
+  int threads = ((dim / 4 + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  long long grid = rows < 4LL * hct_num_sms() ? rows : 4LL * hct_num_sms();
+  decoder_assemble_bwd_kernel<true><<<static_cast<int>(grid), threads, 0, static_cast<cudaStream_t>(s)>>>(
+      dout, reinterpret_cast<const long long*>(ids_restore), dy, dmask_token, ddec_cls, L, keep, dim, rows);
+  return hct_check_launch("decoder_assemble_bwd_kernel<f32>");
 }
 
 static int loss_common_checks(int32_t C, int32_t H, int32_t W, int32_t D, int32_t p) {
@@ -698,63 +772,81 @@ static int loss_common_checks(int32_t C, int32_t H, int32_t W, int32_t D, int32_
 }
 
 // loss_out layout: [0] = sum(mask*mse), [1] = sum(mask), [2] = loss, [3..3+N*L) = per-patch workspace
-extern "C" int hct_mae_loss_fwd(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
-                                float* loss_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
-                                int32_t norm_pix, hct_stream_t s) {
+template <bool BWD, int PS, bool PF32>
+static void loss_set_smem() {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(mae_loss_kernel<BWD, PS, PF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+}
+template <bool PF32>
+static int mae_loss_fwd_impl(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask, float* loss_out,
+                             int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p, int32_t norm_pix, hct_stream_t s) {
   int rc = loss_common_checks(C, H, W, D, p);
   if (rc != HCT_OK) return rc;
   if (N <= 0) return HCT_OK;
   const int L = (H / p) * (W / p) * (D / p);
   const int P = C * p * p * p;
   cudaStream_t st = static_cast<cudaStream_t>(s);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(mae_loss_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(mae_loss_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(mae_loss_kernel<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(mae_loss_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  loss_set_smem<false, 0, PF32>(); loss_set_smem<false, 12, PF32>();
   float* per_patch = loss_out + 4;
   const unsigned grid = static_cast<unsigned>(static_cast<long long>(N) * L);
-  // algorithmic bytes as in SURVEY 8(d): pred (bf16) + target (fp32) of every patch row (an upper bound: unmasked rows are skipped)
-  HctProfScope prof(st, HCT_PROF_LOSS, static_cast<double>(N) * L * P * (2.0 + 4.0));
+  // algorithmic bytes as in SURVEY 8(d): pred + target (fp32) of every patch row (an upper bound: unmasked rows are skipped)
+  HctProfScope prof(st, HCT_PROF_LOSS, static_cast<double>(N) * L * P * ((PF32 ? 4.0 : 2.0) + 4.0));
   if (p == 12)
-    mae_loss_kernel<false, 12><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr,
-                                                                      nullptr, nullptr, L, C, H, W, D, p, norm_pix, pred_prefix_rows);
+    mae_loss_kernel<false, 12, PF32><<<grid, 256, P * sizeof(float), st>>>(pred, imgs, mask, per_patch, nullptr, nullptr, nullptr, L, C,
+                                                                           H, W, D, p, norm_pix, pred_prefix_rows);
   else
-    mae_loss_kernel<false, 0><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, per_patch, nullptr,
-                                                                     nullptr, nullptr, L, C, H, W, D, p, norm_pix, pred_prefix_rows);
+    mae_loss_kernel<false, 0, PF32><<<grid, 256, P * sizeof(float), st>>>(pred, imgs, mask, per_patch, nullptr, nullptr, nullptr, L, C,
+                                                                          H, W, D, p, norm_pix, pred_prefix_rows);
   rc = hct_check_launch("mae_loss_kernel<fwd>");
   if (rc != HCT_OK) return rc;
   loss_reduce_kernel<<<1, 1024, 0, st>>>(per_patch, mask, loss_out, static_cast<long long>(N) * L);
   return hct_check_launch("loss_reduce_kernel");
 }
-
-extern "C" int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
-                                const float* dloss, const float* mask_sum, void* dpred, int32_t N, int32_t C, int32_t H,
-                                int32_t W, int32_t D, int32_t p, int32_t norm_pix, hct_stream_t s) {
+template <bool PF32>
+static int mae_loss_bwd_impl(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask, const float* dloss,
+                             const float* mask_sum, void* dpred, int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
+                             int32_t norm_pix, hct_stream_t s) {
   int rc = loss_common_checks(C, H, W, D, p);
   if (rc != HCT_OK) return rc;
   if (N <= 0) return HCT_OK;
   const int L = (H / p) * (W / p) * (D / p);
   const int P = C * p * p * p;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(mae_loss_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(mae_loss_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  loss_set_smem<true, 0, PF32>(); loss_set_smem<true, 12, PF32>();
   const unsigned grid = static_cast<unsigned>(static_cast<long long>(N) * L);
   cudaStream_t st = static_cast<cudaStream_t>(s);
-  HctProfScope prof(st, HCT_PROF_LOSS, static_cast<double>(N) * L * P * (2.0 + 4.0 + 2.0));      // + dpred out
+  HctProfScope prof(st, HCT_PROF_LOSS, static_cast<double>(N) * L * P * (2.0 * (PF32 ? 4.0 : 2.0) + 4.0));      // + dpred out
   if (p == 12)
-    mae_loss_kernel<true, 12><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss, mask_sum,
-                                                                     static_cast<bf16*>(dpred), L, C, H, W, D, p, norm_pix, pred_prefix_rows);
+    mae_loss_kernel<true, 12, PF32><<<grid, 256, P * sizeof(float), st>>>(pred, imgs, mask, nullptr, dloss, mask_sum, dpred, L, C, H, W,
+                                                                          D, p, norm_pix, pred_prefix_rows);
   else
-    mae_loss_kernel<true, 0><<<grid, 256, P * sizeof(float), st>>>(static_cast<const bf16*>(pred), imgs, mask, nullptr, dloss, mask_sum,
-                                                                    static_cast<bf16*>(dpred), L, C, H, W, D, p, norm_pix, pred_prefix_rows);
+    mae_loss_kernel<true, 0, PF32><<<grid, 256, P * sizeof(float), st>>>(pred, imgs, mask, nullptr, dloss, mask_sum, dpred, L, C, H, W,
+                                                                         D, p, norm_pix, pred_prefix_rows);
   return hct_check_launch("mae_loss_kernel<bwd>");
+}
+
+extern "C" int hct_mae_loss_fwd(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                                float* loss_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
+                                int32_t norm_pix, hct_stream_t s) {
+  return mae_loss_fwd_impl<false>(pred, pred_prefix_rows, imgs, mask, loss_out, N, C, H, W, D, p, norm_pix, s);
+}
+extern "C" int hct_mae_loss_bwd(const void* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                                const float* dloss, const float* mask_sum, void* dpred, int32_t N, int32_t C, int32_t H,
+                                int32_t W, int32_t D, int32_t p, int32_t norm_pix, hct_stream_t s) {
+  return mae_loss_bwd_impl<false>(pred, pred_prefix_rows, imgs, mask, dloss, mask_sum, dpred, N, C, H, W, D, p, norm_pix, s);
+}
+/* fp32 mode: prediction rows (and their gradient) are fp32 */
+extern "C" int hct_mae_loss_fwd_f32(const float* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                                    float* loss_out, int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p,
+                                    int32_t norm_pix, hct_stream_t s) {
+  return mae_loss_fwd_impl<true>(pred, pred_prefix_rows, imgs, mask, loss_out, N, C, H, W, D, p, norm_pix, s);
+}
+extern "C" int hct_mae_loss_bwd_f32(const float* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                                    const float* dloss, const float* mask_sum, float* dpred, int32_t N, int32_t C, int32_t H,
+                                    int32_t W, int32_t D, int32_t p, int32_t norm_pix, hct_stream_t s) {
+  return mae_loss_bwd_impl<true>(pred, pred_prefix_rows, imgs, mask, dloss, mask_sum, dpred, N, C, H, W, D, p, norm_pix, s);
 }
 
 extern "C" int hct_flip_shift(const void* in, int32_t in_f16, float* out, const uint8_t* flip_bits, const float* offsets,

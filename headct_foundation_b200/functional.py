@@ -246,6 +246,198 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, mean, rstd
 
 
 # --------------------------------------------------------------------------------------------
+# Precision switch.  "bf16" (default) = what the reference does under autocast (--use_amp; we use bf16 where it uses fp16 +
+# GradScaler); "fp32" = the reference with use_amp off (engine_pretrain_mae.py:57): fp32 activations, exact-erf GELU, fp32
+# attention, GEMMs through the 3-term bf16 split (include/hct_b200.h, "fp32 mode").  The mode is read when a node's forward
+# runs and remembered for its backward.  Covered: EmbedFn, BlockFn (without LoRA), LayerNormFn, LinearFn, AttentionFn,
+# DecoderAssembleFn, MaeLossFn -- the MAE and ViT trunks; the DINO head / loss and the downstream heads keep bf16 operands.
+# --------------------------------------------------------------------------------------------
+_PRECISION = "bf16"
+
+
+def set_precision(mode: str) -> None:
+    global _PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    _PRECISION = mode
+
+
+def get_precision() -> str:
+    return _PRECISION
+
+
+class precision:
+    """with HF.precision("fp32"): ...  -- scoped precision switch."""
+
+    def __init__(self, mode: str):
+        self.mode, self.prev = mode, None
+
+    def __enter__(self):
+        self.prev = _PRECISION
+        set_precision(self.mode)
+        return self
+
+    def __exit__(self, *a):
+        set_precision(self.prev)
+
+
+def _fp32() -> bool:
+    return _PRECISION == "fp32"
+
+
+def _as_f32(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype == F32:
+        return x.contiguous()
+    return cast_f32(x) if x.dtype == BF16 else x.float().contiguous()
+
+
+def split3(x: torch.Tensor, *, role_b: bool, stack: bool, groups: int = 1, src_rows_per_group: int = 0, src_row_off: int = 0,
+           rows_per_group: int = 0) -> torch.Tensor:
+    """fp32 [rows, cols] (optionally a per-group row window of a larger matrix) -> its 3-term bf16 form
+    ([rows, 3 cols] or [3 rows, cols]); see hct_split3_bf16."""
+    cols = x.shape[-1]
+    if rows_per_group == 0:
+        rows_per_group = src_rows_per_group = x.numel() // cols
+    rows = groups * rows_per_group
+    out = torch.empty((3 * rows, cols) if stack else (rows, 3 * cols), dtype=BF16, device=x.device)
+    call("hct_split3_bf16", x.data_ptr(), cols, src_rows_per_group, src_row_off, rows_per_group, out.data_ptr(), rows, cols,
+         int(role_b), int(stack), stream_ptr(x.device))
+    return out
+
+
+_W3_ATTR = "_hct_split3"        # {stack: (data_ptr, version, tensor)} on the parameter
+
+
+def w_split3(p: torch.Tensor, stack: bool) -> torch.Tensor:
+    """3-term form of a weight [N, K] in the B role, cached on (data_ptr, version): [N, 3K] (forward, K-major) or
+    [3N, K] (dgrad: the weight as stored is the MN-major B operand, contraction over its rows)."""
+    _require_cuda(p, "weight")
+    cache = getattr(p, _W3_ATTR, None)
+    if cache is None:
+        cache = {}
+        setattr(p, _W3_ATTR, cache)
+    hit = cache.get(stack)
+    if hit is not None and hit[0] == p.data_ptr() and hit[1] == p._version:
+        return hit[2]
+    w = p.detach()
+    w2 = w.reshape(w.shape[0], -1).contiguous()
+    t = split3(w2, role_b=True, stack=stack)
+    cache[stack] = (p.data_ptr(), p._version, t)
+    return t
+
+
+def linear_fwd32(x32: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, epi: int = EPI_F32,
+                 out: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
+                 pos_idx: Optional[torch.Tensor] = None, rows_in: int = 0, rows_out: int = 0, row_off: int = 0,
+                 out_rows: Optional[int] = None) -> torch.Tensor:
+    """fp32 y[M,N] = x32[M,K] @ w[N,K]^T + bias (epilogues EPI_F32 / EPI_RES_F32 / EPI_POS_F32)."""
+    M, K = x32.shape
+    N = w.shape[0]
+    A = split3(x32, role_b=False, stack=False)                # [M, 3K]
+    Bw = w_split3(w, False)                                    # [N, 3K]
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else M, N), dtype=F32, device=x32.device)
+    gemm(A, Bw, M=M, N=N, K=3 * K, lda=3 * K, ldb=3 * K, out=out, ldo=N, epi=epi, bias=bias, res=res, ldres=N, pos=pos,
+         ldpos=N, pos_idx=pos_idx, rows_in=rows_in, rows_out=rows_out, row_off=row_off)
+    return out
+
+
+def linear_dgrad32(dy32: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """fp32 dx[M,K] = dy32[M,N] @ w[N,K]."""
+    M, N = dy32.shape
+    Bw = w_split3(w, True)                                     # [3N, K]
+    K = Bw.shape[1]
+    A = split3(dy32, role_b=False, stack=False)                # [M, 3N]
+    out = torch.empty((M, K), dtype=F32, device=dy32.device)
+    gemm(A, Bw, M=M, N=K, K=3 * N, lda=3 * N, ldb=K, b_mn=True, out=out, ldo=K, epi=EPI_F32)
+    return out
+
+
+def linear_wgrad32(dy32: torch.Tensor, x32: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 dW[N,K] = dy32[M,N]^T @ x32[M,K] (both operands MN-major, terms stacked along the contraction = rows)."""
+    M, N = dy32.shape
+    K = x32.shape[1]
+    A = split3(dy32, role_b=False, stack=True)                 # [3M, N]
+    Bx = split3(x32, role_b=True, stack=True)                  # [3M, K]
+    if out is None:
+        out = torch.zeros((N, K), dtype=F32, device=dy32.device)
+    gemm(A, Bx, M=N, N=K, K=3 * M, lda=N, ldb=K, a_mn=True, b_mn=True, out=out, ldo=K, epi=EPI_ATOMIC_F32)
+    return out
+
+
+def gelu32(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    call("hct_gelu_f32", x.data_ptr(), y.data_ptr(), x.numel(), stream_ptr(x.device))
+    return y
+
+
+def gelu_bwd32_(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    call("hct_gelu_bwd_f32", dy.data_ptr(), pre.data_ptr(), dy.data_ptr(), dy.numel(), stream_ptr(dy.device))
+    return dy
+
+
+def _block_fwd32(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, heads, eps, need_grad):
+    B, S, D = x.shape
+    M = B * S
+    st = stream_ptr(x.device)
+    h1, mean1, rstd1 = layernorm_fwd(x, n1w, n1b, eps, False, need_grad)
+    qkv = linear_fwd32(h1.view(M, D), qkv_w, qkv_b)                                   # fp32 [M, 3D]
+    att = torch.empty((M, D), dtype=F32, device=x.device)
+    lse = torch.empty((B, heads, S), dtype=F32, device=x.device)
+    call("hct_attention_f32_fwd", qkv.data_ptr(), att.data_ptr(), lse.data_ptr(), B, S, heads, D // heads, st)
+    x2 = torch.empty_like(x)
+    linear_fwd32(att, proj_w, proj_b, epi=EPI_RES_F32, out=x2.view(M, D), res=x.view(M, D))
+    h2, mean2, rstd2 = layernorm_fwd(x2, n2w, n2b, eps, False, need_grad)
+    pre = linear_fwd32(h2.view(M, D), fc1_w, fc1_b)                                   # fp32 [M, F]
+    g = gelu32(pre)
+    x3 = torch.empty_like(x)
+    linear_fwd32(g, fc2_w, fc2_b, epi=EPI_RES_F32, out=x3.view(M, D), res=x2.view(M, D))
+    if need_grad:
+        ctx.save_for_backward(x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2, mean2, rstd2,
+                              pre, g)
+        ctx.heads = heads
+    return x3
+
+
+def _block_bwd32(ctx, dout):
+    (x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2, mean2, rstd2, pre, g) = ctx.saved_tensors
+    B, S, D = x.shape
+    M = B * S
+    heads = ctx.heads
+    F_ = pre.shape[1]
+    need = ctx.needs_input_grad
+    (N1W, N1B, QKVW, QKVB, PROJW, PROJB, N2W, N2B, FC1W, FC1B, FC2W, FC2B) = range(1, 13)
+    st = stream_ptr(x.device)
+    dout = _as_f32(dout)
+    d3 = dout.view(M, D)
+    dfc2_b = colsum(d3, D) if need[FC2B] else None
+    dfc2_w = linear_wgrad32(d3, g) if need[FC2W] else None
+    da = gelu_bwd32_(linear_dgrad32(d3, fc2_w), pre)                                  # [M, F]
+    dfc1_b = colsum(da, F_) if need[FC1B] else None
+    dfc1_w = linear_wgrad32(da, h2.view(M, D)) if need[FC1W] else None
+    dh2 = linear_dgrad32(da, fc1_w)
+    del da
+    dx2, _, dn2w, dn2b = layernorm_bwd(dh2, x2, n2w, mean2, rstd2, dout, False)
+    dx2m = dx2.view(M, D)
+    dproj_b = colsum(dx2m, D) if need[PROJB] else None
+    dproj_w = linear_wgrad32(dx2m, att) if need[PROJW] else None
+    datt = linear_dgrad32(dx2m, proj_w)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, heads, S), dtype=F32, device=x.device)
+    call("hct_attention_f32_bwd", qkv.data_ptr(), att.data_ptr(), datt.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+         delta.data_ptr(), B, S, heads, D // heads, st)
+    dqkv_w = linear_wgrad32(dqkv, h1.view(M, D)) if need[QKVW] else None
+    dqkv_b = colsum(dqkv, 3 * D) if need[QKVB] else None
+    dh1 = linear_dgrad32(dqkv, qkv_w)
+    dx, _, dn1w, dn1b = layernorm_bwd(dh1, x, n1w, mean1, rstd1, dx2, False)
+
+    def opt(i, t):
+        return t if need[i] else None
+    return (dx, opt(N1W, dn1w), opt(N1B, dn1b), dqkv_w, dqkv_b, dproj_w, dproj_b, opt(N2W, dn2w), opt(N2B, dn2b), dfc1_w,
+            dfc1_b, dfc2_w, dfc2_b, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------
 # a6: transformer block  (attentionblock.py:96-99)
 # --------------------------------------------------------------------------------------------
 class BlockFn(torch.autograd.Function):
@@ -270,6 +462,13 @@ class BlockFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:17])
         st = stream_ptr(dev)
         lora = lqA is not None
+        ctx.fp32 = _fp32()
+        if ctx.fp32:
+            if lora:
+                raise NotImplementedError("fp32 mode does not cover the LoRA adapters (downstream fine-tuning runs under AMP)")
+            ctx.xdtype = xdtype
+            return _block_fwd32(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, heads, eps,
+                                need_grad)
 
         h1, mean1, rstd1 = layernorm_fwd(x, n1w, n1b, eps, True, need_grad)
         qkv = linear_fwd(h1.view(M, D), qkv_w, qkv_b)                                   # [M, 3D] bf16
@@ -303,6 +502,9 @@ class BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.fp32:
+            grads = _block_bwd32(ctx, dout)
+            return ((grads[0] if ctx.xdtype == F32 else grads[0].to(ctx.xdtype)),) + grads[1:]
         (x, n1w, qkv_w, proj_w, n2w, fc1_w, fc2_w, h1, mean1, rstd1, qkv, att, lse, x2, h2, mean2, rstd2, a,
          g, lqA, lqB, lvA, lvB, tq, tv) = ctx.saved_tensors
         B, S, D = x.shape
@@ -394,6 +596,16 @@ class AttentionFn(torch.autograd.Function):
     def forward(ctx, qkv, heads):
         B, S, D3 = qkv.shape
         D = D3 // 3
+        ctx.fp32 = _fp32()
+        if ctx.fp32:
+            qkv = _as_f32(qkv)
+            out = torch.empty((B, S, D), dtype=F32, device=qkv.device)
+            lse = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
+            call("hct_attention_f32_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, heads, D // heads,
+                 stream_ptr(qkv.device))
+            ctx.save_for_backward(qkv, out, lse)
+            ctx.heads = heads
+            return out
         qkv = qkv.contiguous()
         if qkv.dtype != BF16:
             qkv = cast_bf16(qkv.float())
@@ -410,6 +622,13 @@ class AttentionFn(torch.autograd.Function):
         qkv, out, lse = ctx.saved_tensors
         B, S, D3 = qkv.shape
         D, heads = D3 // 3, ctx.heads
+        if ctx.fp32:
+            dout = _as_f32(dout)
+            dqkv = torch.empty_like(qkv)
+            delta = torch.empty((B, heads, S), dtype=F32, device=qkv.device)
+            call("hct_attention_f32_bwd", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                 delta.data_ptr(), B, S, heads, D // heads, stream_ptr(qkv.device))
+            return dqkv, None
         dout = dout.contiguous()
         if dout.dtype != BF16:
             dout = cast_bf16(dout.float())
@@ -596,13 +815,26 @@ class EmbedFn(torch.autograd.Function):
         S = P + n
         dev = vol.device
         st = stream_ptr(dev)
-        cols = torch.empty((B * n, K), dtype=BF16, device=dev)
+        ctx.fp32 = _fp32()
+        has_pos = pos is not None
         pos_idx = torch.empty((B * n,), dtype=torch.int32, device=dev)
+        out = torch.empty((B, S, E), dtype=F32, device=dev)
+        if ctx.fp32:
+            cols = torch.empty((B * n, K), dtype=F32, device=dev)
+            call("hct_patchify_f32", vol.data_ptr(), cols.data_ptr(), ptr(ids_keep), pos_idx.data_ptr(), B, Cin, H, W, Dd,
+                 patch, n, st)
+            linear_fwd32(cols, conv_w, conv_b, epi=EPI_POS_F32 if has_pos else EPI_F32, out=out, pos=pos, pos_idx=pos_idx if has_pos else None,
+                         rows_in=n, rows_out=S, row_off=P)
+            if P:
+                call("hct_broadcast_rows", prefix.data_ptr(), out.data_ptr(), B, P, S, 0, E, st)
+            ctx.save_for_backward(cols, pos_idx)
+            ctx.dims = (B, n, S, P, E, K, L, ids_keep is not None, has_pos, tuple(conv_w.shape),
+                        None if pos is None else tuple(pos.shape), None if prefix is None else tuple(prefix.shape))
+            return out
+        cols = torch.empty((B * n, K), dtype=BF16, device=dev)
         call("hct_patchify", vol.data_ptr(), cols.data_ptr(), ptr(ids_keep), pos_idx.data_ptr(), B, Cin, H, W, Dd,
              patch, n, st)
-        out = torch.empty((B, S, E), dtype=F32, device=dev)
         wb = w16(conv_w).view(E, K)
-        has_pos = pos is not None
         if has_pos:
             gemm(cols, wb, M=B * n, N=E, K=K, lda=K, ldb=K, out=out, ldo=E, epi=EPI_POS_F32, bias=conv_b,
                  pos=pos, ldpos=E, pos_idx=pos_idx, rows_in=n, rows_out=S, row_off=P)
@@ -624,14 +856,21 @@ class EmbedFn(torch.autograd.Function):
         st = stream_ptr(dev)
         dout = dout.contiguous()
         take_bf16_shadow(dout)
-        dy = rows_to_bf16(dout, groups=B, src_rows_per_group=S, src_row_off=P, rows_per_group=n, dim=E)
-        dw = linear_wgrad(dy, cols).view(wshape) if ctx.needs_input_grad[1] else None
+        if ctx.fp32:
+            dout = _as_f32(dout)
+            dy = torch.empty((B * n, E), dtype=F32, device=dev)
+            call("hct_copy_rows_f32", dout.data_ptr(), E, S, P, dy.data_ptr(), B, n, E, st)
+            dw = linear_wgrad32(dy, cols).view(wshape) if ctx.needs_input_grad[1] else None
+        else:
+            dy = rows_to_bf16(dout, groups=B, src_rows_per_group=S, src_row_off=P, rows_per_group=n, dim=E)
+            dw = linear_wgrad(dy, cols).view(wshape) if ctx.needs_input_grad[1] else None
         db = colsum(dy, E) if ctx.needs_input_grad[2] else None
         dpos = None
         if has_pos and ctx.needs_input_grad[3]:
             dpos = torch.zeros(pshape, dtype=F32, device=dev)
             if has_ids:
-                call("hct_scatter_add_rows", dy.data_ptr(), pos_idx.data_ptr(), dpos.data_ptr(), B * n, E, st)
+                call("hct_scatter_add_rows_f32" if ctx.fp32 else "hct_scatter_add_rows", dy.data_ptr(), pos_idx.data_ptr(),
+                     dpos.data_ptr(), B * n, E, st)
             else:
                 call("hct_reduce_rows", dout.data_ptr(), dpos.data_ptr(), B, L, S, P, E, st)
         dprefix = None
@@ -689,7 +928,8 @@ class LayerNormFn(torch.autograd.Function):
         ctx.xdtype = x.dtype
         x = _f32_stream(x, "LayerNorm input")
         need = any(ctx.needs_input_grad[:3])
-        y, mean, rstd = layernorm_fwd(x, w, b, eps, out_bf16, need)
+        ctx.fp32 = _fp32()
+        y, mean, rstd = layernorm_fwd(x, w, b, eps, out_bf16 and not ctx.fp32, need)
         if need:
             ctx.save_for_backward(x, w, mean, rstd)
         return y
@@ -700,7 +940,7 @@ class LayerNormFn(torch.autograd.Function):
         dy = dy.contiguous()
         if dy.dtype not in (F32, BF16):
             dy = dy.float()
-        dx, dx16, dg, db = layernorm_bwd(dy, x, w, mean, rstd, None, True)
+        dx, dx16, dg, db = layernorm_bwd(dy, x, w, mean, rstd, None, not ctx.fp32)
         if ctx.xdtype == F32:
             put_bf16_shadow(dx, dx16)
         else:
@@ -723,6 +963,16 @@ class LinearFn(torch.autograd.Function):
         K = x.shape[-1]
         M = x.numel() // K
         N = w.shape[0]
+        ctx.fp32 = _fp32()
+        if ctx.fp32:
+            x32 = _as_f32(x).view(M, K)
+            need = any(ctx.needs_input_grad[:3])
+            pre = linear_fwd32(x32, w, b)
+            y = gelu32(pre) if gelu else pre
+            if need:
+                ctx.save_for_backward(x32, w, pre if gelu else None)
+            ctx.meta = (tuple(x.shape), x.dtype, b is not None, gelu)
+            return y.view(*x.shape[:-1], N)
         x = x.contiguous()
         x16 = x.view(M, K) if x.dtype == BF16 else rows_to_bf16(x, groups=1, src_rows_per_group=M, src_row_off=0,
                                                                 rows_per_group=M, dim=K)
@@ -741,6 +991,19 @@ class LinearFn(torch.autograd.Function):
         xshape, xdtype, has_bias, gelu = ctx.meta
         M, K = x16.shape
         N = w.shape[0]
+        if ctx.fp32:
+            take_bf16_shadow(dy)
+            dy32 = _as_f32(dy).view(M, N)
+            if gelu:
+                dy32 = gelu_bwd32_(dy32.clone() if dy32.data_ptr() == dy.data_ptr() else dy32, pre)
+            dw = linear_wgrad32(dy32, x16).view(w.shape) if ctx.needs_input_grad[1] else None
+            db = colsum(dy32, N) if (has_bias and ctx.needs_input_grad[2]) else None
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = linear_dgrad32(dy32, w).view(xshape)
+                if xdtype != F32:
+                    dx = dx.to(xdtype)
+            return dx, dw, db, None, None
         dy = dy.contiguous()
         dy2 = take_bf16_shadow(dy) if dy.dtype == F32 else None
         if dy2 is None:
@@ -775,9 +1038,12 @@ class DecoderAssembleFn(torch.autograd.Function):
         N, Sk, D = y16.shape
         L = ids_restore.shape[1]
         keep = Sk - 1
+        ctx.fp32 = y16.dtype == F32                     # fp32 mode hands in fp32 rows
         y16 = y16.contiguous()
+        if not ctx.fp32 and y16.dtype != BF16:
+            y16 = cast_bf16(y16.float())
         out = torch.empty((N, L + 1, D), dtype=F32, device=y16.device)
-        call("hct_decoder_assemble", y16.data_ptr(), ids_restore.data_ptr(), mask_token.data_ptr(), dec_cls.data_ptr(),
+        call("hct_decoder_assemble_f32" if ctx.fp32 else "hct_decoder_assemble", y16.data_ptr(), ids_restore.data_ptr(), mask_token.data_ptr(), dec_cls.data_ptr(),
              dec_pos.data_ptr(), out.data_ptr(), N, L, keep, D, stream_ptr(y16.device))
         ctx.save_for_backward(ids_restore)
         ctx.dims = (N, L, keep, D, tuple(mask_token.shape), tuple(dec_cls.shape))
@@ -790,10 +1056,10 @@ class DecoderAssembleFn(torch.autograd.Function):
         dout = dout.contiguous()
         take_bf16_shadow(dout)
         dev = dout.device
-        dy = torch.empty((N, keep + 1, D), dtype=BF16, device=dev)
+        dy = torch.empty((N, keep + 1, D), dtype=F32 if ctx.fp32 else BF16, device=dev)
         dmask = torch.zeros(mshape, dtype=F32, device=dev)
         dcls = torch.zeros(cshape, dtype=F32, device=dev)
-        call("hct_decoder_assemble_bwd", dout.data_ptr(), ids_restore.data_ptr(), dy.data_ptr(), dmask.data_ptr(),
+        call("hct_decoder_assemble_bwd_f32" if ctx.fp32 else "hct_decoder_assemble_bwd", dout.data_ptr(), ids_restore.data_ptr(), dy.data_ptr(), dmask.data_ptr(),
              dcls.data_ptr(), N, L, keep, D, stream_ptr(dev))
         return dy, None, dmask, dcls, None   # decoder_pos_embed is frozen (mae.py:92)
 
@@ -810,11 +1076,15 @@ class MaeLossFn(torch.autograd.Function):
         if imgs.dtype != F32:
             imgs = imgs.float()
         mask = mask.contiguous().float()
-        pred16 = pred.contiguous() if pred.dtype == BF16 else cast_bf16(pred.float())
+        ctx.fp32 = _fp32() and pred.dtype == F32         # fp32 mode: fp32 prediction rows are compared as they are
+        if ctx.fp32:
+            pred16 = pred.contiguous()
+        else:
+            pred16 = pred.contiguous() if pred.dtype == BF16 else cast_bf16(pred.float())
         N, C, H, W, D = imgs.shape
         L = mask.numel() // N
         ws = torch.empty((4 + N * L,), dtype=F32, device=pred.device)
-        call("hct_mae_loss_fwd", pred16.data_ptr(), int(prefix), imgs.data_ptr(), mask.data_ptr(), ws.data_ptr(), N, C,
+        call("hct_mae_loss_fwd_f32" if ctx.fp32 else "hct_mae_loss_fwd", pred16.data_ptr(), int(prefix), imgs.data_ptr(), mask.data_ptr(), ws.data_ptr(), N, C,
              H, W, D, patch, int(norm_pix), stream_ptr(pred.device))
         ctx.save_for_backward(pred16, imgs, mask, ws)
         ctx.meta = (patch, int(norm_pix), bool(inplace_grad) and pred.dtype == BF16, pred.dtype, tuple(pred.shape),
@@ -827,10 +1097,10 @@ class MaeLossFn(torch.autograd.Function):
         patch, norm_pix, inplace, pdtype, pshape, prefix = ctx.meta
         N, C, H, W, D = imgs.shape
         dloss = dloss.contiguous().float()
-        dpred = pred16 if inplace else torch.empty_like(pred16)
-        call("hct_mae_loss_bwd", pred16.data_ptr(), prefix, imgs.data_ptr(), mask.data_ptr(), dloss.data_ptr(),
+        dpred = pred16 if (inplace and not ctx.fp32) else torch.empty_like(pred16)
+        call("hct_mae_loss_bwd_f32" if ctx.fp32 else "hct_mae_loss_bwd", pred16.data_ptr(), prefix, imgs.data_ptr(), mask.data_ptr(), dloss.data_ptr(),
              ws[1:2].data_ptr(), dpred.data_ptr(), N, C, H, W, D, patch, norm_pix, stream_ptr(pred16.device))
-        if pdtype != BF16:
+        if pdtype != BF16 and not ctx.fp32:
             dpred = cast_f32(dpred)
         return dpred.view(pshape), None, None, None, None, None, None
 

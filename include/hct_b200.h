@@ -287,6 +287,48 @@ int hct_adjust_contrast(float* x, const float* gamma, int32_t* minmax_ws, int64_
                         hct_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * fp32 mode (the reference with --use_amp off: engine_pretrain_mae.py:57, engine_pretrain_dino.py:73,
+ * engine_downstream.py:84 -- autocast(enabled=use_amp)).  Activations stay fp32 between kernels.
+ * GEMMs run on hct_gemm_bf16 with every fp32 operand split into two bf16 terms (hi = bf16(x), lo = bf16(x - hi)) and the
+ * three leading products hi*hi + hi*lo + lo*hi obtained by concatenating the terms along the contraction dimension
+ * (K' = 3K): operand relative precision 2^-17, fp32 accumulation.
+ * ------------------------------------------------------------------------------------------- */
+/* dst (bf16) = the 3-term form of src (fp32 rows gathered as in hct_copy_rows_f32_to_bf16).  role_b = 0: terms
+ * (hi, hi, lo) for the A operand, 1: (hi, lo, hi) for the B operand.  stack = 0: dst [rows, 3*cols] (K-major operand, terms
+ * side by side), 1: dst [3*rows, cols] (MN-major operand, terms as row blocks). */
+int hct_split3_bf16(const float* src, int64_t src_ld, int64_t src_rows_per_group, int32_t src_row_off,
+                    int32_t rows_per_group, void* dst, int64_t rows, int32_t cols, int32_t role_b, int32_t stack,
+                    hct_stream_t stream);
+/* exact-erf GELU (monai MLPBlock act, nn.GELU(approximate='none')) and dy * gelu'(x), elementwise fp32 */
+int hct_gelu_f32(const float* x, float* y, int64_t n, hct_stream_t stream);
+int hct_gelu_bwd_f32(const float* dy, const float* x, float* dx, int64_t n, hct_stream_t stream);
+/* fp32 row gather (same row mapping as hct_copy_rows_f32_to_bf16) and fp32 row scatter-add */
+int hct_copy_rows_f32(const float* src, int64_t src_ld, int64_t src_rows_per_group, int32_t src_row_off, float* dst,
+                      int64_t groups, int32_t rows_per_group, int32_t cols, hct_stream_t stream);
+int hct_scatter_add_rows_f32(const float* src, const int32_t* idx, float* out, int64_t rows, int32_t dim, hct_stream_t stream);
+/* F.scaled_dot_product_attention (attentionblock.py:61) in fp32: qkv / dqkv fp32 [B,S,3,H,hd], out / dout fp32 [B,S,H*hd],
+ * lse / delta_ws fp32 [B,H,S].  hd in {32, 48, 64}. */
+int hct_attention_f32_fwd(const float* qkv, float* out, float* lse, int32_t B, int32_t S, int32_t H, int32_t hd,
+                          hct_stream_t stream);
+int hct_attention_f32_bwd(const float* qkv, const float* out, const float* dout, const float* lse, float* dqkv,
+                          float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd, hct_stream_t stream);
+/* fp32 variants of hct_patchify (cols fp32), hct_decoder_assemble(_bwd) (y / dy fp32) and hct_mae_loss_fwd/_bwd (pred /
+ * dpred fp32); argument meaning as for the bf16 entry points. */
+int hct_patchify_f32(const float* x, float* cols, const int64_t* patch_ids, int32_t* pos_idx_out, int32_t B, int32_t C,
+                     int32_t H, int32_t W, int32_t D, int32_t p, int32_t rows_per_vol, hct_stream_t stream);
+int hct_decoder_assemble_f32(const float* y, const int64_t* ids_restore, const float* mask_token, const float* dec_cls,
+                             const float* dec_pos, float* out, int32_t N, int32_t L, int32_t keep, int32_t dim,
+                             hct_stream_t stream);
+int hct_decoder_assemble_bwd_f32(const float* dout, const int64_t* ids_restore, float* dy, float* dmask_token,
+                                 float* ddec_cls, int32_t N, int32_t L, int32_t keep, int32_t dim, hct_stream_t stream);
+int hct_mae_loss_fwd_f32(const float* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask, float* loss_out,
+                         int32_t N, int32_t C, int32_t H, int32_t W, int32_t D, int32_t p, int32_t norm_pix,
+                         hct_stream_t stream);
+int hct_mae_loss_bwd_f32(const float* pred, int32_t pred_prefix_rows, const float* imgs, const float* mask,
+                         const float* dloss, const float* mask_sum, float* dpred, int32_t N, int32_t C, int32_t H,
+                         int32_t W, int32_t D, int32_t p, int32_t norm_pix, hct_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Train-step glue: per-parameter clip (misc.py:374-383) + AdamW
  * (optimizers.py:354-360) as one multi-tensor launch each.
  * table: int64 [n, 7] = {param_ptr, grad_ptr, exp_avg_ptr, exp_avg_sq_ptr, numel, param_bf16_shadow_ptr or 0,

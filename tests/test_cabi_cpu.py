@@ -94,8 +94,19 @@ def test_no_cpu_fallback_downstream_heads_and_graphs():
     assert L.hct_colnorm_stats(None, None, 8, 6, 1e-6, 0.1, None, None, None, None, None) == 1  # dim % 4
     assert L.hct_lora_shuffle(None, None, None, 0, 9, 2, 48, 0, None) == 0             # empty batch is a no-op
     opt = FusedAdamW(lin.parameters(), lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
-    lr, wd, bc1, bc2s = opt._hyper_values(opt.param_groups[0], 3)                      # what the captured launch reads
-    assert (lr, wd) == (1e-3, 0.05) and abs(bc1 - (1 - 0.9 ** 3)) < 1e-12 and abs(bc2s - (1 - 0.95 ** 3) ** 0.5) < 1e-12
+    lr, wd, bc1, bc2s, step = opt._hyper_values(opt.param_groups[0], 3)                # what the captured launch reads
+    assert (lr, wd, step) == (1e-3, 0.05, 3.0) and abs(bc1 - (1 - 0.9 ** 3)) < 1e-12 and abs(bc2s - (1 - 0.95 ** 3) ** 0.5) < 1e-12
+    # fp32-mode entry points validate their arguments without touching the device
+    assert L.hct_split3_bf16(None, 6, 1, 0, 1, None, 4, 6, 0, 0, None) == 1                # cols % 4
+    assert L.hct_attention_f32_fwd(None, None, None, 1, 8, 2, 40, None) == 3               # unsupported head dim
+    assert L.hct_gelu_f32(None, None, 0, None) == 0                                        # empty is a no-op
+    with pytest.raises(ValueError):
+        H.set_precision("fp64")
+    with H.precision("fp32"):
+        assert H.get_precision() == "fp32"
+        with pytest.raises(RuntimeError):
+            H.AttentionBlock(96, 192, 2)(torch.zeros(2, 9, 96))                            # fp32 mode has no CPU fallback either
+    assert H.get_precision() == "bf16"
 
 
 def test_product_never_imports_the_oracle():
