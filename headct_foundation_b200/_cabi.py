@@ -78,6 +78,7 @@ _SIGNATURES = {
     "hct_attention_set_tcgen05": [_I32],
     "hct_attention_set_merge_tail": [_I32],
     "hct_attention_set_dkdv32": [_I32],
+    "hct_attention_set_bwd3": [_I32],
     "hct_attention_trace": [C.c_void_p],
     "hct_crop_resize_area": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],
     "hct_adjust_contrast": [_P, _P, _P, _I64, _I64, _P],
@@ -136,6 +137,8 @@ def lib() -> C.CDLL:
             L.hct_gemm_set_cta_pair(0)
         if os.environ.get("HCT_ATTN_TCGEN05", "1") == "0":       # debugging aid: mma.sync attention only
             L.hct_attention_set_tcgen05(0)
+        if "HCT_ATTN_BWD3" in os.environ:                        # A/B: pipelined persistent backward on / off
+            L.hct_attention_set_bwd3(int(os.environ["HCT_ATTN_BWD3"] != "0"))
         _lib = L
     return _lib
 

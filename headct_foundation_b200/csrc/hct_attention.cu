@@ -566,12 +566,18 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
 int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
                          int H, int hd, int n_tiles, cudaStream_t st);
 // row kernel for the one row behind the last full tile in the backward (S = 128 k + 1; hct_attention_tail.cu)
+int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S, int H,
+                       int hd, int n_tiles, cudaStream_t st);
 bool hct_attention_bwd_tail_supported(int S, int hd, int r0);
 int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
                            int H, int hd, int r0, cudaStream_t st);
 // 0: mma.sync kernels only; 1: tcgen05, forward tail rows (S % 128 <= 32) on mma.sync; 2 (default): tcgen05 for every
 // forward tile, a single backward tail row (S % 128 == 1) on the row kernel; 3: tcgen05 for every tile, backward included
 static int g_attn_tc = 2;
+// 1: pipelined persistent backward (hct_attention_bwd3.cu: three score buffers, two softmax groups per SM);
+// 0: the two-CTA-per-SM kernels of hct_attention_sm100.cu
+static int g_attn_bwd3 = 0;
+extern "C" int hct_attention_set_bwd3(int enable) { g_attn_bwd3 = enable != 0; return HCT_OK; }
 extern "C" int hct_attention_set_tcgen05(int mode) { g_attn_tc = mode < 0 ? 0 : (mode > 3 ? 3 : mode); return HCT_OK; }
 
 extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t S, int32_t H, int32_t hd,
@@ -612,12 +618,15 @@ extern "C" int hct_attention_bwd(const void* qkv, const void* out, const void* d
   if (rc) return rc;
   if (g_attn_tc && (hd == 64 || hd == 48)) {
     const int full = S / 128, r0 = full * 128;
+    auto tc_bwd = g_attn_bwd3 ? hct_attention_bwd3 : hct_attention_bwd_tc;
     if (g_attn_tc != 3 && r0 < S && hct_attention_bwd_tail_supported(S, hd, r0)) {
-      rc = hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, full, st);
-      if (rc) return rc;
+      if (full > 0) {
+        rc = tc_bwd(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, full, st);
+        if (rc) return rc;
+      }
       return hct_attention_bwd_tail(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, r0, st);
     }
-    return hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, (S + 127) / 128, st);
+    return tc_bwd(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, (S + 127) / 128, st);
   }
   const bf16* q = static_cast<const bf16*>(qkv);
   const bf16* d = static_cast<const bf16*>(dout);

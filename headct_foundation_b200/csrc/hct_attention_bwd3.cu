@@ -1,0 +1,380 @@
+// Attention backward on tcgen05 / TMEM, pipelined variant ("bwd3"): one persistent CTA per SM that keeps THREE score
+// buffer pairs in tensor memory and TWO softmax warp groups busy.
+//
+// Why: the two-CTA-per-SM kernels of hct_attention_sm100.cu run one serial chain per CTA
+//     S/dP MMAs -> commit -> tcgen05.ld -> exp2 / dS -> tcgen05.st -> arrive -> dV/dK (dQ) MMAs -> next S/dP MMAs
+// of ~2500 cycles per 64-wide block (profiles/r01_attn_dkdv_timeline.txt) with the tensor pipe busy ~480 of them; the SM
+// therefore completes one block per ~1250 cycles.  Throughput tracks the score columns in flight and who waits for whom.
+// Here a CTA owns all 512 TMEM columns: accumulators [0,128) + 3 x (S 64 | dP 64).  The MMA warp runs up to three blocks
+// ahead with the S / dP MMAs (the tensor pipe executes in order, so a buffer is overwritten only after the accumulate MMAs
+// that read its bf16 operands), two groups of eight softmax warps take alternate blocks, and neither waits for the MMA
+// stages of its own block any more.  The CTA is persistent over (batch, head, 128-row tile) work items -- resident tiles
+// double-buffered, streamed tiles in a 6-deep TMA ring that runs across item boundaries -- so that prologue / epilogue of an
+// item (TMA round trip, accumulator drain) overlap the neighbouring items' work instead of being paid per CTA.
+//
+// One kernel template serves both passes (same chain, transposed roles):
+//   KV = true   rows (TMEM lanes) = keys:   resident K, V;  streamed Q_i, dO_i (64 queries)
+//               S^T = K Q_i^T, dP^T = V dO_i^T;  P^T = exp2(S^T c - lse[q]), dS^T = P^T (dP^T - delta[q]) written IN PLACE
+//               as bf16 pairs;  dV += P^T dO_i,  dK += dS^T Q_i      (A from TMEM, B = streamed tile read MN-major)
+//   KV = false  rows = queries:             resident Q, dO; streamed K_j, V_j (64 keys)
+//               S = Q K_j^T, dP = dO V_j^T;  dS = P (dP - delta[row]) in place;  dQ += dS K_j
+// Deterministic (no atomics).  Rows behind the last full 128-row tile are handled as in the two-kernel path
+// (hct_attention_tail.cu), a last streamed block with <= 16 valid columns is computed 16 wide.
+#include "../../include/hct_b200.h"
+#include "hct_tcgen05.cuh"
+
+namespace {
+using namespace hct_tc;
+
+constexpr int TILE = 128;
+constexpr int TILE_BYTES = TILE * 128;     // 128 rows x 64 bf16
+constexpr int HALF_BYTES = 64 * 128;       // 64 rows x 64 bf16
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int NSW = 16;                    // softmax warps: group = w >> 3, column half = (w >> 2) & 1, lane quarter = w & 3
+constexpr int W_PROD = 16, W_MMA = 17;
+constexpr int THREADS = 18 * 32;
+constexpr int STAGES = 6;                  // TMA ring of streamed 64-row tile pairs
+constexpr int NBUF = 3;                    // S / dP buffer pairs in tensor memory
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 128;              // [0,64): dV (dQ), [64,128): dK
+constexpr int SMEM_BYTES = 2 * 2 * TILE_BYTES + STAGES * 2 * HALF_BYTES + NSW * 512 + 1024 + 512;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int HD, bool KV>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
+                 const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO64,
+                 const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H,
+                 int n_tiles, int n_items, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sR = smem;                                   // [2 buffers][R1 | R2][128 rows][64]
+  uint8_t* sT1 = smem + 2 * 2 * TILE_BYTES;             // STAGES x [64 rows][64]
+  uint8_t* sT2 = sT1 + STAGES * HALF_BYTES;
+  float* sStat = reinterpret_cast<float*>(sT2 + STAGES * HALF_BYTES);       // [16 warps][2 slots][lse 32 | delta 32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + NSW * 512);
+  uint64_t *kv_full = bars /*[2]*/, *kv_empty = bars + 2 /*[2]*/, *ring_full = bars + 4 /*[STAGES]*/,
+           *ring_empty = bars + 4 + STAGES /*[STAGES]*/, *s_full = bars + 4 + 2 * STAGES /*[NBUF]*/,
+           *p_full = s_full + NBUF /*[NBUF]*/, *done = p_full + NBUF, *acc_empty = done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
+  const int D = H * HD;
+  const int nblk = (S + 63) / 64;                               // streamed 64-row blocks per item
+  const bool tail16 = S - (nblk - 1) * 64 <= 16;                // last block is computed 16 columns wide
+  const float sl2 = scale * LOG2E;
+  const int nmy = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total = nmy * nblk;                                 // blocks this CTA processes, numbered gb = n * nblk + i
+  // item n of this CTA -> (batch, head, row tile); tiles of one head are adjacent items (= neighbouring CTAs: L2 reuse)
+  auto item_coords = [&](int n, int& b, int& h, int& t) {
+    const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+    t = it % n_tiles;
+    h = (it / n_tiles) % H;
+    b = it / (n_tiles * H);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
+    mbar_init(done, 1); mbar_init(acc_empty, NSW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 64;     // KV: dV, dK.  !KV: dQ lives in acc2's place (see below)
+
+  if (warp == W_PROD) {
+    // ===================== TMA producer =====================
+    const bool leader = elect_one();
+    int gb = 0;
+    for (int n = 0; n < nmy; ++n) {
+      int b, h, t;
+      item_coords(n, b, h, t);
+      const int kb = n & 1;
+      mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1u);
+      if (leader) {
+        uint8_t* r1 = sR + kb * 2 * TILE_BYTES;
+        mbar_expect_tx(&kv_full[kb], 2 * TILE_BYTES);
+        if (KV) {
+          tma_load_2d(smem_u32(r1), &tmQKV128, &kv_full[kb], D + h * HD, b * S + t * TILE);                    // K
+          tma_load_2d(smem_u32(r1 + TILE_BYTES), &tmQKV128, &kv_full[kb], 2 * D + h * HD, b * S + t * TILE);   // V
+        } else {
+          tma_load_2d(smem_u32(r1), &tmQKV128, &kv_full[kb], h * HD, b * S + t * TILE);                        // Q
+          tma_load_2d(smem_u32(r1 + TILE_BYTES), &tmDO128, &kv_full[kb], h * HD, b * S + t * TILE);            // dO
+        }
+      }
+      __syncwarp();
+      for (int i = 0; i < nblk; ++i, ++gb) {
+        const int st = gb % STAGES;
+        mbar_wait(&ring_empty[st], ((gb / STAGES) & 1) ^ 1u);
+        if (leader) {
+          mbar_expect_tx(&ring_full[st], 2 * HALF_BYTES);
+          if (KV) {
+            tma_load_2d(smem_u32(sT1 + st * HALF_BYTES), &tmQKV64, &ring_full[st], h * HD, b * S + i * 64);    // Q_i
+            tma_load_2d(smem_u32(sT2 + st * HALF_BYTES), &tmDO64, &ring_full[st], h * HD, b * S + i * 64);     // dO_i
+          } else {
+            tma_load_2d(smem_u32(sT1 + st * HALF_BYTES), &tmQKV64, &ring_full[st], D + h * HD, b * S + i * 64);      // K_j
+            tma_load_2d(smem_u32(sT2 + st * HALF_BYTES), &tmQKV64, &ring_full[st], 2 * D + h * HD, b * S + i * 64);  // V_j
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    const uint32_t idesc_s = make_idesc_bf16(TILE, 64, false, false);
+    const uint32_t idesc_s16 = make_idesc_bf16(TILE, 16, false, false);
+    const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
+    auto issue_sdp = [&](int gbi) {                  // S / dP of block gbi into buffer gbi % NBUF
+      const int n = gbi / nblk, i = gbi - n * nblk;
+      const int kb = n & 1, st = gbi % STAGES, buf = gbi % NBUF;
+      if (i == 0) mbar_wait(&kv_full[kb], (n >> 1) & 1);
+      mbar_wait(&ring_full[st], (gbi / STAGES) & 1);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
+        const uint64_t dR1 = make_sdesc_sw128(smem_u32(sR + kb * 2 * TILE_BYTES), false, 0);
+        const uint64_t dR2 = make_sdesc_sw128(smem_u32(sR + kb * 2 * TILE_BYTES + TILE_BYTES), false, 0);
+        const uint64_t dT1 = make_sdesc_sw128(smem_u32(sT1 + st * HALF_BYTES), false, 0);
+        const uint64_t dT2 = make_sdesc_sw128(smem_u32(sT2 + st * HALF_BYTES), false, 0);
+        const uint32_t id = (i == nblk - 1 && tail16) ? idesc_s16 : idesc_s;
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {       // the two accumulate chains interleaved: consecutive MMAs independent
+          tc_mma(tS, dR1 + ks * 2, dT1 + ks * 2, id, ks > 0 ? 1u : 0u);
+          tc_mma(tdP, dR2 + ks * 2, dT2 + ks * 2, id, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[buf]);
+      }
+      __syncwarp();
+    };
+    int issued = 0;
+    for (int proc = 0; proc < total; ++proc) {
+      const int n = proc / nblk, i = proc - n * nblk;
+      // run ahead with S / dP: at most NBUF blocks in flight, and never beyond the NEXT item (two resident buffers)
+      while (issued < total && issued < proc + NBUF && issued / nblk <= n + 1) issue_sdp(issued++);
+      const int st = proc % STAGES, buf = proc % NBUF;
+      mbar_wait(&p_full[buf], (proc / NBUF) & 1);     // bf16 operands of block proc sit in TMEM (and its fp32 scores were read)
+      if (i == 0) mbar_wait(acc_empty, (n & 1) ^ 1u); // the previous item's accumulators have been drained
+      tc_fence_after();
+      if (leader) {
+        const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
+        const uint64_t dT1m = make_sdesc_sw128(smem_u32(sT1 + st * HALF_BYTES), true, HALF_BYTES);
+        const uint64_t dT2m = make_sdesc_sw128(smem_u32(sT2 + st * HALF_BYTES), true, HALF_BYTES);
+        const uint32_t acc = i > 0 ? 1u : 0u;
+        // k-step ks covers streamed rows [16 ks, 16 ks + 16): packed by column half ks / 2 at column 32 (ks / 2) + 8 (ks % 2)
+        if (i == nblk - 1 && tail16) {
+          if (KV) tc_mma_ts(tmem_acc1, tS, dT2m, idesc_g, acc);
+          tc_mma_ts(tmem_acc2, tdP, dT1m, idesc_g, acc);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (KV) tc_mma_ts(tmem_acc1, tS + (ks >> 1) * 32 + (ks & 1) * 8, dT2m + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+            tc_mma_ts(tmem_acc2, tdP + (ks >> 1) * 32 + (ks & 1) * 8, dT1m + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+          }
+        }
+        tc_commit(&ring_empty[st]);
+        if (i == nblk - 1) { tc_commit(done); tc_commit(&kv_empty[n & 1]); }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax-backward warps: one row (TMEM lane) per thread =====================
+    const int grp = warp >> 3, wg = (warp >> 2) & 1, q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    float* wstat = sStat + warp * 128;
+    int cur_item = 0;                                // next item whose accumulators this warp still has to drain
+
+    // accumulator drain of item m: the four warps of a lane quarter split the columns
+    auto drain = [&](int m) {
+      int b, h, t;
+      item_coords(m, b, h, t);
+      const int row = t * TILE + q * 32 + lane;
+      const bool row_ok = row < S;
+      const bool warp_active = t * TILE + q * 32 < S;
+      mbar_wait(done, m & 1);
+      tc_fence_after();
+      const int id4 = warp >> 2;                     // 0..3
+      if (warp_active && (KV || id4 < 2)) {
+        // KV: id4 0,1 -> dK halves, 2,3 -> dV halves.  !KV: id4 0,1 -> dQ halves
+        const bool second = KV ? (id4 >= 2) : false;
+        const uint32_t src = second ? tmem_acc1 : tmem_acc2;
+        const int c_begin = (id4 & 1) * (HD / 2);
+        bf16* dst = dqkv + (static_cast<long long>(b) * S + row) * (3LL * D) + h * HD + (KV ? (second ? 2 * D : D) : 0);
+        const float sc = second ? 1.0f : scale;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_begin + HD / 2; c0 += 8) {
+          uint32_t o[8];
+          tmem_ld8(src + lane_off + c0, o);
+          if (row_ok) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[0]) * sc, __uint_as_float(o[1]) * sc);
+            u.y = pack_bf16x2(__uint_as_float(o[2]) * sc, __uint_as_float(o[3]) * sc);
+            u.z = pack_bf16x2(__uint_as_float(o[4]) * sc, __uint_as_float(o[5]) * sc);
+            u.w = pack_bf16x2(__uint_as_float(o[6]) * sc, __uint_as_float(o[7]) * sc);
+            *reinterpret_cast<uint4*>(dst + c0) = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
+    };
+
+    // statistics of a block: KV -> per streamed column (queries of block i): lse * log2e | delta for this warp's 32 columns;
+    //                        !KV -> per row (this thread's query row of the item's tile)
+    auto load_stats = [&](int gbi, float& a, float& d) {
+      const int n = gbi / nblk, i = gbi - n * nblk;
+      int b, h, t;
+      item_coords(n, b, h, t);
+      const long long base = (static_cast<long long>(b) * H + h) * S;
+      const int r = KV ? (i * 64 + wg * 32 + lane) : (t * TILE + q * 32 + lane);
+      if (r < S) { a = lse[base + r] * LOG2E; d = delta[base + r]; } else { a = 0.f; d = 0.f; }
+    };
+    float st_a = 0.f, st_d = 0.f;
+    if (grp < total) load_stats(grp, st_a, st_d);
+    int cnt = 0;
+    for (int gb = grp; gb < total; gb += 2, ++cnt) {
+      const int n = gb / nblk, i = gb - n * nblk;
+      while (cur_item < n) { drain(cur_item); ++cur_item; }
+      int b, h, t;
+      item_coords(n, b, h, t);
+      const bool warp_active = t * TILE + q * 32 < S;        // warps without a valid row only keep the barriers moving
+      const int buf = gb % NBUF;
+      const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
+      float* stat = wstat + (cnt & 1) * 64;
+      const float row_a = st_a, row_d = st_d;                // !KV: this thread's row statistics
+      if (KV) {
+        stat[lane] = st_a;
+        stat[32 + lane] = st_d;
+        __syncwarp();
+      }
+      if (gb + 2 < total) load_stats(gb + 2, st_a, st_d);    // one own block ahead: the global-load latency stays off the chain
+      mbar_wait(&s_full[buf], (gb / NBUF) & 1);
+      tc_fence_after();
+      const int ncol = min(64, S - i * 64);                  // valid streamed columns in this block
+      const bool t16 = (i == nblk - 1) && tail16;
+      if (warp_active && !(t16 && wg == 1)) {
+        uint32_t pk[16], dk[16];
+        if (t16) {
+          uint32_t sv[16], dv[16];
+          tmem_ld16(tS + lane_off, sv);
+          tmem_ld16(tdP + lane_off, dv);
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float a0 = KV ? stat[e] : row_a, a1 = KV ? stat[e + 1] : row_a;
+            const float d0 = KV ? stat[32 + e] : row_d, d1 = KV ? stat[32 + e + 1] : row_d;
+            const float p0 = e < ncol ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -a0)) : 0.f;
+            const float p1 = e + 1 < ncol ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -a1)) : 0.f;
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - d0), p1 * (__uint_as_float(dv[e + 1]) - d1));
+          }
+#pragma unroll
+          for (int e = 8; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
+        } else {
+          uint32_t sv[32], dv[32];
+          tmem_ld32_issue(tS + lane_off + wg * 32, sv);
+          tmem_ld32_issue(tdP + lane_off + wg * 32, dv);
+          tmem_ld_wait();
+          const int lim = ncol - wg * 32;                    // valid columns in this warp's half
+          if (lim < 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e >= lim) sv[e] = 0xff800000u;             // exp2(-inf) = 0: P and dS vanish outside the problem
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            float4 ls, dl;
+            if (KV) {
+              ls = *reinterpret_cast<const float4*>(stat + e);
+              dl = *reinterpret_cast<const float4*>(stat + 32 + e);
+            } else {
+              ls = make_float4(row_a, row_a, row_a, row_a);
+              dl = make_float4(row_d, row_d, row_d, row_d);
+            }
+            const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x));
+            const float p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y));
+            const float p2 = ex2f(fmaf(__uint_as_float(sv[e + 2]), sl2, -ls.z));
+            const float p3 = ex2f(fmaf(__uint_as_float(sv[e + 3]), sl2, -ls.w));
+            if (KV) {
+              pk[e >> 1] = pack_bf16x2(p0, p1);
+              pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
+            dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) - dl.z), p3 * (__uint_as_float(dv[e + 3]) - dl.w));
+          }
+        }
+        // in place: this thread's own lanes, inside the fp32 columns it has just read
+        if (KV) tmem_st16(tS + lane_off + wg * 32, pk);
+        tmem_st16(tdP + lane_off + wg * 32, dk);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[buf]);
+    }
+    while (cur_item < nmy) { drain(cur_item); ++cur_item; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+template <int HD, bool KV>
+int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensorMap& q64, const CUtensorMap& do64,
+               const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, int n_tiles, cudaStream_t st) {
+  static bool cfg = false;
+  auto kernel = attn_bwd3_kernel<HD, KV>;
+  if (!cfg) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) { hct_set_error("cudaFuncSetAttribute(attn_bwd3): %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
+    cfg = true;
+  }
+  const long long items = static_cast<long long>(B) * H * n_tiles;
+  if (items <= 0) return HCT_OK;
+  const int sms = hct_num_sms();
+  const int grid = static_cast<int>(items < sms ? items : sms);
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  kernel<<<grid, THREADS, SMEM_BYTES, st>>>(q128, do128, q64, do64, lse, delta, dqkv, S, H, n_tiles, static_cast<int>(items), scale);
+  return hct_check_launch(KV ? "attn_bwd3_kernel<dK/dV>" : "attn_bwd3_kernel<dQ>");
+}
+
+}  // namespace
+
+// n_tiles full 128-row tiles per (batch, head) on tcgen05 (rows behind them: hct_attention_tail.cu)
+int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S, int H,
+                       int hd, int n_tiles, cudaStream_t st) {
+  CUtensorMap q128, q64, do128, do64;
+  const long long D = static_cast<long long>(H) * hd, D3 = 3 * D, rows = static_cast<long long>(B) * S;
+  HCT_REQUIRE(static_cast<long long>(B) * H * n_tiles <= 2147483647LL, "attention_bwd3: too many work items");
+  int rc = hct_make_tmap_bf16_2d(&q128, qkv, D3, rows, D3, 64, TILE); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&q64, qkv, D3, rows, D3, 64, 64); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&do128, dout, D, rows, D, 64, TILE); if (rc) return rc;
+  rc = hct_make_tmap_bf16_2d(&do64, dout, D, rows, D, 64, 64); if (rc) return rc;
+  bf16* dq = static_cast<bf16*>(dqkv);
+  if (hd == 64) {
+    rc = launch_one<64, true>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st); if (rc) return rc;
+    return launch_one<64, false>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st);
+  }
+  rc = launch_one<48, true>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st); if (rc) return rc;
+  return launch_one<48, false>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st);
+}

@@ -205,6 +205,26 @@ def test_attention_bwd_pipelined_dkdv_variant(cuda, HF, B, S, H, hd):
         lib().hct_attention_set_dkdv32(0)
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (3, 65, 2, 48), (2, 260, 2, 48),
+                                      (1, 136, 3, 64), (3, 17, 3, 64), (1, 1, 2, 64), (2, 230, 4, 48), (2, 200, 3, 64),
+                                      (1, 300, 2, 48), (2, 144, 2, 64), (1, 128, 2, 64), (2, 256, 2, 48), (1, 385, 1, 64),
+                                      # many more work items than SMs: every CTA walks several (batch, head, tile) items,
+                                      # with 1, 2, 3 and 9 streamed blocks per item (ring / buffer phases wrap around)
+                                      (40, 129, 12, 64), (12, 513, 16, 48), (90, 40, 4, 64), (70, 100, 3, 48), (9, 517, 12, 64)])
+def test_attention_bwd_pipelined_persistent(cuda, HF, B, S, H, hd, mode):
+    """hct_attention_set_bwd3(1): one persistent CTA per SM, three score-buffer pairs in tensor memory, two softmax groups
+    (csrc/hct_attention_bwd3.cu) against the fp32 torch reference, with and without the row kernel for the tail rows."""
+    from headct_foundation_b200._cabi import lib
+    lib().hct_attention_set_bwd3(1)
+    lib().hct_attention_set_tcgen05(mode)
+    try:
+        _attention_case(cuda, B, S, H, hd)
+    finally:
+        lib().hct_attention_set_bwd3(0)
+        lib().hct_attention_set_tcgen05(2)
+
+
 def _attention_case(cuda, B, S, H, hd):
     from headct_foundation_b200._cabi import call, stream_ptr
     D = H * hd

@@ -52,3 +52,16 @@ for name, (B, S, H, hd) in {"dec": (256, 513, 16, 48), "enc": (256, 129, 12, 64)
                             dqkv.data_ptr(), delta.data_ptr(), B, S, H, hd, st))
     print(f"{name}: bwd {b:.3f} ms")
 lib().hct_attention_set_merge_tail(1)
+
+print("-- backward on the pipelined persistent kernels (hct_attention_set_bwd3(1))")
+lib().hct_attention_set_bwd3(1)
+for name, (B, S, H, hd) in {"dec": (256, 513, 16, 48), "enc": (256, 129, 12, 64), "vit": (64, 517, 12, 64)}.items():
+    D = H * hd
+    qkv = torch.randn(B, S, 3 * D, device=dev).bfloat16(); out = torch.empty(B, S, D, device=dev, dtype=torch.bfloat16)
+    do = torch.randn(B, S, D, device=dev).bfloat16(); lse = torch.empty(B, H, S, device=dev)
+    dqkv = torch.empty_like(qkv); delta = torch.empty(B, H, S, device=dev); st = stream_ptr(dev)
+    call("hct_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, hd, st)
+    b = timeit(lambda: call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(),
+                            dqkv.data_ptr(), delta.data_ptr(), B, S, H, hd, st))
+    print(f"{name}: bwd3 {b:.3f} ms ({2 * 4.0 * B * H * S * S * hd / b / 1e9:.0f} TFLOP/s on 2 x forward flops)")
+lib().hct_attention_set_bwd3(0)
