@@ -576,7 +576,7 @@ int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, 
 static int g_attn_tc = 2;
 // 1: pipelined persistent backward (hct_attention_bwd3.cu: three score buffers, two softmax groups per SM);
 // 0: the two-CTA-per-SM kernels of hct_attention_sm100.cu
-static int g_attn_bwd3 = 0;
+static int g_attn_bwd3 = 1;
 extern "C" int hct_attention_set_bwd3(int enable) { g_attn_bwd3 = enable != 0; return HCT_OK; }
 extern "C" int hct_attention_set_tcgen05(int mode) { g_attn_tc = mode < 0 ? 0 : (mode > 3 ? 3 : mode); return HCT_OK; }
 

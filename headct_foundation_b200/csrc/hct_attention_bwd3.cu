@@ -9,7 +9,7 @@
 // ahead with the S / dP MMAs (the tensor pipe executes in order, so a buffer is overwritten only after the accumulate MMAs
 // that read its bf16 operands), two groups of eight softmax warps take alternate blocks, and neither waits for the MMA
 // stages of its own block any more.  The CTA is persistent over (batch, head, 128-row tile) work items -- resident tiles
-// double-buffered, streamed tiles in a 6-deep TMA ring that runs across item boundaries -- so that prologue / epilogue of an
+// double-buffered, streamed tiles in a 5-deep TMA ring that runs across item boundaries -- so that prologue / epilogue of an
 // item (TMA round trip, accumulator drain) overlap the neighbouring items' work instead of being paid per CTA.
 //
 // One kernel template serves both passes (same chain, transposed roles):
@@ -31,13 +31,18 @@ constexpr int TILE_BYTES = TILE * 128;     // 128 rows x 64 bf16
 constexpr int HALF_BYTES = 64 * 128;       // 64 rows x 64 bf16
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int NSW = 16;                    // softmax warps: group = w >> 3, column half = (w >> 2) & 1, lane quarter = w & 3
-constexpr int W_PROD = 16, W_MMA = 17;
-constexpr int THREADS = 18 * 32;
-constexpr int STAGES = 6;                  // TMA ring of streamed 64-row tile pairs
+constexpr int W_PROD = 16, W_MMA_S = 17, W_MMA_A = 18;     // TMA producer, S / dP issuer, accumulate issuer
+constexpr int THREADS = 19 * 32;
+constexpr int STAGES = 5;                  // TMA ring of streamed 64-row tile pairs
 constexpr int NBUF = 3;                    // S / dP buffer pairs in tensor memory
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 128;              // [0,64): dV (dQ), [64,128): dK
-constexpr int SMEM_BYTES = 2 * 2 * TILE_BYTES + STAGES * 2 * HALF_BYTES + NSW * 512 + 1024 + 512;
+constexpr int DRAIN_SLOTS = NSW, DRAIN_SLOT_BYTES = 32 * 128;   // per softmax warp: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled
+constexpr int SMEM_BYTES = 2 * 2 * TILE_BYTES + STAGES * 2 * HALF_BYTES + NSW * 512 + DRAIN_SLOTS * DRAIN_SLOT_BYTES + 1024 + 512;
+
+__device__ long long* g_trace3 = nullptr;   // event timeline of CTA 0 (tools/attn_dbg3.py); nullptr in production
+// layout: [role: 0 mma-issue, 1 mma-acc, 2 softmax group 0 (warp 0), 3 softmax group 1 (warp 8)][block gb < 64][8 events]
+#define TR3(role, gb, ev) do { if (trace && (gb) < 64) trace[((role) * 64 + (gb)) * 8 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -53,12 +58,36 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       : "memory");
 }
 
+// (batch, head, row tile) of the CTA's items, advanced WITHOUT divisions: an integer division by a run-time divisor is a
+// ~150-cycle dependent chain, and the first version of this kernel spent ~1400 cycles per block on them in every role
+// (profiles/r02_attn_bwd3_timeline_v1.txt).
+struct ItemIter {
+  int b, h, t;              // current item
+  int dt, dh, db;           // decomposition of the item stride gridDim.x
+  int n_tiles, H;
+  __device__ ItemIter(int first, int stride, int n_tiles_, int H_) : n_tiles(n_tiles_), H(H_) {
+    t = first % n_tiles; h = (first / n_tiles) % H; b = first / (n_tiles * H);
+    dt = stride % n_tiles; dh = (stride / n_tiles) % H; db = stride / (n_tiles * H);
+  }
+  __device__ __forceinline__ void next() {
+    t += dt;
+    int c = 0;
+    if (t >= n_tiles) { t -= n_tiles; c = 1; }
+    h += dh + c;
+    c = 0;
+    if (h >= H) { h -= H; c = 1; }
+    b += db + c;
+  }
+};
+
 template <int HD, bool KV>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
                  const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO64,
                  const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H,
                  int n_tiles, int n_items, float scale) {
+  // accumulator sets in tensor memory: the dQ pass (64 columns per set) has room for two, so an item's drain overlaps the
+  // next item's MMAs; the dK/dV pass (2 x HD columns) has one and pays a short bubble per item
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -66,32 +95,27 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   uint8_t* sT1 = smem + 2 * 2 * TILE_BYTES;             // STAGES x [64 rows][64]
   uint8_t* sT2 = sT1 + STAGES * HALF_BYTES;
   float* sStat = reinterpret_cast<float*>(sT2 + STAGES * HALF_BYTES);       // [16 warps][2 slots][lse 32 | delta 32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + NSW * 512);
+  uint8_t* sDrain = reinterpret_cast<uint8_t*>(sStat) + NSW * 512;          // [16 warps][32 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDrain + DRAIN_SLOTS * DRAIN_SLOT_BYTES);
   uint64_t *kv_full = bars /*[2]*/, *kv_empty = bars + 2 /*[2]*/, *ring_full = bars + 4 /*[STAGES]*/,
            *ring_empty = bars + 4 + STAGES /*[STAGES]*/, *s_full = bars + 4 + 2 * STAGES /*[NBUF]*/,
-           *p_full = s_full + NBUF /*[NBUF]*/, *done = p_full + NBUF, *acc_empty = done + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+           *p_full = s_full + NBUF /*[NBUF]*/, *buf_free = p_full + NBUF /*[NBUF]*/, *done = buf_free + NBUF /*[2]*/,
+           *acc_empty = done + 2 /*[2]*/;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp-uniform by construction
   const int D = H * HD;
   const int nblk = (S + 63) / 64;                               // streamed 64-row blocks per item
   const bool tail16 = S - (nblk - 1) * 64 <= 16;                // last block is computed 16 columns wide
   const float sl2 = scale * LOG2E;
-  const int nmy = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-  const int total = nmy * nblk;                                 // blocks this CTA processes, numbered gb = n * nblk + i
-  // item n of this CTA -> (batch, head, row tile); tiles of one head are adjacent items (= neighbouring CTAs: L2 reuse)
-  auto item_coords = [&](int n, int& b, int& h, int& t) {
-    const int it = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-    t = it % n_tiles;
-    h = (it / n_tiles) % H;
-    b = it / (n_tiles * H);
-  };
+  const int G = static_cast<int>(gridDim.x);
+  const int nmy = (n_items - static_cast<int>(blockIdx.x) + G - 1) / G;      // items of this CTA: blockIdx.x + n * G
+  const int total = nmy * nblk;                                 // its blocks, numbered gb = n * nblk + i
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&done[i], 1); mbar_init(&acc_empty[i], 8); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(&ring_full[i], 1); mbar_init(&ring_empty[i], 1); }
-    for (int i = 0; i < NBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); }
-    mbar_init(done, 1); mbar_init(acc_empty, NSW);
+    for (int i = 0; i < NBUF; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&buf_free[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -99,15 +123,16 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 64;     // KV: dV, dK.  !KV: dQ lives in acc2's place (see below)
+  // KV: dV at [0,HD), dK at [64,64+HD).  !KV: dQ of accumulator set a at [64 a, 64 a + HD)
+  long long* trace = (g_trace3 != nullptr && blockIdx.x == 0 && lane == 0 && KV) ? g_trace3 : nullptr;
 
   if (warp == W_PROD) {
     // ===================== TMA producer =====================
     const bool leader = elect_one();
-    int gb = 0;
-    for (int n = 0; n < nmy; ++n) {
-      int b, h, t;
-      item_coords(n, b, h, t);
+    ItemIter it(static_cast<int>(blockIdx.x), G, n_tiles, H);
+    int st = 0; uint32_t ring_ph = 0;
+    for (int n = 0; n < nmy; ++n, it.next()) {
+      const int b = it.b, h = it.h, t = it.t;
       const int kb = n & 1;
       mbar_wait(&kv_empty[kb], ((n >> 1) & 1) ^ 1u);
       if (leader) {
@@ -122,9 +147,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
         }
       }
       __syncwarp();
-      for (int i = 0; i < nblk; ++i, ++gb) {
-        const int st = gb % STAGES;
-        mbar_wait(&ring_empty[st], ((gb / STAGES) & 1) ^ 1u);
+      for (int i = 0; i < nblk; ++i) {
+        mbar_wait(&ring_empty[st], ring_ph ^ 1u);
         if (leader) {
           mbar_expect_tx(&ring_full[st], 2 * HALF_BYTES);
           if (KV) {
@@ -136,139 +160,214 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
           }
         }
         __syncwarp();
+        if (++st == STAGES) { st = 0; ring_ph ^= 1u; }
       }
     }
-  } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
+  } else if (warp == W_MMA_S) {
+    // ===================== MMA issuer 1: S / dP of block gb into buffer gb % NBUF, as far ahead as buffers and tiles allow ====
     const bool leader = elect_one();
     const uint32_t idesc_s = make_idesc_bf16(TILE, 64, false, false);
     const uint32_t idesc_s16 = make_idesc_bf16(TILE, 16, false, false);
-    const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
-    auto issue_sdp = [&](int gbi) {                  // S / dP of block gbi into buffer gbi % NBUF
-      const int n = gbi / nblk, i = gbi - n * nblk;
-      const int kb = n & 1, st = gbi % STAGES, buf = gbi % NBUF;
-      if (i == 0) mbar_wait(&kv_full[kb], (n >> 1) & 1);
-      mbar_wait(&ring_full[st], (gbi / STAGES) & 1);
-      tc_fence_after();
-      if (leader) {
-        const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
-        const uint64_t dR1 = make_sdesc_sw128(smem_u32(sR + kb * 2 * TILE_BYTES), false, 0);
-        const uint64_t dR2 = make_sdesc_sw128(smem_u32(sR + kb * 2 * TILE_BYTES + TILE_BYTES), false, 0);
-        const uint64_t dT1 = make_sdesc_sw128(smem_u32(sT1 + st * HALF_BYTES), false, 0);
-        const uint64_t dT2 = make_sdesc_sw128(smem_u32(sT2 + st * HALF_BYTES), false, 0);
-        const uint32_t id = (i == nblk - 1 && tail16) ? idesc_s16 : idesc_s;
+    int st = 0; uint32_t ring_ph = 0;
+    int buf = 0; uint32_t buf_ph = 0;                 // parity of the buffer's current use
+    int gb = 0;
+    for (int n = 0; n < nmy; ++n) {
+      const int kb = n & 1;
+      mbar_wait(&kv_full[kb], (n >> 1) & 1);
+      const uint64_t dR1 = make_sdesc_sw128(smem_u32(sR + kb * 2 * TILE_BYTES), false, 0);
+      const uint64_t dR2 = make_sdesc_sw128(smem_u32(sR + kb * 2 * TILE_BYTES + TILE_BYTES), false, 0);
+      for (int i = 0; i < nblk; ++i, ++gb) {
+        TR3(0, gb, 0);
+        mbar_wait(&ring_full[st], ring_ph);
+        mbar_wait(&buf_free[buf], buf_ph ^ 1u);       // the accumulate MMAs of the buffer's previous block have completed
+        TR3(0, gb, 1);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
+          const uint64_t dT1 = make_sdesc_sw128(smem_u32(sT1 + st * HALF_BYTES), false, 0);
+          const uint64_t dT2 = make_sdesc_sw128(smem_u32(sT2 + st * HALF_BYTES), false, 0);
+          const uint32_t id = (i == nblk - 1 && tail16) ? idesc_s16 : idesc_s;
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {       // the two accumulate chains interleaved: consecutive MMAs independent
-          tc_mma(tS, dR1 + ks * 2, dT1 + ks * 2, id, ks > 0 ? 1u : 0u);
-          tc_mma(tdP, dR2 + ks * 2, dT2 + ks * 2, id, ks > 0 ? 1u : 0u);
-        }
-        tc_commit(&s_full[buf]);
-      }
-      __syncwarp();
-    };
-    int issued = 0;
-    for (int proc = 0; proc < total; ++proc) {
-      const int n = proc / nblk, i = proc - n * nblk;
-      // run ahead with S / dP: at most NBUF blocks in flight, and never beyond the NEXT item (two resident buffers)
-      while (issued < total && issued < proc + NBUF && issued / nblk <= n + 1) issue_sdp(issued++);
-      const int st = proc % STAGES, buf = proc % NBUF;
-      mbar_wait(&p_full[buf], (proc / NBUF) & 1);     // bf16 operands of block proc sit in TMEM (and its fp32 scores were read)
-      if (i == 0) mbar_wait(acc_empty, (n & 1) ^ 1u); // the previous item's accumulators have been drained
-      tc_fence_after();
-      if (leader) {
-        const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
-        const uint64_t dT1m = make_sdesc_sw128(smem_u32(sT1 + st * HALF_BYTES), true, HALF_BYTES);
-        const uint64_t dT2m = make_sdesc_sw128(smem_u32(sT2 + st * HALF_BYTES), true, HALF_BYTES);
-        const uint32_t acc = i > 0 ? 1u : 0u;
-        // k-step ks covers streamed rows [16 ks, 16 ks + 16): packed by column half ks / 2 at column 32 (ks / 2) + 8 (ks % 2)
-        if (i == nblk - 1 && tail16) {
-          if (KV) tc_mma_ts(tmem_acc1, tS, dT2m, idesc_g, acc);
-          tc_mma_ts(tmem_acc2, tdP, dT1m, idesc_g, acc);
-        } else {
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (KV) tc_mma_ts(tmem_acc1, tS + (ks >> 1) * 32 + (ks & 1) * 8, dT2m + ks * 128, idesc_g, ks > 0 ? 1u : acc);
-            tc_mma_ts(tmem_acc2, tdP + (ks >> 1) * 32 + (ks & 1) * 8, dT1m + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+          for (int ks = 0; ks < HD / 16; ++ks) {       // the two accumulate chains interleaved: consecutive MMAs independent
+            tc_mma(tS, dR1 + ks * 2, dT1 + ks * 2, id, ks > 0 ? 1u : 0u);
+            tc_mma(tdP, dR2 + ks * 2, dT2 + ks * 2, id, ks > 0 ? 1u : 0u);
           }
+          tc_commit(&s_full[buf]);
         }
-        tc_commit(&ring_empty[st]);
-        if (i == nblk - 1) { tc_commit(done); tc_commit(&kv_empty[n & 1]); }
+        __syncwarp();
+        TR3(0, gb, 2);
+        if (++st == STAGES) { st = 0; ring_ph ^= 1u; }
+        if (++buf == NBUF) { buf = 0; buf_ph ^= 1u; }
       }
-      __syncwarp();
+    }
+  } else if (warp == W_MMA_A) {
+    // ===================== MMA issuer 2: accumulate MMAs (A = bf16 operands the softmax warps left in tensor memory) =========
+    const bool leader = elect_one();
+    const uint32_t idesc_g = make_idesc_bf16(TILE, HD, false, true);
+    int st = 0;
+    int buf = 0; uint32_t buf_ph = 0;
+    int gb = 0;
+    for (int n = 0; n < nmy; ++n) {
+      const int ab = KV ? 0 : (n & 1);                 // accumulator set
+      const int ause = KV ? n : (n >> 1);              // how often it has been used before
+      const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 64 - (KV ? 0 : 64) + (KV ? 0 : 64 * ab);
+      for (int i = 0; i < nblk; ++i, ++gb) {
+        TR3(1, gb, 0);
+        mbar_wait(&p_full[buf], buf_ph);              // bf16 operands of block gb sit in TMEM (and its fp32 scores were read)
+        TR3(1, gb, 1);
+        if (i == 0) mbar_wait(&acc_empty[ab], (ause & 1) ^ 1u);   // the set's previous item has been drained
+        TR3(1, gb, 2);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
+          const uint64_t dT1m = make_sdesc_sw128(smem_u32(sT1 + st * HALF_BYTES), true, HALF_BYTES);
+          const uint64_t dT2m = make_sdesc_sw128(smem_u32(sT2 + st * HALF_BYTES), true, HALF_BYTES);
+          const uint32_t acc = i > 0 ? 1u : 0u;
+          // k-step ks covers streamed rows [16 ks, 16 ks + 16): packed by column half ks / 2 at column 32 (ks / 2) + 8 (ks % 2)
+          if (i == nblk - 1 && tail16) {
+            if (KV) tc_mma_ts(tmem_acc1, tS, dT2m, idesc_g, acc);
+            tc_mma_ts(tmem_acc2, tdP, dT1m, idesc_g, acc);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (KV) tc_mma_ts(tmem_acc1, tS + (ks >> 1) * 32 + (ks & 1) * 8, dT2m + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+              tc_mma_ts(tmem_acc2, tdP + (ks >> 1) * 32 + (ks & 1) * 8, dT1m + ks * 128, idesc_g, ks > 0 ? 1u : acc);
+            }
+          }
+          tc_commit(&ring_empty[st]);
+          tc_commit(&buf_free[buf]);
+          // the item's accumulators are complete: tell the group that drains it (the owner of block gb + 1).  One barrier
+          // per group, so that each waiter sees every phase of its barrier in order (parity waits must not skip phases)
+          if (i == nblk - 1) { tc_commit(&done[(gb + 1) & 1]); tc_commit(&kv_empty[n & 1]); }
+        }
+        __syncwarp();
+        TR3(1, gb, 3);
+        if (++st == STAGES) st = 0;
+        if (++buf == NBUF) { buf = 0; buf_ph ^= 1u; }
+      }
     }
   } else {
     // ===================== softmax-backward warps: one row (TMEM lane) per thread =====================
     const int grp = warp >> 3, wg = (warp >> 2) & 1, q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     float* wstat = sStat + warp * 128;
-    int cur_item = 0;                                // next item whose accumulators this warp still has to drain
+    if ((warp & 7) != 0) trace = nullptr;            // warps 0 and 8 (first warp of each group) report
+    const int trole = 2 + grp;
 
-    // accumulator drain of item m: the four warps of a lane quarter split the columns
-    auto drain = [&](int m) {
-      int b, h, t;
-      item_coords(m, b, h, t);
-      const int row = t * TILE + q * 32 + lane;
-      const bool row_ok = row < S;
+    // accumulator drain of item m (coordinates b, h, t): done by ONE group (8 warps, two per lane quarter)
+    uint32_t done_ph = 0;                              // parity of this group's next `done` phase
+    auto drain = [&](int m, int b, int h, int t) {
+      const int ab = KV ? 0 : (m & 1);
       const bool warp_active = t * TILE + q * 32 < S;
-      mbar_wait(done, m & 1);
+      mbar_wait(&done[grp], done_ph);
+      done_ph ^= 1u;
       tc_fence_after();
-      const int id4 = warp >> 2;                     // 0..3
-      if (warp_active && (KV || id4 < 2)) {
-        // KV: id4 0,1 -> dK halves, 2,3 -> dV halves.  !KV: id4 0,1 -> dQ halves
-        const bool second = KV ? (id4 >= 2) : false;
-        const uint32_t src = second ? tmem_acc1 : tmem_acc2;
-        const int c_begin = (id4 & 1) * (HD / 2);
-        bf16* dst = dqkv + (static_cast<long long>(b) * S + row) * (3LL * D) + h * HD + (KV ? (second ? 2 * D : D) : 0);
-        const float sc = second ? 1.0f : scale;
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_begin + HD / 2; c0 += 8) {
-          uint32_t o[8];
-          tmem_ld8(src + lane_off + c0, o);
-          if (row_ok) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[0]) * sc, __uint_as_float(o[1]) * sc);
-            u.y = pack_bf16x2(__uint_as_float(o[2]) * sc, __uint_as_float(o[3]) * sc);
-            u.z = pack_bf16x2(__uint_as_float(o[4]) * sc, __uint_as_float(o[5]) * sc);
-            u.w = pack_bf16x2(__uint_as_float(o[6]) * sc, __uint_as_float(o[7]) * sc);
-            *reinterpret_cast<uint4*>(dst + c0) = u;
+      const bool drains = warp_active && (KV || wg == 0);
+      // KV: column half 0 -> dK, 1 -> dV (HD columns each).  !KV: half 0 -> dQ
+      const bool second = KV && wg == 1;
+      const float sc = second ? 1.0f : scale;
+      // Each thread holds one ROW; stored from registers, a warp-wide 16-byte store would touch 32 different lines.
+      // Transposed through a private swizzled staging slot, eight lanes write one row's contiguous HD x 2 bytes:
+      // 4 rows = 4 lines per instruction.
+      uint8_t* stg = sDrain + warp * DRAIN_SLOT_BYTES;     // private: the two groups' drains of consecutive items may overlap
+      if (drains) {
+        const uint32_t src = tmem_base + (KV ? (second ? 0 : 64) : 64 * ab);
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 32) {            // 32 (+ 32 | + 16) columns: half the registers of one pass
+          uint32_t o[32];
+          if (c0 + 32 <= HD) tmem_ld32(src + lane_off + c0, o);
+          else tmem_ld16(src + lane_off + c0, *reinterpret_cast<uint32_t(*)[16]>(&o[0]));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c0 + 8 * c < HD) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(o[8 * c]) * sc, __uint_as_float(o[8 * c + 1]) * sc);
+              u.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * sc, __uint_as_float(o[8 * c + 3]) * sc);
+              u.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * sc, __uint_as_float(o[8 * c + 5]) * sc);
+              u.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * sc, __uint_as_float(o[8 * c + 7]) * sc);
+              const int ch = c0 / 8 + c;
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = u;
+            }
           }
         }
       }
+      // the accumulators have left tensor memory: hand the set back to the MMA issuer BEFORE the (slow, rarely executed)
+      // global-store path
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty);
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      if (drains) {
+        __syncwarp();
+        const int chunk = lane & 7, rsub = lane >> 3;
+        if (chunk < HD / 8) {
+          const int row0 = t * TILE + q * 32;
+          bf16* dst0 = dqkv + (static_cast<long long>(b) * S + row0) * (3LL * D) + h * HD + (KV ? (second ? 2 * D : D) : 0) + chunk * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = k * 4 + rsub;
+            if (row0 + r < S) {
+              const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
+              *reinterpret_cast<uint4*>(dst0 + static_cast<long long>(r) * (3LL * D)) = v;
+            }
+          }
+        }
+        __syncwarp();
+      }
     };
 
+    // Position of this group's current block and of its next one (statistics are fetched one own block ahead), advanced
+    // incrementally.  `prev` = coordinates of item n - 1.
+    struct Pos { int n, i; };
+    Pos cur{0, grp};
+    ItemIter cit(static_cast<int>(blockIdx.x), G, n_tiles, H);
+    int pb = 0, ph_ = 0, pt = 0;                       // previous item's coordinates
+    auto norm = [&](Pos& p, ItemIter& it, bool track_prev) {
+      while (p.i >= nblk) {
+        p.i -= nblk; ++p.n;
+        if (track_prev) { pb = it.b; ph_ = it.h; pt = it.t; }
+        it.next();
+      }
+    };
+    norm(cur, cit, true);
+    Pos nxt = cur;
+    ItemIter nit = cit;
     // statistics of a block: KV -> per streamed column (queries of block i): lse * log2e | delta for this warp's 32 columns;
     //                        !KV -> per row (this thread's query row of the item's tile)
-    auto load_stats = [&](int gbi, float& a, float& d) {
-      const int n = gbi / nblk, i = gbi - n * nblk;
-      int b, h, t;
-      item_coords(n, b, h, t);
-      const long long base = (static_cast<long long>(b) * H + h) * S;
-      const int r = KV ? (i * 64 + wg * 32 + lane) : (t * TILE + q * 32 + lane);
-      if (r < S) { a = lse[base + r] * LOG2E; d = delta[base + r]; } else { a = 0.f; d = 0.f; }
+    auto load_stats = [&](const Pos& p, const ItemIter& it, float& a, float& d) {
+      const long long base = (static_cast<long long>(it.b) * H + it.h) * S;
+      // Nothing may depend on the loaded registers here -- neither a multiply nor the `else a = 0` of a bounds select (a
+      // predicated move to the load's destination waits on its scoreboard): the in-order warp would sit out the whole
+      // global-load latency on the spot (400-1100 cycles per block in profiles/r02_attn_bwd3_timeline_v1.txt).  The row
+      // index is clamped instead; columns / rows beyond S are masked or never stored.
+      const int r = min(KV ? (p.i * 64 + wg * 32 + lane) : (it.t * TILE + q * 32 + lane), S - 1);
+      a = lse[base + r];
+      d = delta[base + r];
     };
     float st_a = 0.f, st_d = 0.f;
-    if (grp < total) load_stats(grp, st_a, st_d);
+    if (cur.n < nmy) load_stats(cur, cit, st_a, st_d);
+    int buf = grp % NBUF; uint32_t buf_ph = 0;         // buffer / use parity of block gb = grp, advanced by 2 per own block
     int cnt = 0;
     for (int gb = grp; gb < total; gb += 2, ++cnt) {
-      const int n = gb / nblk, i = gb - n * nblk;
-      while (cur_item < n) { drain(cur_item); ++cur_item; }
-      int b, h, t;
-      item_coords(n, b, h, t);
-      const bool warp_active = t * TILE + q * 32 < S;        // warps without a valid row only keep the barriers moving
-      const int buf = gb % NBUF;
+      const int n = cur.n, i = cur.i;
+      TR3(trole, gb, 0);
+      const bool warp_active = cit.t * TILE + q * 32 < S;    // warps without a valid row only keep the barriers moving
       const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
       float* stat = wstat + (cnt & 1) * 64;
-      const float row_a = st_a, row_d = st_d;                // !KV: this thread's row statistics
+      const float row_a = st_a * LOG2E, row_d = st_d;        // !KV: this thread's row statistics
       if (KV) {
-        stat[lane] = st_a;
+        stat[lane] = row_a;
         stat[32 + lane] = st_d;
         __syncwarp();
       }
-      if (gb + 2 < total) load_stats(gb + 2, st_a, st_d);    // one own block ahead: the global-load latency stays off the chain
-      mbar_wait(&s_full[buf], (gb / NBUF) & 1);
+      TR3(trole, gb, 1);
+      nxt.i += 2;
+      norm(nxt, nit, false);
+      TR3(trole, gb, 7);
+      // one own block ahead: the global-load latency stays off the chain (dQ pass: row statistics change with the item only)
+      if (nxt.n < nmy && (KV || nxt.n != n)) load_stats(nxt, nit, st_a, st_d);
+      TR3(trole, gb, 2);
+      mbar_wait(&s_full[buf], buf_ph);
+      TR3(trole, gb, 3);
       tc_fence_after();
       const int ncol = min(64, S - i * 64);                  // valid streamed columns in this block
       const bool t16 = (i == nblk - 1) && tail16;
@@ -322,6 +421,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
             dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) - dl.z), p3 * (__uint_as_float(dv[e + 3]) - dl.w));
           }
         }
+        TR3(trole, gb, 4);
         // in place: this thread's own lanes, inside the fp32 columns it has just read
         if (KV) tmem_st16(tS + lane_off + wg * 32, pk);
         tmem_st16(tdP + lane_off + wg * 32, dk);
@@ -330,8 +430,23 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[buf]);
+      TR3(trole, gb, 5);
+      // The group that owns the FIRST block of an item drains the previous item, after that block: its operands are in
+      // place, so the accumulate issuer is held up by the drain alone (dK/dV pass) or not at all (dQ pass, two sets).
+      if (i == 0 && n > 0) drain(n - 1, pb, ph_, pt);
+      TR3(trole, gb, 6);
+      cur.i += 2;
+      norm(cur, cit, true);
+      buf += 2; if (buf >= NBUF) { buf -= NBUF; buf_ph ^= 1u; }
     }
-    while (cur_item < nmy) { drain(cur_item); ++cur_item; }
+    // the last item: drained by the group that would own the next block
+    if ((total & 1) == grp) {
+      // coordinates of item nmy - 1: cur has run past the end; cit is the item AFTER the last processed one only if it was
+      // advanced, so recompute from scratch (once per kernel)
+      ItemIter lit(static_cast<int>(blockIdx.x), G, n_tiles, H);
+      for (int k = 0; k < nmy - 1; ++k) lit.next();
+      drain(nmy - 1, lit.b, lit.h, lit.t);
+    }
   }
 
   tc_fence_before();
@@ -359,6 +474,11 @@ int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensor
 }
 
 }  // namespace
+
+extern "C" int hct_attention_trace3(void* buf) {      // device buffer of >= 4 * 64 * 8 int64 (or NULL): bwd3 dK/dV timeline
+  long long* p = static_cast<long long*>(buf);
+  return cudaMemcpyToSymbol(g_trace3, &p, sizeof(p)) == cudaSuccess ? HCT_OK : HCT_ERR_CUDA;
+}
 
 // n_tiles full 128-row tiles per (batch, head) on tcgen05 (rows behind them: hct_attention_tail.cu)
 int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S, int H,

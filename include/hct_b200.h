@@ -214,6 +214,8 @@ int hct_attention_set_dkdv32(int enable);
 /* 1: backward on the pipelined persistent kernels of hct_attention_bwd3.cu (one CTA per SM, three score-buffer pairs in
  * tensor memory, two softmax warp groups); 0: the two-CTA-per-SM kernels.  Same results either way. */
 int hct_attention_set_bwd3(int enable);
+/* debugging aid: clock64 timeline of CTA 0 of the bwd3 dK/dV kernel into a device buffer of >= 2048 int64 (NULL = off) */
+int hct_attention_trace3(void* buf);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
 /* Diagnostics: clock64 event timeline of one CTA of the dK/dV backward kernel.  buf = device buffer of >= 768 int64
  * (layout: [producer | MMA | softmax warp 0][block][8 events], see tools/attn_dbg.py) or NULL to switch it off. */

@@ -169,8 +169,10 @@ def test_layernorm_fwd_bwd(cuda, HF, rows, dim, eps):
                                       (1, 128, 2, 64), (2, 256, 2, 48), (1, 385, 1, 64)])
 def test_attention_fwd_bwd(cuda, HF, B, S, H, hd, mode):
     """mode 2 (default): tcgen05 kernels, backward rows behind the last full 128-row tile on the row kernel; 3: tcgen05 for
-    every tile; 1: forward tail rows on mma.sync; 0: mma.sync kernels only."""
+    every tile; 1: forward tail rows on mma.sync; 0: mma.sync kernels only.  Backward on the two-CTA-per-SM kernels here
+    (hct_attention_set_bwd3(0)); the default pipelined persistent backward has its own test below."""
     from headct_foundation_b200._cabi import call, stream_ptr, lib
+    lib().hct_attention_set_bwd3(0)
     if mode != 2 and (hd == 32 or S < 64):
         pytest.skip("mode only matters for the tcgen05 shapes")
     lib().hct_attention_set_tcgen05(mode)
@@ -178,6 +180,7 @@ def test_attention_fwd_bwd(cuda, HF, B, S, H, hd, mode):
         _attention_case(cuda, B, S, H, hd)
     finally:
         lib().hct_attention_set_tcgen05(2)
+        lib().hct_attention_set_bwd3(1)
 
 
 @pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (2, 65, 2, 48), (1, 321, 2, 64),
@@ -186,11 +189,13 @@ def test_attention_bwd_unmerged_tail_block(cuda, HF, B, S, H, hd):
     """The default backward computes a <= 16-row last block together with block 0 (hct_attention_set_merge_tail(1));
     the older schedule -- the tail block as its own chain step -- stays available for A/B timing and must agree too."""
     from headct_foundation_b200._cabi import lib
+    lib().hct_attention_set_bwd3(0)
     lib().hct_attention_set_merge_tail(0)
     try:
         _attention_case(cuda, B, S, H, hd)
     finally:
         lib().hct_attention_set_merge_tail(1)
+        lib().hct_attention_set_bwd3(1)
 
 
 @pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (2, 65, 2, 48), (1, 321, 2, 64),
@@ -198,11 +203,13 @@ def test_attention_bwd_unmerged_tail_block(cuda, HF, B, S, H, hd):
 def test_attention_bwd_pipelined_dkdv_variant(cuda, HF, B, S, H, hd):
     """The off-by-default dK/dV kernel with 32-query blocks and two S^T / dP^T buffer pairs (hct_attention_set_dkdv32)."""
     from headct_foundation_b200._cabi import lib
+    lib().hct_attention_set_bwd3(0)
     lib().hct_attention_set_dkdv32(1)
     try:
         _attention_case(cuda, B, S, H, hd)
     finally:
         lib().hct_attention_set_dkdv32(0)
+        lib().hct_attention_set_bwd3(1)
 
 
 @pytest.mark.parametrize("mode", [2, 3])
@@ -221,7 +228,6 @@ def test_attention_bwd_pipelined_persistent(cuda, HF, B, S, H, hd, mode):
     try:
         _attention_case(cuda, B, S, H, hd)
     finally:
-        lib().hct_attention_set_bwd3(0)
         lib().hct_attention_set_tcgen05(2)
 
 
