@@ -1355,3 +1355,44 @@ def adjust_contrast_(vol: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
     ws = torch.empty((2 * n,), dtype=torch.int32, device=vol.device)
     call("hct_adjust_contrast", vol.data_ptr(), g.data_ptr(), ws.data_ptr(), n, vol.numel() // n, stream_ptr(vol.device))
     return vol
+
+
+# --------------------------------------------------------------------------------------------
+# Dispatch used by the modules: eager mode applies the autograd.Functions directly; under torch.compile the same bodies
+# run as torch.library ops (ops.py) so that the tracer goes through the modules without graph breaks.
+# --------------------------------------------------------------------------------------------
+def _tracing() -> bool:
+    return torch.compiler.is_compiling()
+
+
+def block(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, lora, heads, eps):
+    """AttentionBlock body.  `lora`: (lqA, lqB, lvA, lvB) or four Nones."""
+    if _tracing() and lora[0] is None:
+        return _ops.block(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, heads, eps)
+    return _block_eager(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, lora, heads, eps)
+
+
+@torch.compiler.disable
+def _block_eager(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, lora, heads, eps):
+    return BlockFn.apply(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, *lora, heads, eps)
+
+
+def embed(vol, conv_w, conv_b, pos, prefix, ids_keep, patch):
+    if _tracing():
+        return _ops.embed(vol, conv_w, conv_b, pos, prefix, ids_keep, patch)
+    return EmbedFn.apply(vol, conv_w, conv_b, pos, prefix, ids_keep, patch)
+
+
+def layernorm(x, w, b, eps, out_bf16):
+    if _tracing():
+        return _ops.layernorm(x, w, b, eps, out_bf16)
+    return LayerNormFn.apply(x, w, b, eps, out_bf16)
+
+
+def linear(x, w, b, gelu=False, out_f32=False):
+    if _tracing():
+        return _ops.linear(x, w, b, gelu, out_f32)
+    return LinearFn.apply(x, w, b, gelu, out_f32)
+
+
+from . import ops as _ops  # noqa: E402  (ops.py needs the Functions defined above)

@@ -100,8 +100,8 @@ class AttentionBlock(nn.Module):
         self.ffn_norm = norm_layer(hidden_size)
         self.attn = SelfAttention(hidden_size, num_heads, dropout=dropout_rate, qkv_proj_bias=qkv_bias, lora=lora)
 
-    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, hidden_states, residual=None):
+        # traceable: under torch.compile the body runs as the torch.library op headct::block (ops.py)
         if self.dropout_rate > 0 and self.training:
             raise NotImplementedError("dropout is outside the accelerated path")
         if self.att_norm.eps != self.ffn_norm.eps:
@@ -109,9 +109,9 @@ class AttentionBlock(nn.Module):
         a, m = self.attn, self.mlp
         lora = ((a.lora_q.lora_matrix_A, a.lora_q.lora_matrix_B, a.lora_v.lora_matrix_A, a.lora_v.lora_matrix_B)
                 if a.lora else (None, None, None, None))
-        out = HF.BlockFn.apply(hidden_states, self.att_norm.weight, getattr(self.att_norm, "bias", None),
-                               a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
-                               self.ffn_norm.weight, getattr(self.ffn_norm, "bias", None),
-                               m.linear1.weight, m.linear1.bias, m.linear2.weight, m.linear2.bias, *lora,
-                               self.num_heads, self.att_norm.eps)
+        out = HF.block(hidden_states, self.att_norm.weight, getattr(self.att_norm, "bias", None),
+                       a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+                       self.ffn_norm.weight, getattr(self.ffn_norm, "bias", None),
+                       m.linear1.weight, m.linear1.bias, m.linear2.weight, m.linear2.bias, lora,
+                       self.num_heads, self.att_norm.eps)
         return out, residual

@@ -50,8 +50,9 @@ class ViT(nn.Module):
         if self.register_tokens is not None:
             nn.init.normal_(self.register_tokens, std=1e-6)
 
-    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
     def forward(self, x):
+        # traceable: under torch.compile (main_downstream.py:162) the kernels are reached through torch.library ops
+        # (ops.py: headct::embed, headct::block, headct::layernorm) -- no graph breaks
         with torch.autocast(device_type="cuda", enabled=False):
             prefix = self.cls_token
             if self.register_tokens is not None:
@@ -62,7 +63,7 @@ class ViT(nn.Module):
             for blk in self.blocks:
                 x, residual = blk(x, residual)
                 hidden_states_out.append(x)
-            x = HF.LayerNormFn.apply(x, self.norm.weight, getattr(self.norm, "bias", None), self.norm.eps, False)
+            x = HF.layernorm(x, self.norm.weight, getattr(self.norm, "bias", None), self.norm.eps, False)
             if hasattr(self, "classification_head"):
                 x = self.classification_head(x[:, 0])       # tiny host-torch head (CLASSIFICATION: False in all configs)
         return x, hidden_states_out

@@ -97,9 +97,7 @@ class PatchEmbeddingBlock(nn.Module):
         """[B, P + n, hidden] fp32: optional prefix tokens (cls / registers) then the (selected) patch tokens."""
         self._check(x)
         pe = self.patch_embeddings
-        return HF.EmbedFn.apply(x, pe.weight, pe.bias, self.position_embeddings, prefix, ids_keep,
-                                self.patch_size[0])
+        return HF.embed(x, pe.weight, pe.bias, self.position_embeddings, prefix, ids_keep, self.patch_size[0])
 
-    @torch.compiler.disable          # opaque to torch.compile: the body enqueues C-ABI launches, nothing to trace
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor) -> torch.Tensor:      # traceable (headct::embed under torch.compile)
         return self.embed(x)
