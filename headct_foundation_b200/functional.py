@@ -155,13 +155,16 @@ class ZeroArena:
     one `torch.zeros` at a time cost ~250 tiny fill launches per step, this costs one per autograd node.
     `take` of a name that was not requested returns None (gradient not wanted)."""
 
+    separate = False      # ops.py sets this around a backward: outputs of a torch.library op may not share storage
+
     def __init__(self, sizes: Dict[str, int], device: torch.device):
         self._offs: Dict[str, Tuple[int, int]] = {}
         total = 0
         for k, n in sizes.items():
             self._offs[k] = (total, n)
             total += (n + 63) // 64 * 64
-        self._buf = torch.zeros((max(total, 64),), dtype=F32, device=device)
+        self._device = device
+        self._buf = None if ZeroArena.separate else torch.zeros((max(total, 64),), dtype=F32, device=device)
 
     def has(self, name: str) -> bool:
         return name in self._offs
@@ -174,6 +177,8 @@ class ZeroArena:
         for d in shape:
             n *= d
         assert n == size, (name, shape, size)
+        if self._buf is None:
+            return torch.zeros(shape, dtype=F32, device=self._device)
         return self._buf[off:off + n].view(*shape)
 
 

@@ -117,7 +117,11 @@ def _(x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, n2w, n2b, fc1_w, fc1_b, fc2_w, 
 
 @torch.library.custom_op("headct::block_bwd", mutates_args=())
 def _block_bwd(dout: Tensor, token: Tensor, like: List[Tensor], mask: int) -> List[Tensor]:
-    grads = HF.BlockFn.backward(_take(token), dout)
+    HF.ZeroArena.separate = True          # op outputs may not alias each other: no shared gradient arena here
+    try:
+        grads = HF.BlockFn.backward(_take(token), dout)
+    finally:
+        HF.ZeroArena.separate = False
     return _pack_grads(grads, mask, _NB)
 
 
