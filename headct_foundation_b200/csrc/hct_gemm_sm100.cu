@@ -29,7 +29,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;   // 384
 constexpr int TMEM_COLS = 512;
-constexpr int STG_BYTES = 32 * 128;           // per epilogue warp: 32 rows x 32 fp32
+constexpr int STG_BYTES = 4096;              // per epilogue warp: one 32 x 32 fp32 transpose buffer, or (TMA epilogue) two 2 KiB bf16 units
 
 struct GemmParams {
   int M, N, K;
@@ -186,7 +186,104 @@ struct EpiTraits {
                                    EPI == HCT_EPI_GELU_DERIV_BF16 || EPI == HCT_EPI_MUL_BF16;
   static constexpr bool uses_aux = EPI == HCT_EPI_DGELU_BF16 || EPI == HCT_EPI_MUL_BF16;   // bf16 multiplicand, no bias
   static constexpr bool gelu_fwd = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16;
+  // bf16-output epilogues whose tiles leave (and whose bf16 multiplicand arrives) through TMA: see epilogue_tma_unit
+  static constexpr bool tma = EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16 ||
+                              EPI == HCT_EPI_MUL_BF16;
+  static constexpr bool tma_in = EPI == HCT_EPI_MUL_BF16;      // aux tile loaded by TMA
 };
+
+// ------------------------------------------------------------------ TMA epilogue (bf16 outputs)
+// The transposing epilogue above moves every accumulator element through the LSU four times (st.shared, ld.shared,
+// st.global, plus the multiplicand's ld.global) and spends a third of its instructions on addresses and predicates: ncu
+// shows the LSU data pipe at 51-54 % over the whole launch and the aux loads' latency exposed (stall_long_sb) for the K = 768
+// GEMMs with two large bf16 streams (profiles/r02_ncu_gemm_epilogue.txt).  Here a thread keeps its accumulator ROW: the
+// math runs in the TMEM register layout, results are written once to shared memory as a 32 x 32 bf16 box in the TMA
+// 64-byte swizzle (conflict-free 16-byte stores), and one elected lane hands the box to cp.async.bulk.tensor -- no
+// ld.shared, no st.global, no address arithmetic, M / N tails clipped by the tensor map.  The MUL epilogue's multiplicand
+// comes in the same way (TMA load into the same swizzled layout, one unit ahead; the first unit of a tile while the main
+// loop still runs), so its DRAM latency never meets a scoreboard.
+__device__ __forceinline__ uint32_t sw64(int row, int chunk) {      // byte offset of 16-byte chunk (8 bf16) of a 64-byte row
+  return static_cast<uint32_t>(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// One 32 x 32 unit: `acc` = this thread's row (32 fp32 columns).  buf: the unit's 4 KiB buffer (out1 at +0, out2 / aux at
+// +2048).  Returns after the results sit in shared memory (the caller fences and issues the TMA store).
+// the unit's 32 bias values (the same for every lane: broadcast loads), requested ahead of the accumulator wait
+template <int EPI>
+__device__ __forceinline__ void load_bias_row(const GemmParams& p, int col0, float4 (&b)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!EpiTraits<EPI>::uses_aux && p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (col0 + 4 * j < p.N) b[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_tma_unit(const GemmParams& p, uint32_t buf, int lane, int col0, const uint32_t (&acc)[32],
+                                                  const float4 (&bias)[8]) {
+  using T = EpiTraits<EPI>;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {                         // 8 columns per pass
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[8 * j + e]);
+    if (EPI == HCT_EPI_BF16) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] *= p.alpha;
+    }
+    if (!T::uses_aux) {
+      const float4 b0 = bias[2 * j], b1 = bias[2 * j + 1];
+      x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w; x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+    }
+    const uint32_t off = sw64(lane, j);
+    if (EPI == HCT_EPI_GELU_BF16 && p.out2 != nullptr) {      // pre-activation side output
+      st_shared_v4(buf + 2048 + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+    }
+    if (T::gelu_fwd) {
+      float d[8];
+      gelu_multi<8, EPI == HCT_EPI_GELU_DERIV_BF16>(x, d);
+      if (EPI == HCT_EPI_GELU_DERIV_BF16)
+        st_shared_v4(buf + 2048 + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+    }
+    if (EPI == HCT_EPI_MUL_BF16) {
+      const uint4 a = ld_shared_u4(buf + 2048 + off);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      x[0] *= a0.x; x[1] *= a0.y; x[2] *= a1.x; x[3] *= a1.y; x[4] *= a2.x; x[5] *= a2.y; x[6] *= a3.x; x[7] *= a3.y;
+    }
+    st_shared_v4(buf + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+  }
+}
+// column sums of a staged bf16 unit (as the consumer will read it): lane = column, 32 two-byte reads down the rows
+__device__ __forceinline__ void colsum_tma_unit(const GemmParams& p, uint32_t buf, int lane, int row_base, int col0) {
+  const int rows = min(32, p.M - row_base);
+  float s = 0.f;
+  const int chunk = lane >> 3, within = (lane & 7) * 2;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    const uint32_t u = ld_shared_u16(buf + sw64(r, chunk) + within);
+    if (r < rows) s += __uint_as_float(u << 16);
+  }
+  if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, s);
+}
 
 // bf16 multiplicand rows of one interior 32 x 32 unit (lane = (row sub-index, 4-column group)), eight 8-byte loads
 template <int EPI>
@@ -446,13 +543,17 @@ __device__ __forceinline__ void epilogue_drain(const GemmParams& p, uint32_t stg
 //           issues MMAs; TMA loads of both CTAs complete on the leader's `full` barrier; tcgen05.commit
 //           multicasts to both CTAs' `empty` / `tmem full` barriers; both epilogues report to the leader's
 //           `tmem empty` barrier.
-template <int CTAS>
+template <int CTAS, int EPI>
 struct Cfg {
-  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  // TMA epilogues with a second bf16 stream (gelu' / pre-activation out, multiplicand in) double-buffer 2 x 2 KiB per warp
+  // and give up one pipeline stage for it (their GEMMs have K = 768: the ring depth matters least there)
+  static constexpr bool TWO_STREAMS = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16 || EPI == HCT_EPI_MUL_BF16;
+  static constexpr int WARP_STG = TWO_STREAMS ? 2 * STG_BYTES : STG_BYTES;
+  static constexpr int STAGES = (CTAS == 2 ? 6 : 4) - (TWO_STREAMS ? 1 : 0);
   static constexpr int B_ROWS = BN / CTAS;                     // B rows staged by each CTA
   static constexpr int B_STAGE = B_ROWS * BK * 2;
   static constexpr int STAGE = A_STAGE_BYTES + B_STAGE;
-  static constexpr int SMEM = STAGES * STAGE + EPI_WARPS * STG_BYTES + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE + EPI_WARPS * WARP_STG + 1024 + 512;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -493,8 +594,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // remote 
 template <int EPI, int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                        const GemmParams p) {
-  using C = Cfg<CTAS>;
+                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                        const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  using C = Cfg<CTAS, EPI>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -502,11 +604,12 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint8_t* sStage = smem + STAGES * C::STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + EPI_WARPS * STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + EPI_WARPS * C::WARP_STG);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* aux_bar = tempty_bar + 2;                   // [EPI_WARPS][2]: TMA loads of the MUL epilogue's multiplicand units
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + 2 * EPI_WARPS);
 
   // warp id and CTA rank are made warp-uniform by construction (shfl): the control warps below run their loops as whole
   // converged warps and issue TMA / MMA under elect_one(), so descriptors stay in uniform registers and the four
@@ -522,10 +625,12 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (EpiTraits<EPI>::tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmOut)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS * CTAS); }
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -628,11 +733,86 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       if (trace && lane == 0 && tix < 64) trace[tix * 8 + 2] = clock64();
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+  } else if (warp >= FIRST_EPI_WARP && EpiTraits<EPI>::tma) {
+    // ===================== epilogue, TMA path (bf16 outputs; see epilogue_tma_unit) =====================
+    using T = EpiTraits<EPI>;
+    const int q = warp & 3;                               // TMEM lane quarter this warp may touch
+    const int half = (warp - FIRST_EPI_WARP) >> 2;        // which 128-column half
+    constexpr int UB = C::WARP_STG / 2;                   // bytes per unit buffer: out1 at +0, second stream (if any) at +2048
+    const uint32_t stg = smem_u32(sStage + (warp - FIRST_EPI_WARP) * C::WARP_STG);
+    uint64_t* my_aux_bar = aux_bar + 2 * (warp - FIRST_EPI_WARP);
+    const bool two_out = EPI == HCT_EPI_GELU_DERIV_BF16 || (EPI == HCT_EPI_GELU_BF16 && p.out2 != nullptr);
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t u = 0;                                       // units handled by this warp: buffer u & 1, aux parity (u >> 1) & 1
+    for (int w = unit; w < total_work; w += num_units) {
+      const int tile = w % tiles;
+      const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * TILE_M + rank * BM;
+      const int row_base = m0 + q * 32;
+      const int colw = n0 + half * (BN / 2);
+      int nunits = 0;
+      if (row_base < p.M && colw < p.N) nunits = min(4, (p.N - colw + 31) / 32);
+      // the multiplicand of the first unit is requested before the tile's MMAs have finished (off the chain)
+      if (T::tma_in && nunits > 0 && lane == 0) {
+        const uint32_t b = stg + (u & 1) * UB + 2048;
+        mbar_expect_tx(&my_aux_bar[u & 1], 2048);
+        tma_load_2d(b, &tmAux, &my_aux_bar[u & 1], colw, row_base);
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2);
+      uint32_t v[32];
+      if (nunits > 0) tmem_ld32_issue(t0, v);
+#pragma unroll 1
+      for (int c = 0; c < nunits; ++c, ++u) {
+        const uint32_t buf = stg + (u & 1) * UB;
+        const int col0 = colw + c * 32;
+        // the store that read this buffer two units ago must have finished reading before it is overwritten
+        if (lane == 0) {
+          bulk_wait_read<1>();
+          if (T::tma_in && c + 1 < nunits) {              // multiplicand of the next unit: its buffer half was last read one unit ago
+            const uint32_t bn = stg + ((u + 1) & 1) * UB + 2048;
+            mbar_expect_tx(&my_aux_bar[(u + 1) & 1], 2048);
+            tma_load_2d(bn, &tmAux, &my_aux_bar[(u + 1) & 1], col0 + 32, row_base);
+          }
+        }
+        __syncwarp();
+        float4 bias[8];
+        load_bias_row<EPI>(p, col0, bias);                // in flight across the accumulator wait
+        tmem_ld_wait();
+        uint32_t a[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = v[i];
+        if (c + 1 < nunits) {
+          tmem_ld32_issue(t0 + (c + 1) * 32, v);          // next unit's accumulators in flight under this unit's math
+        } else {
+          tc_fence_before(); __syncwarp();
+          if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
+        }
+        if (T::tma_in) mbar_wait(&my_aux_bar[u & 1], (u >> 1) & 1);
+        epilogue_tma_unit<EPI>(p, buf, lane, col0, a, bias);
+        fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmOut, buf, col0, row_base);
+          if (two_out) tma_store_2d(&tmOut2, buf + 2048, col0, row_base);
+          bulk_commit();
+        }
+        if (p.colsum != nullptr) colsum_tma_unit(p, buf, lane, row_base, col0);
+        if (T::tma_in) __syncwarp();                      // every lane has read the multiplicand before its half is reloaded
+      }
+      if (nunits == 0) {
+        tc_fence_before(); __syncwarp();
+        if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) bulk_wait_all();                       // shared memory (and the stores) outlive the CTA otherwise
+    __syncwarp();
   } else if (warp >= FIRST_EPI_WARP) {
     // ===================== epilogue =====================
     const int q = warp & 3;                               // TMEM lane quarter this warp may touch
     const int half = (warp - FIRST_EPI_WARP) >> 2;        // which 128-column half
-    const uint32_t stg = smem_u32(sStage + (warp - FIRST_EPI_WARP) * STG_BYTES);
+    const uint32_t stg = smem_u32(sStage + (warp - FIRST_EPI_WARP) * C::WARP_STG);
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = unit; w < total_work; w += num_units) {
       const int tile = w % tiles;
@@ -740,7 +920,7 @@ PFN_encodeTiled get_encode_fn() {
 
 // 2-D bf16 tensor map over a row-major [outer, inner] matrix with leading dimension ld (elements).
 int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld, int box_inner,
-              int box_outer) {
+              int box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) { hct_set_error("cuTensorMapEncodeTiled entry point unavailable"); return HCT_ERR_CUDA; }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
@@ -748,7 +928,7 @@ int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long oute
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     hct_set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r, base,
@@ -758,42 +938,44 @@ int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long oute
   return HCT_OK;
 }
 
+struct EpiMaps { CUtensorMap out, out2, aux; };
+
 template <int EPI, int CTAS>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, const GemmParams& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   auto kernel = hct_gemm_tcgen05_kernel<EPI, CTAS>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CTAS>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CTAS, EPI>::SMEM);
     if (e != cudaSuccess) { hct_set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM;
+  cfg.dynamicSmemBytes = Cfg<CTAS, EPI>::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, em.out, em.out2, em.aux, p);
   if (e != cudaSuccess) { hct_set_error("cudaLaunchKernelEx(gemm): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return HCT_ERR_CUDA; }
   return hct_check_launch("hct_gemm_tcgen05_kernel");
 }
 
 template <int CTAS>
-int dispatch(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t st) {
+int dispatch(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, const GemmParams& p, int grid, cudaStream_t st) {
   switch (epi) {
-    case HCT_EPI_BF16: return launch<HCT_EPI_BF16, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_GELU_BF16: return launch<HCT_EPI_GELU_BF16, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_RES_F32: return launch<HCT_EPI_RES_F32, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_POS_F32: return launch<HCT_EPI_POS_F32, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_DGELU_BF16: return launch<HCT_EPI_DGELU_BF16, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_F32: return launch<HCT_EPI_F32, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_GELU_DERIV_BF16: return launch<HCT_EPI_GELU_DERIV_BF16, CTAS>(tmA, tmB, p, grid, st);
-    case HCT_EPI_MUL_BF16: return launch<HCT_EPI_MUL_BF16, CTAS>(tmA, tmB, p, grid, st);
-    default: return launch<HCT_EPI_ATOMIC_F32, CTAS>(tmA, tmB, p, grid, st);
+    case HCT_EPI_BF16: return launch<HCT_EPI_BF16, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_GELU_BF16: return launch<HCT_EPI_GELU_BF16, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_RES_F32: return launch<HCT_EPI_RES_F32, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_POS_F32: return launch<HCT_EPI_POS_F32, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_DGELU_BF16: return launch<HCT_EPI_DGELU_BF16, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_F32: return launch<HCT_EPI_F32, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_GELU_DERIV_BF16: return launch<HCT_EPI_GELU_DERIV_BF16, CTAS>(tmA, tmB, em, p, grid, st);
+    case HCT_EPI_MUL_BF16: return launch<HCT_EPI_MUL_BF16, CTAS>(tmA, tmB, em, p, grid, st);
+    default: return launch<HCT_EPI_ATOMIC_F32, CTAS>(tmA, tmB, em, p, grid, st);
   }
 }
 
@@ -895,10 +1077,29 @@ extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
   else rc = make_tmap(&tmB, d->B, d->N, d->K, d->ldb, 64, BK);
   if (rc != HCT_OK) return rc;
 
+  // bf16-output epilogues store (and read their bf16 multiplicand) through TMA: 32 x 32 boxes, 64-byte swizzle
+  EpiMaps em;
+  em.out = tmA; em.out2 = tmA; em.aux = tmA;
+  const bool tma_epi = d->epilogue == HCT_EPI_BF16 || d->epilogue == HCT_EPI_GELU_BF16 ||
+                       d->epilogue == HCT_EPI_GELU_DERIV_BF16 || d->epilogue == HCT_EPI_MUL_BF16;
+  if (tma_epi) {
+    HCT_REQUIRE(d->rows_in <= 0, "hct_gemm_bf16: row remapping is only available with the POS_F32 / F32 epilogues");
+    rc = make_tmap(&em.out, d->out, d->N, d->M, d->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != HCT_OK) return rc;
+    if (d->out2 != nullptr && (d->epilogue == HCT_EPI_GELU_BF16 || d->epilogue == HCT_EPI_GELU_DERIV_BF16)) {
+      rc = make_tmap(&em.out2, d->out2, d->N, d->M, d->ldo2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != HCT_OK) return rc;
+    }
+    if (d->epilogue == HCT_EPI_MUL_BF16) {
+      rc = make_tmap(&em.aux, d->aux, d->N, d->M, d->ldaux, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != HCT_OK) return rc;
+    }
+  }
+
   const int total_work = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int grid = (total_work < units ? total_work : units) * ctas;
   void* prof = hct_prof_enabled() ? hct_prof_begin(stream) : nullptr;
-  rc = ctas == 2 ? dispatch<2>(d->epilogue, tmA, tmB, p, grid, stream) : dispatch<1>(d->epilogue, tmA, tmB, p, grid, stream);
+  rc = ctas == 2 ? dispatch<2>(d->epilogue, tmA, tmB, em, p, grid, stream) : dispatch<1>(d->epilogue, tmA, tmB, em, p, grid, stream);
   if (prof != nullptr) hct_prof_end(prof, stream, 2.0 * d->M * d->N * static_cast<double>(d->K));
   return rc;
 }

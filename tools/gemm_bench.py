@@ -65,6 +65,10 @@ cases += [("pred fwd", fwd(131328, 5184, 768, HF.EPI_BF16), 131328, 5184, 768),
           ("pred wgrad", wgrad(131328, 5184, 768), 5184, 768, 131328),
           ("embed fwd", fwd(32768, 768, 5184, HF.EPI_F32), 32768, 768, 5184),
           ("embed wgrad", wgrad(32768, 768, 5184), 768, 5184, 32768)]
+_a = torch.randn(8192, 8192, device=dev).bfloat16(); _b = torch.randn(8192, 8192, device=dev).bfloat16()
+_ms = timeit(lambda: torch.matmul(_a, _b), iters=10)
+print(f"box reference: cuBLAS bf16 8192^3 {_ms:.3f} ms = {2 * 8192 ** 3 / _ms / 1e9:.0f} TFLOP/s")
+del _a, _b
 tot_ms = tot_fl = 0
 mult = {"dec": 8, "enc": 12}
 print(f"{'case':28s} {'ms':>8s} {'TFLOP/s':>9s} {'of peak':>8s}")
