@@ -327,7 +327,10 @@ def run_ours(args):
     step_model = model
     if world > 1:
         step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
-                                                               gradient_as_bucket_view=True, bucket_cap_mb=64)
+                                                               gradient_as_bucket_view=True, bucket_cap_mb=args.bucket_mb)
+        if args.grad_comm == "bf16":      # optional: halve the all-reduce payload (torch's stock bf16 compression hook)
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            step_model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     # lr scaling rule of main_pretrain_mae.py:149-152; TRAIN.* values from mae_HeadCT.yaml
     lr = 1.5e-4 * B * world / 256
     opt = FusedAdamW(params, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05, clip_grad=3.0)
@@ -478,6 +481,8 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD + (", DDP grad all-reduce" if world > 1 else ""),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "grad_comm": (args.grad_comm if world > 1 else None),
+                       "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
                        "l2_policy": "per-step inputs (%.0f MB) and activations exceed the 126 MB L2; no explicit flush"
                                     % (B * 3 * 96 ** 3 * 4 / 1e6),
                        "final_loss": final_loss,
@@ -524,6 +529,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="volumes per GPU per step (DATA.BATCH_SIZE semantics)")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-comm", choices=["fp32", "bf16"], default="fp32",
+                    help="gradient all-reduce payload: fp32 (DDP default, what the reference does) or bf16-compressed buckets")
+    ap.add_argument("--bucket-mb", type=int, default=64)
     ap.add_argument("--no-secondary", action="store_true", help="skip roofline_secondary and the DINO / fine-tune / extraction runs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
