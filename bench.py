@@ -269,15 +269,17 @@ def secondary_extract(torch, dist, H, dev, world, peak, batches=(1, 8, 64, 256))
     return {"by_batch": rows, "workload": "extract_feature: ViT-B 3D eval forward (S = 513), per-GPU batch as keyed, replicas"}
 
 
-def class_rooflines(torch, _cabi, train_step, resident, peaks, steps=2):
+def class_rooflines(torch, _cabi, train_step, resident, peaks, steps=2, window_fn=None):
     """roofline_secondary: every kernel class above ~1 % of the step, timed launch by launch with CUDA events in an extra
     (untimed for the headline) pass of `steps` steps.  Tensor classes vs the bf16 peak, the others vs HBM copy bandwidth."""
-    names = ["attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "mae_loss", "clip_adamw", "patchify"]
+    names = ["attention_fwd", "attention_bwd", "layernorm_fwd", "layernorm_bwd", "mae_loss", "clip_adamw", "patchify", "window"]
     _cabi.profile_enable(*names)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     a.record()
     for _ in range(steps):
+        if window_fn is not None:
+            window_fn()                  # HU windowing of one batch (part of the e2e path, not of the resident-input step)
         train_step(resident)
     b.record()
     torch.cuda.synchronize()
@@ -321,7 +323,8 @@ def run_ours(args):
     from headct_foundation_b200.configs import MAE_HEADCT
     cfg = dict(MAE_HEADCT)
     B = args.batch
-    torch.manual_seed(42 + rank)      # SEED + rank (main_pretrain_mae.py:213)
+    from headct_foundation_b200 import parallel
+    torch.manual_seed(parallel.rank_seed(42, rank))      # SEED + rank (main_pretrain_mae.py:213)
     model = H.MaskedAutoencoderViT(**cfg).to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
     step_model = model
@@ -332,7 +335,7 @@ def run_ours(args):
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
             step_model.register_comm_hook(None, default_hooks.bf16_compress_hook)
     # lr scaling rule of main_pretrain_mae.py:149-152; TRAIN.* values from mae_HeadCT.yaml
-    lr = 1.5e-4 * B * world / 256
+    lr = parallel.scaled_lr(1.5e-4, B, world)
     opt = FusedAdamW(params, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05, clip_grad=3.0)
 
     # ---- inputs: HU volumes on the host (pinned, int16) and their windowed fp32 form resident in HBM
@@ -436,7 +439,8 @@ def run_ours(args):
     # ---- per-class roofline fractions (extra pass, rank-local) and the secondary workloads (every rank takes part)
     peaks = _peaks()
     class_rooflines.adamw_bytes = sum(p.numel() for p in params) * (4 + 16 + 12 + 2)
-    roof2 = class_rooflines(torch, _cabi, train_step, resident, peaks) if not args.no_secondary else None
+    roof2 = (class_rooflines(torch, _cabi, train_step, resident, peaks, window_fn=lambda: window({"image": dev_hu[0]}))
+             if not args.no_secondary else None)
     h2d_bytes = int(host_hu[0].numel() * 2)
     secondary = None
     if not args.no_secondary:
@@ -457,9 +461,7 @@ def run_ours(args):
 
     # ---- max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms = parallel.max_over_ranks([ms, e2e_ms], device=dev)
         tl = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
         dist.all_reduce(tl)
         launches_all = int(tl.item())

@@ -1226,14 +1226,11 @@ class DinoLossFn(torch.autograd.Function):
 
 def center_update(center: torch.Tensor, teacher: torch.Tensor, momentum: float) -> None:
     """DINOLoss.update_center (losses.py:91-102): column sum -> all-reduce -> EMA, in place on `center`."""
-    import torch.distributed as dist
+    from . import parallel
     teacher = teacher.contiguous().float()
     K = teacher.shape[1]
-    bc = colsum(teacher, K)
-    world = 1
-    if dist.is_available() and dist.is_initialized():
-        dist.all_reduce(bc)
-        world = dist.get_world_size()
+    bc = parallel.allreduce_sum_(colsum(teacher, K))           # NCCL all-reduce(sum) of [K] fp32 between the two kernels
+    world = parallel.world()[1]
     call("hct_center_ema", center.data_ptr(), bc.data_ptr(), float(teacher.shape[0] * world), float(momentum), K,
          stream_ptr(center.device))
 

@@ -25,15 +25,14 @@ def _worker(rank, world, port, out):
     bc = torch.full((1, 8), float(rank + 1))
     P.allreduce_sum_(bc)
     res["center"] = (bc / (4 * world)).tolist()
-    # gradient mean over ranks, bucketed
+    # gradient mean over ranks through torch DDP on gloo (what main_pretrain_mae.py:139 / bench.py do on NCCL)
     torch.manual_seed(0)
-    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
-    for i, p in enumerate(params):
-        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
-    res["buckets"] = P.mean_gradients_(params, bucket_bytes=64)
-    res["grads"] = [float(p.grad.flatten()[0]) for p in params]
-    lo, hi = P.shard_bounds(11, rank, world)
-    res["shard"] = [lo, hi]
+    lin = torch.nn.Linear(5, 3)
+    ddp = torch.nn.parallel.DistributedDataParallel(lin, bucket_cap_mb=1)
+    x = torch.full((2, 5), float(rank + 1))
+    ddp(x).sum().backward()
+    res["wgrad"] = float(lin.weight.grad[0, 0])                  # d/dw sum = sum of inputs = 2 (rank + 1); mean over ranks = 3
+    res["lr"] = P.scaled_lr(1.5e-4, 256, world)
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
@@ -48,15 +47,14 @@ def test_two_rank_gloo_helpers():
     assert (r0["seed"], r1["seed"]) == (42, 43)
     assert r0["max"] == [11.0, 5.0] == r1["max"]
     assert r0["center"] == r1["center"] == [[3.0 / 8] * 8]
-    assert r0["grads"] == r1["grads"] == [1.5, 3.0, 4.5]          # mean over ranks of (rank+1)*(i+1)
-    assert r0["buckets"] == r1["buckets"] >= 2
-    assert r0["shard"] == [0, 6] and r1["shard"] == [6, 11]
+    assert r0["wgrad"] == r1["wgrad"] == 3.0                      # mean over ranks of 2 (rank + 1)
+    assert r0["lr"] == r1["lr"] == pytest.approx(3e-4)
 
 
 def test_scaled_lr_rule():
     from headct_foundation_b200 import parallel as P
     assert P.scaled_lr(1.5e-4, 256, 8) == pytest.approx(1.5e-4 * 8)
-    assert P.shard_bounds(10, 0, 1) == (0, 10)
+    assert P.world() == (0, 1) and P.max_over_ranks([1.0, 2.0]) == [1.0, 2.0]      # single process: identity
 
 
 @pytest.mark.timeout(600)
