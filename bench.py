@@ -42,12 +42,12 @@ WORKLOAD = ("MAE ViT-B 3D pretraining step (mae_HeadCT.yaml: 96^3x3 volumes, pat
 
 
 def _gemm_traffic():
-    """DRAM bytes per GEMM launch from the committed ncu pass over one step (profiles/r01_gemm_traffic.json), or None."""
+    """DRAM bytes per GEMM launch from the committed ncu pass over one step (profiles/r02_gemm_traffic.json), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")) as f:
             t = json.load(f)
         return {"bytes_per_launch": float(t["traffic_bytes_per_launch"]), "over_algorithmic": float(t["traffic_over_algorithmic"]),
-                "source": "profiles/r01_gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 248 GEMM launches of one step)"}
+                "source": "profiles/r02_gemm_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 248 GEMM launches of one step)"}
     except Exception:
         return None
 

@@ -188,8 +188,10 @@ struct EpiTraits {
   static constexpr bool gelu_fwd = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16;
   // bf16-output epilogues whose tiles leave (and whose bf16 multiplicand arrives) through TMA: see epilogue_tma_unit
   static constexpr bool tma = EPI == HCT_EPI_BF16 || EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16 ||
-                              EPI == HCT_EPI_MUL_BF16;
-  static constexpr bool tma_in = EPI == HCT_EPI_MUL_BF16;      // aux tile loaded by TMA
+                              EPI == HCT_EPI_MUL_BF16 || EPI == HCT_EPI_RES_F32;
+  static constexpr bool tma_in = EPI == HCT_EPI_MUL_BF16 || EPI == HCT_EPI_RES_F32;      // second operand tile loaded by TMA
+  // unit = 32 rows x UC columns with 64-byte rows either way: 32 bf16 or 16 fp32 (2 KiB, the same swizzle and buffers)
+  static constexpr int UC = EPI == HCT_EPI_RES_F32 ? 16 : 32;
 };
 
 // ------------------------------------------------------------------ TMA epilogue (bf16 outputs)
@@ -228,11 +230,12 @@ __device__ __forceinline__ uint32_t ld_shared_u16(uint32_t addr) {
 // the unit's 32 bias values (the same for every lane: broadcast loads), requested ahead of the accumulator wait
 template <int EPI>
 __device__ __forceinline__ void load_bias_row(const GemmParams& p, int col0, float4 (&b)[8]) {
+  constexpr int NV = EpiTraits<EPI>::UC / 4;
 #pragma unroll
   for (int j = 0; j < 8; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!EpiTraits<EPI>::uses_aux && p.bias != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < NV; ++j)
       if (col0 + 4 * j < p.N) b[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
   }
 }
@@ -270,6 +273,17 @@ __device__ __forceinline__ void epilogue_tma_unit(const GemmParams& p, uint32_t 
       x[0] *= a0.x; x[1] *= a0.y; x[2] *= a1.x; x[3] *= a1.y; x[4] *= a2.x; x[5] *= a2.y; x[6] *= a3.x; x[7] *= a3.y;
     }
     st_shared_v4(buf + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+  }
+}
+// fp32 variant (RES_F32: out = acc + bias + res, residual stream): 16 columns per unit, four 16-byte chunks of 4 floats
+__device__ __forceinline__ void epilogue_tma_unit_res(uint32_t buf, int lane, const uint32_t (&acc)[16], const float4 (&bias)[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t off = sw64(lane, j);
+    const float4 r = ld_shared_f4(buf + 2048 + off);
+    const float4 b = bias[j];
+    st_shared_v4(buf + off, __float_as_uint(__uint_as_float(acc[4 * j]) + b.x + r.x), __float_as_uint(__uint_as_float(acc[4 * j + 1]) + b.y + r.y),
+                 __float_as_uint(__uint_as_float(acc[4 * j + 2]) + b.z + r.z), __float_as_uint(__uint_as_float(acc[4 * j + 3]) + b.w + r.w));
   }
 }
 // column sums of a staged bf16 unit (as the consumer will read it): lane = column, 32 two-byte reads down the rows
@@ -547,7 +561,8 @@ template <int CTAS, int EPI>
 struct Cfg {
   // TMA epilogues with a second bf16 stream (gelu' / pre-activation out, multiplicand in) double-buffer 2 x 2 KiB per warp
   // and give up one pipeline stage for it (their GEMMs have K = 768: the ring depth matters least there)
-  static constexpr bool TWO_STREAMS = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16 || EPI == HCT_EPI_MUL_BF16;
+  static constexpr bool TWO_STREAMS = EPI == HCT_EPI_GELU_BF16 || EPI == HCT_EPI_GELU_DERIV_BF16 || EPI == HCT_EPI_MUL_BF16 ||
+                                      EPI == HCT_EPI_RES_F32;
   static constexpr int WARP_STG = TWO_STREAMS ? 2 * STG_BYTES : STG_BYTES;
   static constexpr int STAGES = (CTAS == 2 ? 6 : 4) - (TWO_STREAMS ? 1 : 0);
   static constexpr int B_ROWS = BN / CTAS;                     // B rows staged by each CTA
@@ -749,8 +764,9 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const int n0 = (tile % p.num_n_tiles) * BN, m0 = (tile / p.num_n_tiles) * TILE_M + rank * BM;
       const int row_base = m0 + q * 32;
       const int colw = n0 + half * (BN / 2);
+      constexpr int UC = T::UC;
       int nunits = 0;
-      if (row_base < p.M && colw < p.N) nunits = min(4, (p.N - colw + 31) / 32);
+      if (row_base < p.M && colw < p.N) nunits = min((BN / 2) / UC, (p.N - colw + UC - 1) / UC);
       // the multiplicand of the first unit is requested before the tile's MMAs have finished (off the chain)
       if (T::tma_in && nunits > 0 && lane == 0) {
         const uint32_t b = stg + (u & 1) * UB + 2048;
@@ -760,36 +776,37 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * (BN / 2);
-      uint32_t v[32];
-      if (nunits > 0) tmem_ld32_issue(t0, v);
+      uint32_t v[UC];
+      if (nunits > 0) { if constexpr (UC == 32) tmem_ld32_issue(t0, v); else tmem_ld16_issue(t0, v); }
 #pragma unroll 1
       for (int c = 0; c < nunits; ++c, ++u) {
         const uint32_t buf = stg + (u & 1) * UB;
-        const int col0 = colw + c * 32;
+        const int col0 = colw + c * UC;
         // the store that read this buffer two units ago must have finished reading before it is overwritten
         if (lane == 0) {
           bulk_wait_read<1>();
           if (T::tma_in && c + 1 < nunits) {              // multiplicand of the next unit: its buffer half was last read one unit ago
             const uint32_t bn = stg + ((u + 1) & 1) * UB + 2048;
             mbar_expect_tx(&my_aux_bar[(u + 1) & 1], 2048);
-            tma_load_2d(bn, &tmAux, &my_aux_bar[(u + 1) & 1], col0 + 32, row_base);
+            tma_load_2d(bn, &tmAux, &my_aux_bar[(u + 1) & 1], col0 + UC, row_base);
           }
         }
         __syncwarp();
         float4 bias[8];
         load_bias_row<EPI>(p, col0, bias);                // in flight across the accumulator wait
         tmem_ld_wait();
-        uint32_t a[32];
+        uint32_t a[UC];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a[i] = v[i];
-        if (c + 1 < nunits) {
-          tmem_ld32_issue(t0 + (c + 1) * 32, v);          // next unit's accumulators in flight under this unit's math
+        for (int i = 0; i < UC; ++i) a[i] = v[i];
+        if (c + 1 < nunits) {                             // next unit's accumulators in flight under this unit's math
+          if constexpr (UC == 32) tmem_ld32_issue(t0 + (c + 1) * UC, v); else tmem_ld16_issue(t0 + (c + 1) * UC, v);
         } else {
           tc_fence_before(); __syncwarp();
           if (lane == 0) { if (CTAS == 2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]); }
         }
         if (T::tma_in) mbar_wait(&my_aux_bar[u & 1], (u >> 1) & 1);
-        epilogue_tma_unit<EPI>(p, buf, lane, col0, a, bias);
+        if constexpr (EPI == HCT_EPI_RES_F32) epilogue_tma_unit_res(buf, lane, a, bias);
+        else epilogue_tma_unit<EPI>(p, buf, lane, col0, a, bias);
         fence_proxy_async_smem();                         // generic-proxy writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
@@ -797,7 +814,7 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (two_out) tma_store_2d(&tmOut2, buf + 2048, col0, row_base);
           bulk_commit();
         }
-        if (p.colsum != nullptr) colsum_tma_unit(p, buf, lane, row_base, col0);
+        if (UC == 32 && p.colsum != nullptr) colsum_tma_unit(p, buf, lane, row_base, col0);
         if (T::tma_in) __syncwarp();                      // every lane has read the multiplicand before its half is reloaded
       }
       if (nunits == 0) {
@@ -920,14 +937,15 @@ PFN_encodeTiled get_encode_fn() {
 
 // 2-D bf16 tensor map over a row-major [outer, inner] matrix with leading dimension ld (elements).
 int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld, int box_inner,
-              int box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+              int box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) { hct_set_error("cuTensorMapEncodeTiled entry point unavailable"); return HCT_ERR_CUDA; }
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * (dtype == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 2)};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(tm, dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1082,6 +1100,14 @@ extern "C" int hct_gemm_bf16(const hct_gemm_desc* d, hct_stream_t stream_) {
   em.out = tmA; em.out2 = tmA; em.aux = tmA;
   const bool tma_epi = d->epilogue == HCT_EPI_BF16 || d->epilogue == HCT_EPI_GELU_BF16 ||
                        d->epilogue == HCT_EPI_GELU_DERIV_BF16 || d->epilogue == HCT_EPI_MUL_BF16;
+  if (d->epilogue == HCT_EPI_RES_F32) {        // fp32 boxes of 16 columns x 32 rows (64-byte rows as well)
+    HCT_REQUIRE(d->rows_in <= 0, "hct_gemm_bf16: row remapping is only available with the POS_F32 / F32 epilogues");
+    HCT_REQUIRE((reinterpret_cast<uintptr_t>(d->res) & 15) == 0, "hct_gemm_bf16: res misaligned");
+    rc = make_tmap(&em.out, d->out, d->N, d->M, d->ldo, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    if (rc != HCT_OK) return rc;
+    rc = make_tmap(&em.aux, d->res, d->N, d->M, d->ldres, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    if (rc != HCT_OK) return rc;
+  }
   if (tma_epi) {
     HCT_REQUIRE(d->rows_in <= 0, "hct_gemm_bf16: row remapping is only available with the POS_F32 / F32 epilogues");
     rc = make_tmap(&em.out, d->out, d->N, d->M, d->ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);

@@ -144,3 +144,49 @@ def test_precision_switch_is_scoped_and_validated(cuda):
     assert H.get_precision() == "bf16"
     with pytest.raises(ValueError):
         H.set_precision("fp16")
+
+
+def test_fp32_mode_report(cuda):
+    """Measured numbers for DESIGN.md: loss error of both precision modes against the oracle run in fp32 on the same GPU
+    (full mae_HeadCT.yaml shape, batch 8) and what the fp32 mode costs in time.  Written to gpurun_out/ when that exists."""
+    import time
+    import headct_foundation_b200 as H
+    from oracle import headct_oracle as O, synth
+    cfg = synth.MAE_FULL
+    sd = synth.to_device(synth.mae_state_dict(cfg, seed=31), cuda)
+    B = 8
+    x = synth.volume(B, 3, 96, 32).to(cuda)
+    noise = synth.noise(B, 512, seed=33).to(cuda)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ref = O.mae_forward(sd, x, noise, patch=(12, 12, 12), mask_ratio=0.75, enc_heads=12, dec_heads=16, norm_pix=False)["loss"].item()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    model = H.MaskedAutoencoderViT(**cfg)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(cuda).train()
+    model.noise_override = noise
+    rep = {"batch": B, "oracle_fp32_loss": ref}
+    for mode in ("bf16", "fp32"):
+        with H.precision(mode):
+            for _ in range(2):
+                model.zero_grad(set_to_none=True)
+                loss = model(x)[0]
+                loss.backward()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                model.zero_grad(set_to_none=True)
+                loss = model(x)[0]
+                loss.backward()
+            torch.cuda.synchronize()
+            rep[mode] = {"loss": loss.item(), "rel_err": abs(loss.item() - ref) / ref, "ms_per_fwd_bwd": (time.perf_counter() - t0) / 3 * 1e3}
+    assert rep["fp32"]["rel_err"] < LOSS_TOL and rep["bf16"]["rel_err"] < 1e-2
+    rep["fp32_over_bf16_time"] = rep["fp32"]["ms_per_fwd_bwd"] / rep["bf16"]["ms_per_fwd_bwd"]
+    out = os.path.join(os.path.dirname(os.path.dirname(__file__)), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "fp32_mode_report.json"), "w") as f:
+            json.dump(rep, f, indent=1)
+    print(rep)
