@@ -79,6 +79,8 @@ _SIGNATURES = {
     "hct_attention_set_merge_tail": [_I32],
     "hct_attention_set_dkdv32": [_I32],
     "hct_attention_set_bwd3": [_I32],
+    "hct_attention_set_poly": [_I32, _I32],
+    "hct_attention_set_bwd3_drain": [_I32],
     "hct_attention_trace": [C.c_void_p],
     "hct_attention_trace3": [C.c_void_p],
     "hct_crop_resize_area": [_P, _I32, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P],

@@ -40,14 +40,19 @@ constexpr int ACC_COLS = 128;              // [0,64): dV (dQ), [64,128): dK
 constexpr int DRAIN_SLOTS = NSW, DRAIN_SLOT_BYTES = 32 * 128;   // per softmax warp: 32 rows x 64 bf16, 16-byte chunks XOR-swizzled
 constexpr int SMEM_BYTES = 2 * 2 * TILE_BYTES + STAGES * 2 * HALF_BYTES + NSW * 512 + DRAIN_SLOTS * DRAIN_SLOT_BYTES + 1024 + 512;
 
+static bool g_trace3_host = false;         // host mirror of g_trace3 != nullptr
 __device__ long long* g_trace3 = nullptr;   // event timeline of CTA 0 (tools/attn_dbg3.py); nullptr in production
-// layout: [role: 0 mma-issue, 1 mma-acc, 2 softmax group 0 (warp 0), 3 softmax group 1 (warp 8)][block gb < 64][8 events]
-#define TR3(role, gb, ev) do { if (trace && (gb) < 64) trace[((role) * 64 + (gb)) * 8 + (ev)] = clock64(); } while (0)
+// layout: [role: 0 mma-issue, 1 mma-acc, 2 softmax group 0 (warp 0), 3 softmax group 1 (warp 8)][block gb < 64][16 events]
+#define TR3(role, gb, ev) do { if (TRACE && trace && (gb) < 64) trace[((role) * 64 + (gb)) * 16 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -80,12 +85,15 @@ struct ItemIter {
   }
 };
 
-template <int HD, bool KV>
+// POLY of every 8 exponential pairs run on the FMA pipe (hct_tcgen05.cuh).  TRACE: the instrumented instantiation behind
+// hct_attention_trace3 -- compiled apart because the live trace pointer and its predicates cost the production kernel
+// registers (spilled: a local-memory load in front of every stamp).
+template <int HD, bool KV, int POLY, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
                  const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO64,
-                 const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H,
-                 int n_tiles, int n_items, float scale) {
+                 const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H,
+                 int n_tiles, int n_items, float scale, int tma_drain_ok) {
   // accumulator sets in tensor memory: the dQ pass (64 columns per set) has room for two, so an item's drain overlaps the
   // next item's MMAs; the dK/dV pass (2 x HD columns) has one and pays a short bubble per item
   extern __shared__ uint8_t smem_raw[];
@@ -111,6 +119,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   const int G = static_cast<int>(gridDim.x);
   const int nmy = (n_items - static_cast<int>(blockIdx.x) + G - 1) / G;      // items of this CTA: blockIdx.x + n * G
   const int total = nmy * nblk;                                 // its blocks, numbered gb = n * nblk + i
+  const bool tma_drain = tma_drain_ok != 0 && n_tiles * TILE <= S;                 // every tile full: results leave through TMA stores
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&done[i], 1); mbar_init(&acc_empty[i], 8); }
@@ -124,7 +133,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // KV: dV at [0,HD), dK at [64,64+HD).  !KV: dQ of accumulator set a at [64 a, 64 a + HD)
-  long long* trace = (g_trace3 != nullptr && blockIdx.x == 0 && lane == 0 && KV) ? g_trace3 : nullptr;
+  long long* trace = (TRACE && g_trace3 != nullptr && blockIdx.x == 0 && lane == 0 && KV) ? g_trace3 : nullptr;
 
   if (warp == W_PROD) {
     // ===================== TMA producer =====================
@@ -256,21 +265,33 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
 
     // accumulator drain of item m (coordinates b, h, t): done by ONE group (8 warps, two per lane quarter)
     uint32_t done_ph = 0;                              // parity of this group's next `done` phase
-    auto drain = [&](int m, int b, int h, int t) {
+    auto drain = [&](int m, int b, int h, int t, int tgb) {
       const int ab = KV ? 0 : (m & 1);
       const bool warp_active = t * TILE + q * 32 < S;
+      TR3(trole, tgb, 8);
       mbar_wait(&done[grp], done_ph);
       done_ph ^= 1u;
       tc_fence_after();
+      TR3(trole, tgb, 9);
       const bool drains = warp_active && (KV || wg == 0);
       // KV: column half 0 -> dK, 1 -> dV (HD columns each).  !KV: half 0 -> dQ
       const bool second = KV && wg == 1;
       const float sc = second ? 1.0f : scale;
       // Each thread holds one ROW; stored from registers, a warp-wide 16-byte store would touch 32 different lines.
-      // Transposed through a private swizzled staging slot, eight lanes write one row's contiguous HD x 2 bytes:
-      // 4 rows = 4 lines per instruction.
+      // The rows go through a private staging slot.  When every tile is full (n_tiles * 128 <= S: the shipped S = 128 k + 1
+      // shapes, whose last row has its own kernel) the slot is laid out as a TMA box (32 rows x HD: dense 96-byte rows for
+      // HD = 48, the 128-byte swizzle for HD = 64) and ONE lane hands it to cp.async.bulk.tensor -- the first version's
+      // per-lane LDS -> STG loop held the draining group for ~1600-2000 cycles per item (profiles/r02_attn_bwd3_timeline_v5.txt).
+      // Otherwise (a partial last tile) eight lanes write one row's contiguous HD x 2 bytes from the swizzled slot.
       uint8_t* stg = sDrain + warp * DRAIN_SLOT_BYTES;     // private: the two groups' drains of consecutive items may overlap
+      auto slot_off = [&](int row, int ch) -> int {
+        return (tma_drain && HD == 48) ? row * 96 + ch * 16 : row * 128 + ((ch ^ (row & 7)) << 4);
+      };
       if (drains) {
+        if (tma_drain) {                                   // the slot's previous box has been read by the TMA unit
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         const uint32_t src = tmem_base + (KV ? (second ? 0 : 64) : 64 * ab);
 #pragma unroll
         for (int c0 = 0; c0 < HD; c0 += 32) {            // 32 (+ 32 | + 16) columns: half the registers of one pass
@@ -285,33 +306,42 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
               u.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * sc, __uint_as_float(o[8 * c + 3]) * sc);
               u.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * sc, __uint_as_float(o[8 * c + 5]) * sc);
               u.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * sc, __uint_as_float(o[8 * c + 7]) * sc);
-              const int ch = c0 / 8 + c;
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = u;
+              *reinterpret_cast<uint4*>(stg + slot_off(lane, c0 / 8 + c)) = u;
             }
           }
         }
+        if (tma_drain) fence_proxy_async_smem();           // the staged rows become visible to the TMA unit
       }
-      // the accumulators have left tensor memory: hand the set back to the MMA issuer BEFORE the (slow, rarely executed)
-      // global-store path
+      // the accumulators have left tensor memory: hand the set back to the MMA issuer BEFORE the global-store path
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      TR3(trole, tgb, 10);
       if (drains) {
-        __syncwarp();
-        const int chunk = lane & 7, rsub = lane >> 3;
-        if (chunk < HD / 8) {
-          const int row0 = t * TILE + q * 32;
-          bf16* dst0 = dqkv + (static_cast<long long>(b) * S + row0) * (3LL * D) + h * HD + (KV ? (second ? 2 * D : D) : 0) + chunk * 8;
+        const int row0 = t * TILE + q * 32;
+        const int col = h * HD + (KV ? (second ? 2 * D : D) : 0);
+        if (tma_drain) {
+          if (lane == 0) {
+            tma_store_2d(&tmOut, smem_u32(stg), col, b * S + row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          __syncwarp();
+        } else {
+          __syncwarp();
+          const int chunk = lane & 7, rsub = lane >> 3;
+          if (chunk < HD / 8) {
+            bf16* dst0 = dqkv + (static_cast<long long>(b) * S + row0) * (3LL * D) + col + chunk * 8;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int r = k * 4 + rsub;
-            if (row0 + r < S) {
-              const uint4 v = *reinterpret_cast<const uint4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
-              *reinterpret_cast<uint4*>(dst0 + static_cast<long long>(r) * (3LL * D)) = v;
+            for (int k = 0; k < 8; ++k) {
+              const int r = k * 4 + rsub;
+              if (row0 + r < S) {
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + slot_off(r, chunk));
+                *reinterpret_cast<uint4*>(dst0 + static_cast<long long>(r) * (3LL * D)) = v;
+              }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     };
 
@@ -343,8 +373,22 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       a = lse[base + r];
       d = delta[base + r];
     };
+    // dK/dV pass: the per-column statistics of the NEXT own block travel global -> shared with cp.async (no registers: a
+    // register destination was spilled by the compiler right behind the load, which parked the warp for the whole
+    // global-load latency, ~900 cycles per block in profiles/r02_attn_bwd3_timeline_v5.txt); each lane then rewrites its
+    // own element scaled and negated.  Slot (cnt & 1) of the warp's private 2 x [lse 32 | delta 32] floats.
+    auto prefetch_stats = [&](const Pos& p, const ItemIter& it, float* slot) {
+      const long long base = (static_cast<long long>(it.b) * H + it.h) * S;
+      const int r = min(p.i * 64 + wg * 32 + lane, S - 1);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(slot + lane)), "l"(lse + base + r) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(slot + 32 + lane)), "l"(delta + base + r) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     float st_a = 0.f, st_d = 0.f;
-    if (cur.n < nmy) load_stats(cur, cit, st_a, st_d);
+    if (cur.n < nmy) {
+      if (KV) prefetch_stats(cur, cit, wstat);
+      else load_stats(cur, cit, st_a, st_d);
+    }
     int buf = grp % NBUF; uint32_t buf_ph = 0;         // buffer / use parity of block gb = grp, advanced by 2 per own block
     int cnt = 0;
     for (int gb = grp; gb < total; gb += 2, ++cnt) {
@@ -353,10 +397,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       const bool warp_active = cit.t * TILE + q * 32 < S;    // warps without a valid row only keep the barriers moving
       const uint32_t tS = tmem_base + ACC_COLS + buf * 128, tdP = tS + 64;
       float* stat = wstat + (cnt & 1) * 64;
-      const float row_a = st_a * LOG2E, row_d = st_d;        // !KV: this thread's row statistics
+      // NEGATED statistics (!KV: of this thread's row): added, not subtracted
+      const float row_a = KV ? 0.f : -st_a * LOG2E, row_d = KV ? 0.f : -st_d;
       if (KV) {
-        stat[lane] = row_a;
-        stat[32 + lane] = st_d;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        stat[lane] = -stat[lane] * LOG2E;
+        stat[32 + lane] = -stat[32 + lane];
         __syncwarp();
       }
       TR3(trole, gb, 1);
@@ -364,7 +410,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       norm(nxt, nit, false);
       TR3(trole, gb, 7);
       // one own block ahead: the global-load latency stays off the chain (dQ pass: row statistics change with the item only)
-      if (nxt.n < nmy && (KV || nxt.n != n)) load_stats(nxt, nit, st_a, st_d);
+      if (nxt.n < nmy) {
+        if (KV) prefetch_stats(nxt, nit, wstat + ((cnt + 1) & 1) * 64);
+        else if (nxt.n != n) load_stats(nxt, nit, st_a, st_d);
+      }
       TR3(trole, gb, 2);
       mbar_wait(&s_full[buf], buf_ph);
       TR3(trole, gb, 3);
@@ -381,10 +430,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
           for (int e = 0; e < 16; e += 2) {
             const float a0 = KV ? stat[e] : row_a, a1 = KV ? stat[e + 1] : row_a;
             const float d0 = KV ? stat[32 + e] : row_d, d1 = KV ? stat[32 + e + 1] : row_d;
-            const float p0 = e < ncol ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, -a0)) : 0.f;
-            const float p1 = e + 1 < ncol ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -a1)) : 0.f;
+            const float p0 = e < ncol ? ex2f(fmaf(__uint_as_float(sv[e]), sl2, a0)) : 0.f;
+            const float p1 = e + 1 < ncol ? ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, a1)) : 0.f;
             pk[e >> 1] = pack_bf16x2(p0, p1);
-            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - d0), p1 * (__uint_as_float(dv[e + 1]) - d1));
+            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) + d0), p1 * (__uint_as_float(dv[e + 1]) + d1));
           }
 #pragma unroll
           for (int e = 8; e < 16; ++e) { pk[e] = 0u; dk[e] = 0u; }
@@ -399,6 +448,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
             for (int e = 0; e < 32; ++e)
               if (e >= lim) sv[e] = 0xff800000u;             // exp2(-inf) = 0: P and dS vanish outside the problem
           }
+          const float2 sl2v = make_float2(sl2, sl2);
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             float4 ls, dl;
@@ -409,16 +459,17 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
               ls = make_float4(row_a, row_a, row_a, row_a);
               dl = make_float4(row_d, row_d, row_d, row_d);
             }
-            const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, -ls.x));
-            const float p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, -ls.y));
-            const float p2 = ex2f(fmaf(__uint_as_float(sv[e + 2]), sl2, -ls.z));
-            const float p3 = ex2f(fmaf(__uint_as_float(sv[e + 3]), sl2, -ls.w));
+            // packed fp32: one issue slot per two elements for the shift, the (dP - delta) and the product
+            const float2 p01 = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, make_float2(ls.x, ls.y)), e >> 1);
+            const float2 p23 = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sl2v, make_float2(ls.z, ls.w)), (e >> 1) + 1);
             if (KV) {
-              pk[e >> 1] = pack_bf16x2(p0, p1);
-              pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+              pk[e >> 1] = pack_bf16x2(p01.x, p01.y);
+              pk[(e >> 1) + 1] = pack_bf16x2(p23.x, p23.y);
             }
-            dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) - dl.x), p1 * (__uint_as_float(dv[e + 1]) - dl.y));
-            dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) - dl.z), p3 * (__uint_as_float(dv[e + 3]) - dl.w));
+            const float2 d01 = __fmul2_rn(p01, __fadd2_rn(make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])), make_float2(dl.x, dl.y)));
+            const float2 d23 = __fmul2_rn(p23, __fadd2_rn(make_float2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), make_float2(dl.z, dl.w)));
+            dk[e >> 1] = pack_bf16x2(d01.x, d01.y);
+            dk[(e >> 1) + 1] = pack_bf16x2(d23.x, d23.y);
           }
         }
         TR3(trole, gb, 4);
@@ -433,7 +484,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       TR3(trole, gb, 5);
       // The group that owns the FIRST block of an item drains the previous item, after that block: its operands are in
       // place, so the accumulate issuer is held up by the drain alone (dK/dV pass) or not at all (dQ pass, two sets).
-      if (i == 0 && n > 0) drain(n - 1, pb, ph_, pt);
+      if (i == 0 && n > 0) drain(n - 1, pb, ph_, pt, gb);
       TR3(trole, gb, 6);
       cur.i += 2;
       norm(cur, cit, true);
@@ -445,8 +496,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
       // advanced, so recompute from scratch (once per kernel)
       ItemIter lit(static_cast<int>(blockIdx.x), G, n_tiles, H);
       for (int k = 0; k < nmy - 1; ++k) lit.next();
-      drain(nmy - 1, lit.b, lit.h, lit.t);
+      drain(nmy - 1, lit.b, lit.h, lit.t, 63);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged boxes outlive the CTA otherwise
   }
 
   tc_fence_before();
@@ -454,11 +506,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
-template <int HD, bool KV>
+int g_bwd3_tma_drain = 1;   // 0: results leave through the per-lane store loop (A/B, hct_attention_set_bwd3_drain)
+template <int HD, bool KV, int POLY, bool TRACE = false>
 int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensorMap& q64, const CUtensorMap& do64,
-               const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, int n_tiles, cudaStream_t st) {
+               const CUtensorMap& out, const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, int n_tiles, cudaStream_t st) {
   static bool cfg = false;
-  auto kernel = attn_bwd3_kernel<HD, KV>;
+  auto kernel = attn_bwd3_kernel<HD, KV, POLY, TRACE>;
   if (!cfg) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) { hct_set_error("cudaFuncSetAttribute(attn_bwd3): %s", cudaGetErrorString(e)); return HCT_ERR_CUDA; }
@@ -469,15 +522,33 @@ int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensor
   const int sms = hct_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
-  kernel<<<grid, THREADS, SMEM_BYTES, st>>>(q128, do128, q64, do64, lse, delta, dqkv, S, H, n_tiles, static_cast<int>(items), scale);
+  kernel<<<grid, THREADS, SMEM_BYTES, st>>>(q128, do128, q64, do64, out, lse, delta, dqkv, S, H, n_tiles, static_cast<int>(items), scale, g_bwd3_tma_drain);
   return hct_check_launch(KV ? "attn_bwd3_kernel<dK/dV>" : "attn_bwd3_kernel<dQ>");
 }
 
 }  // namespace
 
-extern "C" int hct_attention_trace3(void* buf) {      // device buffer of >= 4 * 64 * 8 int64 (or NULL): bwd3 dK/dV timeline
+extern "C" int hct_attention_set_bwd3_drain(int tma) { g_bwd3_tma_drain = tma != 0; return HCT_OK; }
+extern "C" int hct_attention_trace3(void* buf) {      // device buffer of >= 4 * 64 * 16 int64 (or NULL): bwd3 dK/dV timeline
   long long* p = static_cast<long long*>(buf);
+  g_trace3_host = p != nullptr;                      // hd = 48 dK/dV pass runs its instrumented instantiation while set
   return cudaMemcpyToSymbol(g_trace3, &p, sizeof(p)) == cudaSuccess ? HCT_OK : HCT_ERR_CUDA;
+}
+
+static int g_bwd3_poly = 0;      // exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
+int hct_attention_bwd3_set_poly(int n) { g_bwd3_poly = n; return HCT_OK; }
+template <int POLY>
+static int launch_both(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensorMap& q64, const CUtensorMap& do64,
+                       const CUtensorMap& out, const float* lse, const float* delta, bf16* dq, int B, int S, int H, int hd, int n_tiles, cudaStream_t st) {
+  int rc;
+  if (hd == 64) {
+    rc = launch_one<64, true, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st); if (rc) return rc;
+    return launch_one<64, false, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
+  }
+  if (POLY == 0 && g_trace3_host) rc = launch_one<48, true, 0, true>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
+  else rc = launch_one<48, true, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
+  if (rc) return rc;
+  return launch_one<48, false, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
 }
 
 // n_tiles full 128-row tiles per (batch, head) on tcgen05 (rows behind them: hct_attention_tail.cu)
@@ -490,11 +561,10 @@ int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, cons
   rc = hct_make_tmap_bf16_2d(&q64, qkv, D3, rows, D3, 64, 64); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&do128, dout, D, rows, D, 64, TILE); if (rc) return rc;
   rc = hct_make_tmap_bf16_2d(&do64, dout, D, rows, D, 64, 64); if (rc) return rc;
+  // results: 32-row x hd boxes of dqkv (dense rows for hd = 48, 128-byte swizzle for hd = 64)
+  CUtensorMap out;
+  rc = hct_make_tmap_bf16_2d_sw(&out, dqkv, D3, rows, D3, hd, 32, hd == 64 ? 1 : 0); if (rc) return rc;
   bf16* dq = static_cast<bf16*>(dqkv);
-  if (hd == 64) {
-    rc = launch_one<64, true>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st); if (rc) return rc;
-    return launch_one<64, false>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st);
-  }
-  rc = launch_one<48, true>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st); if (rc) return rc;
-  return launch_one<48, false>(q128, do128, q64, do64, lse, delta, dq, B, S, H, n_tiles, st);
+  return g_bwd3_poly == 0 ? launch_both<0>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st)
+                          : launch_both<2>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st);
 }

@@ -47,7 +47,7 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 //                   over the first 32 of the 64 fp32 columns the thread has just read (tcgen05.st), O rescaled in TMEM
 //                   when the running max moves, final O / l and log-sum-exp written out.
 // S, P and O never leave the SM; P never touches shared memory.
-template <int HD>
+template <int HD, int POLY>   // POLY of every 8 exponential pairs run on the FMA pipe (hct_tcgen05.cuh)
 __global__ void __launch_bounds__(FWD_THREADS, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                    bf16* __restrict__ out, float* __restrict__ lse, int S, int H, float scale) {
@@ -231,18 +231,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           const float alpha = move_max(j, mb);
           const float msc = m * sl2;
-          float rs0 = 0.f, rs1 = 0.f;
+          // packed fp32 (one issue slot per two elements) for scale-and-shift and row sums
+          const float2 sl2v = make_float2(sl2, sl2), nmsc = make_float2(-msc, -msc);
+          float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
           uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float a0 = ex2f(fmaf(__uint_as_float(v0[i]), sl2, -msc)), a1 = ex2f(fmaf(__uint_as_float(v0[i + 1]), sl2, -msc));
-            const float b0 = ex2f(fmaf(__uint_as_float(v1[i]), sl2, -msc)), b1 = ex2f(fmaf(__uint_as_float(v1[i + 1]), sl2, -msc));
-            rs0 += a0 + a1;
-            rs1 += b0 + b1;
-            pk[i >> 1] = pack_bf16x2(a0, a1);
-            pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
+            const float2 a = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])), sl2v, nmsc), i >> 1);
+            const float2 c = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1])), sl2v, nmsc), (i >> 1) + 4);
+            rs0 = __fadd2_rn(rs0, a);
+            rs1 = __fadd2_rn(rs1, c);
+            pk[i >> 1] = pack_bf16x2(a.x, a.y);
+            pk[16 + (i >> 1)] = pack_bf16x2(c.x, c.y);
           }
-          l = l * alpha + (rs0 + rs1);
+          l = l * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
           if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
           tmem_st32(tmem_S + lane_off, pk);                   // keys 2c, 2c+1 -> column c: the A operand of P_j V_j
         }
@@ -1084,6 +1086,27 @@ int hct_attn_tc_tiles(int S, int tail_on_mma_sync) {
   return (S + TILE - 1) / TILE;
 }
 
+static int g_fwd_poly = 0;       // exponential pairs of every 8 evaluated on the FMA pipe by the forward (0, 2, 3, 4)
+int hct_attention_bwd3_set_poly(int n);
+extern "C" int hct_attention_set_poly(int fwd, int bwd) {
+  if (fwd >= 0) g_fwd_poly = fwd;
+  if (bwd >= 0) hct_attention_bwd3_set_poly(bwd);
+  return HCT_OK;
+}
+template <int POLY>
+static int launch_fwd_tc(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* out, float* lse, int S, int H, int hd, float scale,
+                         dim3 grid, cudaStream_t st) {
+  static bool cfg = false;
+  if (!cfg) {
+    int rc = set_smem(attn_fwd_tc_kernel<64, POLY>, FWD_SMEM); if (rc) return rc;
+    rc = set_smem(attn_fwd_tc_kernel<48, POLY>, FWD_SMEM); if (rc) return rc;
+    cfg = true;
+  }
+  if (hd == 64) attn_fwd_tc_kernel<64, POLY><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
+  else attn_fwd_tc_kernel<48, POLY><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
+  return HCT_OK;
+}
+
 int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles,
                          cudaStream_t st) {
   CUtensorMap tmq, tmkv;
@@ -1094,15 +1117,11 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
   if (rc != HCT_OK) return rc;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   dim3 grid(n_tiles, H, B);
-  if (hd == 64) {
-    static bool cfg = false;
-    if (!cfg) { rc = set_smem(attn_fwd_tc_kernel<64>, FWD_SMEM); if (rc) return rc; cfg = true; }
-    attn_fwd_tc_kernel<64><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
-  } else {
-    static bool cfg = false;
-    if (!cfg) { rc = set_smem(attn_fwd_tc_kernel<48>, FWD_SMEM); if (rc) return rc; cfg = true; }
-    attn_fwd_tc_kernel<48><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
-  }
+  rc = g_fwd_poly == 0   ? launch_fwd_tc<0>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
+       : g_fwd_poly == 2 ? launch_fwd_tc<2>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
+       : g_fwd_poly == 4 ? launch_fwd_tc<4>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
+                         : launch_fwd_tc<3>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st);
+  if (rc) return rc;
   return hct_check_launch("attn_fwd_tc_kernel");
 }
 

@@ -1006,6 +1006,12 @@ int hct_make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long inner, lo
   return make_tmap(tm, base, inner, outer, ld_elems, box_inner, box_outer);
 }
 
+int hct_make_tmap_bf16_2d_sw(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld_elems,
+                             int box_inner, int box_outer, int swizzle128) {
+  return make_tmap(tm, base, inner, outer, ld_elems, box_inner, box_outer,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
 extern "C" int hct_gemm_set_cta_pair(int enable) { g_gemm_ctas = enable ? 2 : 1; return HCT_OK; }
 extern "C" int hct_gemm_trace(void* buf) {     // device buffer of >= 1536 int64 (or NULL): timeline of CTA 0
   long long* p = static_cast<long long*>(buf);

@@ -184,8 +184,54 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, bool a_mn, boo
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+
+// ------------------------------------------------------------------ softmax arithmetic of the attention kernels
+// The softmax threads of the attention kernels are bound by issue slots and by the MUFU pipe (16 ex2 per clock per SM
+// against 128 fp32 lanes), not by the tensor core.  Two levers, both used by the forward and the pipelined backward:
+//  * the packed two-lane fp32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2): one issue slot per TWO elements for the
+//    scale-and-shift, the row sums and the dS product;
+//  * a share of the exponentials evaluated on the FMA pipe instead of MUFU (Cody-Waite split + degree-3 minimax polynomial
+//    of 2^f on [-0.5, 0.5], relative error 7.5e-5 -- 50x below the bf16 rounding of the probabilities it feeds).
+__device__ __forceinline__ float ex2_approx_ftz(float x) {   // bare MUFU.EX2; ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 ex2_mufu2(float2 x) { return make_float2(ex2_approx_ftz(x.x), ex2_approx_ftz(x.y)); }
+// 2^x for a pair, no MUFU: x = n + f with n = round(x) taken from the low mantissa bits of x + 1.5 * 2^23, 2^f by a
+// polynomial, n added to the exponent field (as_int(r) << 23 drops the magic constant's bits).  Inputs below -126 (and
+// -inf) are clamped: the result is <= 2^-126, i.e. zero for every consumer here.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  constexpr float kMagic = 12582912.0f;
+  constexpr float c0 = 0.9999280571937561f, c1 = 0.6932609677314758f, c2 = 0.2426111251115799f, c3 = 0.0551716685295105f;
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 r = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 n = __fadd2_rn(r, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(make_float2(c3, c3), f, make_float2(c2, c2));
+  p = __ffma2_rn(p, f, make_float2(c1, c1));
+  p = __ffma2_rn(p, f, make_float2(c0, c0));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+  y.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+  return y;
+}
+// pair `pi` of a row goes to the polynomial when POLY of every 8 pairs do (evenly spread)
+template <int POLY>
+__device__ __forceinline__ constexpr bool ex2_pair_on_fma(int pi) {
+  return ((pi & 7) + 1) * POLY / 8 != (pi & 7) * POLY / 8;
+}
+template <int POLY>
+__device__ __forceinline__ float2 ex2_pair(float2 x, int pi) {
+  return ex2_pair_on_fma<POLY>(pi) ? ex2_poly2(x) : ex2_mufu2(x);
+}
+
 }  // namespace hct_tc
 
 // host: 2-D bf16 tensor map over a row-major [outer, inner] matrix, 128B swizzle (defined in hct_gemm_sm100.cu)
 int hct_make_tmap_bf16_2d(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld_elems,
                           int box_inner, int box_outer);
+// same with the swizzle chosen: 1 = 128-byte swizzle, 0 = none (dense box rows)
+int hct_make_tmap_bf16_2d_sw(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld_elems,
+                             int box_inner, int box_outer, int swizzle128);

@@ -214,7 +214,15 @@ int hct_attention_set_dkdv32(int enable);
 /* 1: backward on the pipelined persistent kernels of hct_attention_bwd3.cu (one CTA per SM, three score-buffer pairs in
  * tensor memory, two softmax warp groups); 0: the two-CTA-per-SM kernels.  Same results either way. */
 int hct_attention_set_bwd3(int enable);
-/* debugging aid: clock64 timeline of CTA 0 of the bwd3 dK/dV kernel into a device buffer of >= 2048 int64 (NULL = off) */
+/* How many of every 8 exponential pairs the softmax threads of the tcgen05 forward (fwd) and of the pipelined backward
+ * (bwd) evaluate on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error 7.5e-5) instead of MUFU.EX2:
+ * 0, 2, 3 (default) or 4; a negative value leaves that setting unchanged.  A throughput knob: probabilities are rounded
+ * to bf16 (2^-9) right after, so results agree to that rounding. */
+int hct_attention_set_poly(int fwd, int bwd);
+/* 1 (default): the pipelined backward hands its dQ / dK / dV tiles to cp.async.bulk.tensor stores (when every 128-row tile
+ * is full); 0: per-lane store loop (A/B comparison).  Same results. */
+int hct_attention_set_bwd3_drain(int tma);
+/* debugging aid: clock64 timeline of CTA 0 of the bwd3 dK/dV kernel into a device buffer of >= 4096 int64 (NULL = off) */
 int hct_attention_trace3(void* buf);
 /* dqkv bf16 same layout as qkv.  delta_ws: fp32 workspace [B, H, S]. */
 /* Diagnostics: clock64 event timeline of one CTA of the dK/dV backward kernel.  buf = device buffer of >= 768 int64

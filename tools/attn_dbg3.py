@@ -16,14 +16,14 @@ def bwd():
     call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), delta.data_ptr(), B, S, H, hd, st)
 for _ in range(2): bwd()
 torch.cuda.synchronize()
-tr = torch.zeros(4 * 64 * 8, dtype=torch.int64, device=dev)
+tr = torch.zeros(4 * 64 * 16, dtype=torch.int64, device=dev)
 lib().hct_attention_trace3(tr.data_ptr())
 bwd(); torch.cuda.synchronize()
 lib().hct_attention_trace3(None)
-t = tr.cpu().view(4, 64, 8)
+t = tr.cpu().view(4, 64, 16)
 t0 = int(t[t > 0].min())
 names = {0: ["issue: start", "tiles+buffer ready", "S/dP issued"], 1: ["acc: wait p_full", "got", "acc_empty ok", "acc issued"],
-         2: ["top", "stats stored", "pre-wait", "s_full", "computed", "arrived", "drained", "nxt pos"], 3: ["top", "stats stored", "pre-wait", "s_full", "computed", "arrived", "drained", "nxt pos"]}
+         2: ["top", "stats stored", "pre-wait", "s_full", "computed", "arrived", "drained", "nxt pos", "drain: top", "done ok", "acc_empty arrived"], 3: ["top", "stats stored", "pre-wait", "s_full", "computed", "arrived", "drained", "nxt pos", "drain: top", "done ok", "acc_empty arrived"]}
 for role, rn in enumerate(["mma S/dP issue", "mma accumulate", "softmax group 0 (warp 0)", "softmax group 1 (warp 8)"]):
     print(f"-- {rn}: " + " | ".join(names[role]))
     for i in range(30):
