@@ -459,9 +459,19 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
               ls = make_float4(row_a, row_a, row_a, row_a);
               dl = make_float4(row_d, row_d, row_d, row_d);
             }
+            if constexpr (POLY < 0) {     // scalar fp32 arithmetic (A/B)
+              const float p0 = ex2f(fmaf(__uint_as_float(sv[e]), sl2, ls.x)), p1 = ex2f(fmaf(__uint_as_float(sv[e + 1]), sl2, ls.y));
+              const float p2 = ex2f(fmaf(__uint_as_float(sv[e + 2]), sl2, ls.z)), p3 = ex2f(fmaf(__uint_as_float(sv[e + 3]), sl2, ls.w));
+              if (KV) {
+                pk[e >> 1] = pack_bf16x2(p0, p1);
+                pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+              }
+              dk[e >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[e]) + dl.x), p1 * (__uint_as_float(dv[e + 1]) + dl.y));
+              dk[(e >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[e + 2]) + dl.z), p3 * (__uint_as_float(dv[e + 3]) + dl.w));
+            } else {
             // packed fp32: one issue slot per two elements for the shift, the (dP - delta) and the product
-            const float2 p01 = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, make_float2(ls.x, ls.y)), e >> 1);
-            const float2 p23 = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sl2v, make_float2(ls.z, ls.w)), (e >> 1) + 1);
+            const float2 p01 = ex2_pair<(POLY < 0 ? 0 : POLY)>(__ffma2_rn(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2v, make_float2(ls.x, ls.y)), e >> 1);
+            const float2 p23 = ex2_pair<(POLY < 0 ? 0 : POLY)>(__ffma2_rn(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sl2v, make_float2(ls.z, ls.w)), (e >> 1) + 1);
             if (KV) {
               pk[e >> 1] = pack_bf16x2(p01.x, p01.y);
               pk[(e >> 1) + 1] = pack_bf16x2(p23.x, p23.y);
@@ -470,6 +480,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
             const float2 d23 = __fmul2_rn(p23, __fadd2_rn(make_float2(__uint_as_float(dv[e + 2]), __uint_as_float(dv[e + 3])), make_float2(dl.z, dl.w)));
             dk[e >> 1] = pack_bf16x2(d01.x, d01.y);
             dk[(e >> 1) + 1] = pack_bf16x2(d23.x, d23.y);
+            }
           }
         }
         TR3(trole, gb, 4);
@@ -535,7 +546,7 @@ extern "C" int hct_attention_trace3(void* buf) {      // device buffer of >= 4 *
   return cudaMemcpyToSymbol(g_trace3, &p, sizeof(p)) == cudaSuccess ? HCT_OK : HCT_ERR_CUDA;
 }
 
-static int g_bwd3_poly = 0;      // exponential pairs of every 8 evaluated on the FMA pipe (0, 2, 3, 4)
+static int g_bwd3_poly = 0;      // -1: scalar fp32; 0 (default): packed fp32; 2: packed + 2 of 8 exponential pairs on the FMA pipe
 int hct_attention_bwd3_set_poly(int n) { g_bwd3_poly = n; return HCT_OK; }
 template <int POLY>
 static int launch_both(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensorMap& q64, const CUtensorMap& do64,
@@ -565,6 +576,7 @@ int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, cons
   CUtensorMap out;
   rc = hct_make_tmap_bf16_2d_sw(&out, dqkv, D3, rows, D3, hd, 32, hd == 64 ? 1 : 0); if (rc) return rc;
   bf16* dq = static_cast<bf16*>(dqkv);
-  return g_bwd3_poly == 0 ? launch_both<0>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st)
-                          : launch_both<2>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st);
+  return g_bwd3_poly == 0   ? launch_both<0>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st)
+         : g_bwd3_poly == 2 ? launch_both<2>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st)
+                            : launch_both<-1>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st);
 }

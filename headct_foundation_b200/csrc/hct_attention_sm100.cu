@@ -210,7 +210,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
           tmem_st16(tmem_S + lane_off, pk);
         } else {
-          // ---- full 64-column block (a partial one is padded with -inf first)
+          if constexpr (POLY < 0) {
+          // ---- full 64-column block (a partial one is padded with -inf first): scalar fp32, one pass
           uint32_t v0[32], v1[32];
           tmem_ld32_issue(tmem_S + lane_off, v0);
           tmem_ld32_issue(tmem_S + lane_off + 32, v1);
@@ -231,23 +232,71 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
           const float alpha = move_max(j, mb);
           const float msc = m * sl2;
-          // packed fp32 (one issue slot per two elements) for scale-and-shift and row sums
-          const float2 sl2v = make_float2(sl2, sl2), nmsc = make_float2(-msc, -msc);
-          float2 rs0 = make_float2(0.f, 0.f), rs1 = make_float2(0.f, 0.f);
+          float rs0 = 0.f, rs1 = 0.f;
           uint32_t pk[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float2 a = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])), sl2v, nmsc), i >> 1);
-            const float2 c = ex2_pair<POLY>(__ffma2_rn(make_float2(__uint_as_float(v1[i]), __uint_as_float(v1[i + 1])), sl2v, nmsc), (i >> 1) + 4);
-            rs0 = __fadd2_rn(rs0, a);
-            rs1 = __fadd2_rn(rs1, c);
-            pk[i >> 1] = pack_bf16x2(a.x, a.y);
-            pk[16 + (i >> 1)] = pack_bf16x2(c.x, c.y);
+            const float a0 = ex2f(fmaf(__uint_as_float(v0[i]), sl2, -msc)), a1 = ex2f(fmaf(__uint_as_float(v0[i + 1]), sl2, -msc));
+            const float b0 = ex2f(fmaf(__uint_as_float(v1[i]), sl2, -msc)), b1 = ex2f(fmaf(__uint_as_float(v1[i + 1]), sl2, -msc));
+            rs0 += a0 + a1;
+            rs1 += b0 + b1;
+            pk[i >> 1] = pack_bf16x2(a0, a1);
+            pk[16 + (i >> 1)] = pack_bf16x2(b0, b1);
           }
-          l = l * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
+          l = l * alpha + (rs0 + rs1);
           if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
           tmem_st32(tmem_S + lane_off, pk);                   // keys 2c, 2c+1 -> column c: the A operand of P_j V_j
+          } else {
+          // ---- full 64-column block (a partial one is padded with -inf first).  Two passes over the row's scores: the
+          // maximum first, then the exponentials 32 columns at a time -- re-reading tensor memory is cheaper than holding 64
+          // scores plus the packed-pair temporaries in 80 registers (the one-pass form spilled, 0.505 -> 0.58 ms).
+          float mb;
+          {
+            uint32_t v0[32], v1[32];
+            tmem_ld32_issue(tmem_S + lane_off, v0);
+            tmem_ld32_issue(tmem_S + lane_off + 32, v1);
+            tmem_ld_wait();
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float x0 = i + t < nvalid ? __uint_as_float(v0[i + t]) : -INFINITY;
+                const float x1 = i + t + 32 < nvalid ? __uint_as_float(v1[i + t]) : -INFINITY;
+                mx[t] = fmaxf(mx[t], fmaxf(x0, x1));
+              }
+            }
+            mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          }
+          const float alpha = move_max(j, mb);
+          const float msc = m * sl2;
+          // packed fp32 (one issue slot per two elements) for scale-and-shift and row sums
+          const float2 sl2v = make_float2(sl2, sl2), nmsc = make_float2(-msc, -msc);
+          float2 rs = make_float2(0.f, 0.f);
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t v[32], pk[16];
+            tmem_ld32(tmem_S + lane_off + hf * 32, v);
+            const int lim = nvalid - hf * 32;
+            if (lim < 32) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i >= lim) v[i] = 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float2 a = ex2_pair<(POLY < 0 ? 0 : POLY)>(__ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sl2v, nmsc), i >> 1);
+              rs = __fadd2_rn(rs, a);
+              pk[i >> 1] = pack_bf16x2(a.x, a.y);
+            }
+            // keys 2c, 2c+1 -> column c: the A operand of P_j V_j.  Half 0 lands in columns [0,16) (scores it has read),
+            // half 1 in [16,32); the second half's scores sit in columns [32,64), untouched by either store
+            tmem_st16(tmem_S + lane_off + hf * 16, pk);
+          }
+          l = l * alpha + (rs.x + rs.y);
+          if (j > 0 && !__all_sync(0xffffffffu, alpha == 1.0f)) rescale_o(alpha);
         }
+          }
         tmem_st_wait();
       }
       tc_fence_before();
@@ -1086,11 +1135,11 @@ int hct_attn_tc_tiles(int S, int tail_on_mma_sync) {
   return (S + TILE - 1) / TILE;
 }
 
-static int g_fwd_poly = 0;       // exponential pairs of every 8 evaluated on the FMA pipe by the forward (0, 2, 3, 4)
+static int g_fwd_poly = -1;      // forward softmax arithmetic: -1 scalar fp32, one pass (default: measured fastest, 0.516 vs 0.577 ms); 0 / 3: packed fp32, two passes, 0 or 3 of 8 exponential pairs on the FMA pipe
 int hct_attention_bwd3_set_poly(int n);
-extern "C" int hct_attention_set_poly(int fwd, int bwd) {
-  if (fwd >= 0) g_fwd_poly = fwd;
-  if (bwd >= 0) hct_attention_bwd3_set_poly(bwd);
+extern "C" int hct_attention_set_poly(int fwd, int bwd) {     // -1: scalar fp32 arithmetic; -2: leave unchanged
+  if (fwd >= -1) g_fwd_poly = fwd;
+  if (bwd >= -1) hct_attention_bwd3_set_poly(bwd);
   return HCT_OK;
 }
 template <int POLY>
@@ -1118,9 +1167,8 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   dim3 grid(n_tiles, H, B);
   rc = g_fwd_poly == 0   ? launch_fwd_tc<0>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
-       : g_fwd_poly == 2 ? launch_fwd_tc<2>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
-       : g_fwd_poly == 4 ? launch_fwd_tc<4>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
-                         : launch_fwd_tc<3>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st);
+       : g_fwd_poly == 3 ? launch_fwd_tc<3>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
+                         : launch_fwd_tc<-1>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st);
   if (rc) return rc;
   return hct_check_launch("attn_fwd_tc_kernel");
 }

@@ -39,8 +39,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+#ifdef HCT_MBAR_DEBUG   // the printf call costs every waiting role an ABI call site (registers, stack, no setmaxnreg below ~96)
         printf("hct: mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x,
                parity);
+#endif
         __trap();
       }
     }

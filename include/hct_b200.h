@@ -214,10 +214,11 @@ int hct_attention_set_dkdv32(int enable);
 /* 1: backward on the pipelined persistent kernels of hct_attention_bwd3.cu (one CTA per SM, three score-buffer pairs in
  * tensor memory, two softmax warp groups); 0: the two-CTA-per-SM kernels.  Same results either way. */
 int hct_attention_set_bwd3(int enable);
-/* How many of every 8 exponential pairs the softmax threads of the tcgen05 forward (fwd) and of the pipelined backward
- * (bwd) evaluate on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error 7.5e-5) instead of MUFU.EX2:
- * 0, 2, 3 (default) or 4; a negative value leaves that setting unchanged.  A throughput knob: probabilities are rounded
- * to bf16 (2^-9) right after, so results agree to that rounding. */
+/* Softmax arithmetic of the tcgen05 forward (fwd) and of the pipelined backward (bwd): -1 = scalar fp32; 0 = the packed
+ * two-lane fp32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2); n > 0 = packed, and n of every 8 exponential pairs evaluated
+ * on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error 7.5e-5) instead of MUFU.EX2 (fwd: 3, bwd: 2);
+ * -2 leaves a setting unchanged.  Defaults are the measured fastest: fwd -1, bwd 0 (profiles/r02_attn_softmax_ab_v2.txt).
+ * A throughput knob: probabilities are rounded to bf16 (2^-9) right after, so results agree to that rounding. */
 int hct_attention_set_poly(int fwd, int bwd);
 /* 1 (default): the pipelined backward hands its dQ / dK / dV tiles to cp.async.bulk.tensor stores (when every 128-row tile
  * is full); 0: per-lane store loop (A/B comparison).  Same results. */

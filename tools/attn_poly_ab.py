@@ -49,8 +49,8 @@ for name, (B, S, H, hd) in shapes.items():
                                 dqkv.data_ptr(), delta.data_ptr(), B, S, H, hd, st))
     lib().hct_attention_set_bwd3(1)
     print(f"{name}: two-kernel backward {b_old:.3f} ms (reference)")
-    for poly, tma in ((0, 0), (0, 1), (2, 1)):
-        lib().hct_attention_set_poly(0, poly)
+    for poly, tma in ((-1, 1), (0, 1), (3, 1), (-1, 1), (0, 1)):
+        lib().hct_attention_set_poly(poly, min(poly, 0))
         lib().hct_attention_set_bwd3_drain(tma)
         f = timeit(lambda: call("hct_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, hd, st))
         b = timeit(lambda: call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(),
@@ -58,5 +58,5 @@ for name, (B, S, H, hd) in shapes.items():
         torch.cuda.synchronize()
         eo = ((out[:4].float() - o_ref).norm() / o_ref.norm()).item()
         ed = ((dqkv[:4].float() - d_ref).norm() / d_ref.norm()).item()
-        print(f"{name} B={B} S={S} H={H} hd={hd} poly {poly}/8 tma-drain {tma}: fwd {f:.3f} ms  bwd {b:.3f} ms ({b / b_old:.3f} of the reference)   rel L2 err out {eo:.2e} dqkv {ed:.2e}", flush=True)
-lib().hct_attention_set_poly(0, 0)
+        print(f"{name} B={B} S={S} H={H} hd={hd} fwd poly {poly}/8, bwd {min(poly, 0)}: fwd {f:.3f} ms  bwd {b:.3f} ms ({b / b_old:.3f} of the reference)   rel L2 err out {eo:.2e} dqkv {ed:.2e}", flush=True)
+lib().hct_attention_set_poly(-1, 0); lib().hct_attention_set_bwd3_drain(1)
