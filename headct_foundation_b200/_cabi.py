@@ -63,6 +63,7 @@ _SIGNATURES = {
     "hct_gelu_bwd": [_P, _P, _P, _I64, _P],
     "hct_attention_fwd": [_P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "hct_attention_bwd": [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
+    "hct_attention_bwd_bias": [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P],
     "hct_l2norm_fwd": [_P, _I32, _P, _P, _I64, _I32, _P],
     "hct_l2norm_bwd": [_P, _P, _P, _P, _I64, _I32, _P],
     "hct_weightnorm_fwd": [_P, _P, _P, _P, _I64, _I32, _P],

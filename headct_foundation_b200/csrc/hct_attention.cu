@@ -566,10 +566,10 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
 int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
                          int H, int hd, int n_tiles, cudaStream_t st);
 // row kernel for the one row behind the last full tile in the backward (S = 128 k + 1; hct_attention_tail.cu)
-int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S, int H,
+int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* colsum, int B, int S, int H,
                        int hd, int n_tiles, cudaStream_t st);
 bool hct_attention_bwd_tail_supported(int S, int hd, int r0);
-int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
+int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* colsum, int B, int S,
                            int H, int hd, int r0, cudaStream_t st);
 // 0: mma.sync kernels only; 1: tcgen05, forward tail rows (S % 128 <= 32) on mma.sync; 2 (default): tcgen05 for every
 // forward tile, a single backward tail row (S % 128 == 1) on the row kernel; 3: tcgen05 for every tile, backward included
@@ -604,36 +604,61 @@ extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t
   }
 }
 
-extern "C" int hct_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                                 float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd, hct_stream_t s) {
+// hct_attention_bwd plus the qkv-bias gradient: the column sums of dqkv over all B * S tokens are ADDED to dqkv_colsum
+// (fp32 [3 * H * hd], may be NULL).  The pipelined tcgen05 path sums them from the tiles it has staged for its stores; every
+// other path runs the column-sum kernel over the finished dqkv.
+extern "C" int hct_colsum(const void* x, int32_t x_bf16, int64_t ld, float* out, int64_t rows, int32_t cols, hct_stream_t s);
+extern "C" int hct_attention_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                      float* delta_ws, float* dqkv_colsum, int32_t B, int32_t S, int32_t H, int32_t hd,
+                                      hct_stream_t s) {
   HCT_REQUIRE(B > 0 && S > 0 && H > 0 && H <= 65535 && B <= 65535, "attention_bwd: bad B=%d S=%d H=%d", B, S, H);
   HCT_REQUIRE(hd == 64 || hd == 48 || hd == 32, "attention_bwd: head dim %d unsupported (32/48/64)", hd);
   cudaStream_t st = static_cast<cudaStream_t>(s);
-  HctProfScope prof(st, HCT_PROF_ATTN_BWD, 8.0 * B * static_cast<double>(S) * S * H * hd);   // 2 x forward
   const long long total = static_cast<long long>(B) * S * H;
-  HCT_REQUIRE(hd % 8 == 0 && hd <= 64, "attention_bwd: head dim %d unsupported by the delta pre-pass", hd);
-  attn_delta_kernel<<<dim3((S + DELTA_TOK - 1) / DELTA_TOK, B), 256, H * (DELTA_TOK + 1) * sizeof(float), st>>>(
-      static_cast<const bf16*>(out), static_cast<const bf16*>(dout), delta_ws, S, H, hd, total);
-  int rc = hct_check_launch("attn_delta_kernel");
-  if (rc) return rc;
-  if (g_attn_tc && (hd == 64 || hd == 48)) {
-    const int full = S / 128, r0 = full * 128;
-    auto tc_bwd = g_attn_bwd3 ? hct_attention_bwd3 : hct_attention_bwd_tc;
-    if (g_attn_tc != 3 && r0 < S && hct_attention_bwd_tail_supported(S, hd, r0)) {
-      if (full > 0) {
-        rc = tc_bwd(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, full, st);
-        if (rc) return rc;
+  int rc;
+  bool fused = false;
+  {
+    HctProfScope prof(st, HCT_PROF_ATTN_BWD, 8.0 * B * static_cast<double>(S) * S * H * hd);   // 2 x forward
+    HCT_REQUIRE(hd % 8 == 0 && hd <= 64, "attention_bwd: head dim %d unsupported by the delta pre-pass", hd);
+    attn_delta_kernel<<<dim3((S + DELTA_TOK - 1) / DELTA_TOK, B), 256, H * (DELTA_TOK + 1) * sizeof(float), st>>>(
+        static_cast<const bf16*>(out), static_cast<const bf16*>(dout), delta_ws, S, H, hd, total);
+    rc = hct_check_launch("attn_delta_kernel");
+    if (rc) return rc;
+    if (g_attn_tc && (hd == 64 || hd == 48)) {
+      const int full = S / 128, r0 = full * 128;
+      fused = g_attn_bwd3 != 0;                          // the pipelined kernels (and the row kernel behind them) sum as they store
+      float* cs = fused ? dqkv_colsum : nullptr;
+      auto tc_bwd = [&](int n_tiles) {
+        return g_attn_bwd3 ? hct_attention_bwd3(qkv, dout, lse, delta_ws, dqkv, cs, B, S, H, hd, n_tiles, st)
+                           : hct_attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, n_tiles, st);
+      };
+      if (g_attn_tc != 3 && r0 < S && hct_attention_bwd_tail_supported(S, hd, r0)) {
+        if (full > 0) {
+          rc = tc_bwd(full);
+          if (rc) return rc;
+        }
+        rc = hct_attention_bwd_tail(qkv, dout, lse, delta_ws, dqkv, cs, B, S, H, hd, r0, st);
+      } else {
+        rc = tc_bwd((S + 127) / 128);
       }
-      return hct_attention_bwd_tail(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, r0, st);
+    } else {
+      const bf16* q = static_cast<const bf16*>(qkv);
+      const bf16* d = static_cast<const bf16*>(dout);
+      bf16* dq = static_cast<bf16*>(dqkv);
+      switch (hd) {
+        case 64: rc = launch_bwd<64>(q, d, lse, delta_ws, dq, B, S, H, st); break;
+        case 48: rc = launch_bwd<48>(q, d, lse, delta_ws, dq, B, S, H, st); break;
+        default: rc = launch_bwd<32>(q, d, lse, delta_ws, dq, B, S, H, st); break;
+      }
     }
-    return tc_bwd(qkv, dout, lse, delta_ws, dqkv, B, S, H, hd, (S + 127) / 128, st);
   }
-  const bf16* q = static_cast<const bf16*>(qkv);
-  const bf16* d = static_cast<const bf16*>(dout);
-  bf16* dq = static_cast<bf16*>(dqkv);
-  switch (hd) {
-    case 64: return launch_bwd<64>(q, d, lse, delta_ws, dq, B, S, H, st);
-    case 48: return launch_bwd<48>(q, d, lse, delta_ws, dq, B, S, H, st);
-    default: return launch_bwd<32>(q, d, lse, delta_ws, dq, B, S, H, st);
-  }
+  if (rc) return rc;
+  if (dqkv_colsum != nullptr && !fused)
+    return hct_colsum(dqkv, 1, 3LL * H * hd, dqkv_colsum, static_cast<long long>(B) * S, 3 * H * hd, s);
+  return HCT_OK;
+}
+
+extern "C" int hct_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                 float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd, hct_stream_t s) {
+  return hct_attention_bwd_bias(qkv, out, dout, lse, dqkv, delta_ws, nullptr, B, S, H, hd, s);
 }

@@ -92,8 +92,8 @@ template <int HD, bool KV, int POLY, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmDO128,
                  const __grid_constant__ CUtensorMap tmQKV64, const __grid_constant__ CUtensorMap tmDO64,
-                 const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H,
-                 int n_tiles, int n_items, float scale, int tma_drain_ok) {
+                 const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
+                 float* __restrict__ colsum, int S, int H, int n_tiles, int n_items, float scale, int tma_drain_ok) {
   // accumulator sets in tensor memory: the dQ pass (64 columns per set) has room for two, so an item's drain overlaps the
   // next item's MMAs; the dK/dV pass (2 x HD columns) has one and pays a short bubble per item
   extern __shared__ uint8_t smem_raw[];
@@ -312,6 +312,22 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
         }
         if (tma_drain) fence_proxy_async_smem();           // the staged rows become visible to the TMA unit
       }
+      // qkv-bias gradient (column sums of dqkv over all tokens, attentionblock.py:36 qkv_bias): summed here from the staged
+      // bf16 rows -- two columns per lane, one red.global per column and warp tile -- instead of re-reading dqkv from HBM
+      auto tile_colsum = [&](int col) {
+        __syncwarp();
+        if (lane < HD / 2) {
+          const int row0c = t * TILE + q * 32;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(stg + slot_off(r, lane >> 2) + (lane & 3) * 4));
+            if (row0c + r < S) { s0 += f.x; s1 += f.y; }
+          }
+          atomicAdd(colsum + col + 2 * lane, s0);
+          atomicAdd(colsum + col + 2 * lane + 1, s1);
+        }
+      };
       // the accumulators have left tensor memory: hand the set back to the MMA issuer BEFORE the global-store path
       tc_fence_before();
       __syncwarp();
@@ -342,6 +358,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
           }
           __syncwarp();
         }
+        if (colsum != nullptr) tile_colsum(col);             // off the accumulator hand-over path; the slot is rewritten next item
       }
     };
 
@@ -520,7 +537,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
 int g_bwd3_tma_drain = 1;   // 0: results leave through the per-lane store loop (A/B, hct_attention_set_bwd3_drain)
 template <int HD, bool KV, int POLY, bool TRACE = false>
 int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensorMap& q64, const CUtensorMap& do64,
-               const CUtensorMap& out, const float* lse, const float* delta, bf16* dqkv, int B, int S, int H, int n_tiles, cudaStream_t st) {
+               const CUtensorMap& out, const float* lse, const float* delta, bf16* dqkv, float* colsum, int B, int S, int H, int n_tiles,
+               cudaStream_t st) {
   static bool cfg = false;
   auto kernel = attn_bwd3_kernel<HD, KV, POLY, TRACE>;
   if (!cfg) {
@@ -533,7 +551,7 @@ int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensor
   const int sms = hct_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
-  kernel<<<grid, THREADS, SMEM_BYTES, st>>>(q128, do128, q64, do64, out, lse, delta, dqkv, S, H, n_tiles, static_cast<int>(items), scale, g_bwd3_tma_drain);
+  kernel<<<grid, THREADS, SMEM_BYTES, st>>>(q128, do128, q64, do64, out, lse, delta, dqkv, colsum, S, H, n_tiles, static_cast<int>(items), scale, g_bwd3_tma_drain);
   return hct_check_launch(KV ? "attn_bwd3_kernel<dK/dV>" : "attn_bwd3_kernel<dQ>");
 }
 
@@ -550,21 +568,23 @@ static int g_bwd3_poly = 0;      // -1: scalar fp32; 0 (default): packed fp32; 2
 int hct_attention_bwd3_set_poly(int n) { g_bwd3_poly = n; return HCT_OK; }
 template <int POLY>
 static int launch_both(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensorMap& q64, const CUtensorMap& do64,
-                       const CUtensorMap& out, const float* lse, const float* delta, bf16* dq, int B, int S, int H, int hd, int n_tiles, cudaStream_t st) {
+                       const CUtensorMap& out, const float* lse, const float* delta, bf16* dq, float* colsum, int B, int S, int H, int hd,
+                       int n_tiles, cudaStream_t st) {
   int rc;
   if (hd == 64) {
-    rc = launch_one<64, true, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st); if (rc) return rc;
-    return launch_one<64, false, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
+    rc = launch_one<64, true, POLY>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, n_tiles, st); if (rc) return rc;
+    return launch_one<64, false, POLY>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, n_tiles, st);
   }
-  if (POLY == 0 && g_trace3_host) rc = launch_one<48, true, 0, true>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
-  else rc = launch_one<48, true, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
+  if (POLY == 0 && g_trace3_host) rc = launch_one<48, true, 0, true>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, n_tiles, st);
+  else rc = launch_one<48, true, POLY>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, n_tiles, st);
   if (rc) return rc;
-  return launch_one<48, false, POLY>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, n_tiles, st);
+  return launch_one<48, false, POLY>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, n_tiles, st);
 }
 
 // n_tiles full 128-row tiles per (batch, head) on tcgen05 (rows behind them: hct_attention_tail.cu)
-int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S, int H,
-                       int hd, int n_tiles, cudaStream_t st) {
+// colsum (may be NULL): fp32 [3 * H * hd], the column sums of the written dqkv rows are ADDED to it
+int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* colsum, int B, int S,
+                       int H, int hd, int n_tiles, cudaStream_t st) {
   CUtensorMap q128, q64, do128, do64;
   const long long D = static_cast<long long>(H) * hd, D3 = 3 * D, rows = static_cast<long long>(B) * S;
   HCT_REQUIRE(static_cast<long long>(B) * H * n_tiles <= 2147483647LL, "attention_bwd3: too many work items");
@@ -576,7 +596,7 @@ int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, cons
   CUtensorMap out;
   rc = hct_make_tmap_bf16_2d_sw(&out, dqkv, D3, rows, D3, hd, 32, hd == 64 ? 1 : 0); if (rc) return rc;
   bf16* dq = static_cast<bf16*>(dqkv);
-  return g_bwd3_poly == 0   ? launch_both<0>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st)
-         : g_bwd3_poly == 2 ? launch_both<2>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st)
-                            : launch_both<-1>(q128, do128, q64, do64, out, lse, delta, dq, B, S, H, hd, n_tiles, st);
+  return g_bwd3_poly == 0   ? launch_both<0>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, hd, n_tiles, st)
+         : g_bwd3_poly == 2 ? launch_both<2>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, hd, n_tiles, st)
+                            : launch_both<-1>(q128, do128, q64, do64, out, lse, delta, dq, colsum, B, S, H, hd, n_tiles, st);
 }

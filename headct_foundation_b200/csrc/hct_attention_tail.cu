@@ -37,7 +37,8 @@ __device__ __forceinline__ float group8_sum(float v) {      // sum over the 8 la
 template <int HD, int RMAX>
 __global__ void __launch_bounds__(TAIL_THREADS)
 attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
-                     const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, int r0, int R, float scale) {
+                     const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ colsum, int S, int H, int r0, int R,
+                     float scale) {
   __shared__ float red[TAIL_GROUPS][HD + 1];
   __shared__ float sl[RMAX], sdl[RMAX];                 // rows [r0, r0 + R), 1 <= R <= RMAX
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -67,7 +68,7 @@ attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
   }
   __syncthreads();
 
-  auto reduce_store = [&](const float* acc8, bf16* dst, float mul) {     // sum over row groups, write one output row
+  auto reduce_store = [&](const float* acc8, bf16* dst, float mul, int col) {     // sum over row groups, write one output row
     __syncthreads();
     if (live) {
 #pragma unroll
@@ -78,7 +79,9 @@ attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
       float t = 0.f;
 #pragma unroll
       for (int g = 0; g < TAIL_GROUPS; ++g) t += red[g][tid];
-      dst[tid] = __float2bfloat16_rn(t * mul);
+      const bf16 v = __float2bfloat16_rn(t * mul);
+      dst[tid] = v;
+      if (colsum != nullptr) atomicAdd(colsum + col + tid, __bfloat162float(v));   // qkv-bias gradient: this row's share
     }
   };
 
@@ -112,7 +115,7 @@ attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
     }
 #pragma unroll
     for (int r = 0; r < RMAX; ++r)
-      if (r < R) reduce_store(acc[r], dqkv + (static_cast<long long>(b) * S + r0 + r) * rs + h * HD, scale);
+      if (r < R) reduce_store(acc[r], dqkv + (static_cast<long long>(b) * S + r0 + r) * rs + h * HD, scale, h * HD);
   }
 
   // ---------------- part B: every query against the tail keys  ->  dK, dV rows
@@ -148,17 +151,17 @@ attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
     for (int r = 0; r < RMAX; ++r) {
       if (r < R) {
         bf16* o = dqkv + (static_cast<long long>(b) * S + r0 + r) * rs + h * HD;
-        reduce_store(ak[r], o + D, scale);
-        reduce_store(av[r], o + 2 * D, 1.0f);
+        reduce_store(ak[r], o + D, scale, D + h * HD);
+        reduce_store(av[r], o + 2 * D, 1.0f, 2 * D + h * HD);
       }
     }
   }
 }
 
 template <int HD, int RMAX>
-int launch_tail(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv, int B, int S, int H,
+int launch_tail(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv, float* colsum, int B, int S, int H,
                 int r0, int R, cudaStream_t st) {
-  attn_bwd_tail_kernel<HD, RMAX><<<dim3(H, B), TAIL_THREADS, 0, st>>>(qkv, dout, lse, delta, dqkv, S, H, r0, R,
+  attn_bwd_tail_kernel<HD, RMAX><<<dim3(H, B), TAIL_THREADS, 0, st>>>(qkv, dout, lse, delta, dqkv, colsum, S, H, r0, R,
                                                                        1.0f / sqrtf(static_cast<float>(HD)));
   return hct_check_launch("attn_bwd_tail_kernel");
 }
@@ -172,11 +175,11 @@ bool hct_attention_bwd_tail_supported(int S, int hd, int r0) {
   return (hd == 64 || hd == 48) && r0 > 0 && S - r0 == 1;
 }
 
-int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int B, int S,
-                           int H, int hd, int r0, cudaStream_t st) {
+int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* colsum, int B,
+                           int S, int H, int hd, int r0, cudaStream_t st) {
   const bf16* q = static_cast<const bf16*>(qkv);
   const bf16* d = static_cast<const bf16*>(dout);
   bf16* o = static_cast<bf16*>(dqkv);
-  if (hd == 64) return launch_tail<64, 1>(q, d, lse, delta, o, B, S, H, r0, S - r0, st);
-  return launch_tail<48, 1>(q, d, lse, delta, o, B, S, H, r0, S - r0, st);
+  if (hd == 64) return launch_tail<64, 1>(q, d, lse, delta, o, colsum, B, S, H, r0, S - r0, st);
+  return launch_tail<48, 1>(q, d, lse, delta, o, colsum, B, S, H, r0, S - r0, st);
 }

@@ -555,11 +555,12 @@ class BlockFn(torch.autograd.Function):
         del dx2_16
         dqkv = torch.empty_like(qkv)
         delta = torch.empty((B, heads, S), dtype=F32, device=dev)
-        call("hct_attention_bwd", qkv.data_ptr(), att.data_ptr(), datt.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-             delta.data_ptr(), B, S, heads, hd, st)
+        # the qkv-bias gradient (column sums of dqkv) comes out of the attention backward itself (hct_attention_bwd_bias)
+        dqkv_b = zs.take("qkv_b", 3 * D) if need[QKVB] else None
+        call("hct_attention_bwd_bias", qkv.data_ptr(), att.data_ptr(), datt.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+             delta.data_ptr(), ptr(dqkv_b), B, S, heads, hd, st)
         del datt
         dqkv_w = linear_wgrad(dqkv, h1.view(M, D), out=zs.take("qkv_w", 3 * D, D)) if need[QKVW] else None
-        dqkv_b = colsum(dqkv, 3 * D, out=zs.take("qkv_b", 3 * D)) if need[QKVB] else None
         dlqA = dlqB = dlvA = dlvB = None
         if not lora:
             dh1 = linear_dgrad(dqkv, qkv_w)                                             # [M, D] bf16

@@ -232,6 +232,13 @@ int hct_attention_trace(void* buf);
 int hct_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                       void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t H, int32_t hd,
                       hct_stream_t stream);
+/* The same, and the qkv-bias gradient of the block's qkv Linear (attentionblock.py:36, qkv_bias=True in the shipped configs):
+ * the column sums of dqkv over all B * S tokens are ADDED to dqkv_colsum (fp32 [3 * H * hd], zeroed by the caller; NULL = none).
+ * The pipelined tcgen05 backward sums them from the tiles it stages for its stores (no second pass over dqkv); the other
+ * paths run hct_colsum behind the kernels.  Accumulation order differs between the two (fp32 atomics). */
+int hct_attention_bwd_bias(const void* qkv, const void* out, const void* dout, const float* lse,
+                           void* dqkv, float* delta_ws, float* dqkv_colsum, int32_t B, int32_t S, int32_t H,
+                           int32_t hd, hct_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DINO kernels

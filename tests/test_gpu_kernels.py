@@ -249,8 +249,12 @@ def _attention_case(cuda, B, S, H, hd):
     ref.backward(do.float())
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, H, S, device=cuda)
-    call("hct_attention_bwd", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-         delta.data_ptr(), B, S, H, hd, stream_ptr(cuda))
+    # the entry point with the qkv-bias gradient: column sums of the dqkv it writes, added to a zeroed fp32 vector
+    bias = torch.zeros(3 * D, device=cuda)
+    call("hct_attention_bwd_bias", qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+         delta.data_ptr(), bias.data_ptr(), B, S, H, hd, stream_ptr(cuda))
+    want = dqkv.double().sum((0, 1))
+    assert (bias.double() - want).abs().max().item() < 1e-4 * dqkv.double().abs().sum((0, 1)).max().item() + 1e-6
     dref = torch.stack([q.grad, k.grad, v.grad]).permute(1, 3, 0, 2, 4).reshape(B, S, 3 * D)
     d = dqkv.float().view(B, S, 3, D)
     dr = dref.view(B, S, 3, D)
