@@ -250,6 +250,45 @@ def secondary_finetune(torch, dist, H, FusedAdamW, dev, world, local_rank, peak,
             "workload": "fine-tune step ViT-B + LinearClassifier + CE (vit_HeadCT_cq500 shape), replicas (not DDP, as the reference)"}
 
 
+def secondary_global256(torch, dist, H, FusedAdamW, dev, world, local_rank, peak, steps=10, warmup=3):
+    """configs[1] read as a GLOBAL batch of 256 (strong scaling: 256 / world volumes per GPU): the whole step -- forward,
+    loss, backward, gradient all-reduce(mean), per-parameter clip + AdamW -- replayed from ONE CUDA graph per rank
+    (utils/graphs.py GraphedTrainStep with the all-reduce captured), next to the same per-GPU batch issued eagerly under
+    DistributedDataParallel, which the host's ~13 ms of launch work per step bounds."""
+    from headct_foundation_b200.configs import MAE_HEADCT
+    from headct_foundation_b200 import parallel
+    B = 256 // world
+    out = {"batch_per_gpu": B, "global_batch": B * world,
+           "workload": "MAE ViT-B 3D pretraining step, global batch 256 split over the ranks (strong scaling)"}
+    torch.manual_seed(parallel.rank_seed(42, dist.get_rank() if world > 1 else 0))
+    x = torch.rand(B, 3, 96, 96, 96, device=dev)
+    lr = parallel.scaled_lr(1.5e-4, B, world)
+    # eager under DDP
+    model = H.MaskedAutoencoderViT(**MAE_HEADCT).to(dev).train()
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False,
+                                                    gradient_as_bucket_view=True, bucket_cap_mb=64) if world > 1 else model
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=lr, betas=(0.9, 0.95), weight_decay=0.05, clip_grad=3.0)
+
+    def eager():
+        opt.zero_grad(set_to_none=True)
+        loss, _, _ = ddp(x)
+        loss.backward()
+        opt.step()
+    ms = _timed_steps(torch, dist, world, eager, warmup, steps)
+    out["eager_ddp"] = {"volumes_per_s": B * world / ms * 1e3, "ms_per_step": ms, "step_frac_of_peak": MAE_FWD_BWD_GFLOP * B / ms / peak}
+    del ddp, opt, model
+    import gc
+    gc.collect(); torch.cuda.empty_cache()
+    # one graph per rank, gradient all-reduce inside
+    model = H.MaskedAutoencoderViT(**MAE_HEADCT).to(dev).train()
+    opt = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=lr, betas=(0.9, 0.95), weight_decay=0.05, clip_grad=3.0)
+    step = H.GraphedTrainStep(model, opt, x)
+    ms = _timed_steps(torch, dist, world, lambda: step(x), warmup, steps)
+    out["graph_replay"] = {"volumes_per_s": B * world / ms * 1e3, "ms_per_step": ms, "step_frac_of_peak": MAE_FWD_BWD_GFLOP * B / ms / peak,
+                           "loss": float(step.static_loss.item()), "grad_sync": "all-reduce(mean) captured in the graph" if world > 1 else None}
+    return out
+
+
 def secondary_extract(torch, dist, H, dev, world, peak, batches=(1, 8, 64, 256)):
     """configs[4]: encoder-only feature extraction, ViT.eval() under no_grad, 12 hidden states materialised."""
     from headct_foundation_b200 import configs as C
@@ -450,7 +489,10 @@ def run_ours(args):
         secondary = {}
         for name, fn in (("dino", lambda: secondary_dino(torch, dist, H, FusedAdamW, dev, world, local_rank, peaks["tflops"])),
                          ("finetune", lambda: secondary_finetune(torch, dist, H, FusedAdamW, dev, world, local_rank, peaks["tflops"])),
-                         ("extract", lambda: secondary_extract(torch, dist, H, dev, world, peaks["tflops"]))):
+                         ("extract", lambda: secondary_extract(torch, dist, H, dev, world, peaks["tflops"])),
+                         ("mae_global256", lambda: secondary_global256(torch, dist, H, FusedAdamW, dev, world, local_rank, peaks["tflops"]))):
+            if name == "mae_global256" and (world == 1 or 256 % world):
+                continue
             try:
                 secondary[name] = fn()
             except Exception as e:                      # the headline line must survive a secondary failure; say what broke

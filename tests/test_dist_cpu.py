@@ -33,6 +33,17 @@ def _worker(rank, world, port, out):
     ddp(x).sum().backward()
     res["wgrad"] = float(lin.weight.grad[0, 0])                  # d/dw sum = sum of inputs = 2 (rank + 1); mean over ranks = 3
     res["lr"] = P.scaled_lr(1.5e-4, 256, world)
+    # the exchange step in its capturable form: every .grad becomes the mean over ranks; parameters start from rank 0's
+    torch.manual_seed(rank)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    P.broadcast_params_(net)
+    res["w0"] = float(net[0].weight.sum())
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    net[1].bias.grad = None                                       # a frozen tensor takes no part
+    n_groups = P.allreduce_mean_grads_(list(net.parameters()))
+    res["mean_grads"] = [None if p.grad is None else float(p.grad.flatten()[0]) for p in net.parameters()]
+    res["groups"] = n_groups
     out[rank] = res
     dist.barrier()
     dist.destroy_process_group()
@@ -49,6 +60,8 @@ def test_two_rank_gloo_helpers():
     assert r0["center"] == r1["center"] == [[3.0 / 8] * 8]
     assert r0["wgrad"] == r1["wgrad"] == 3.0                      # mean over ranks of 2 (rank + 1)
     assert r0["lr"] == r1["lr"] == pytest.approx(3e-4)
+    assert r0["w0"] == r1["w0"]                                   # broadcast_params_: both ranks hold rank 0's weights
+    assert r0["mean_grads"] == r1["mean_grads"] == [1.5, 3.0, 4.5, None] and r0["groups"] == 3
 
 
 def test_scaled_lr_rule():

@@ -137,6 +137,82 @@ def test_ddp_reduced_gradients_equal_mean_of_rank_gradients(cuda, tmp_path):
     assert out["worst_rel"] < 1e-4, out
 
 
+_GRAPH_DDP_WORKER = r'''
+import json, os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HCT_ROOT"])
+import headct_foundation_b200 as H
+from headct_foundation_b200 import parallel
+from headct_foundation_b200.optim import FusedAdamW
+from oracle import synth
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+cfg = synth.MAE_SMALL
+sd = synth.mae_state_dict(cfg, seed=31)
+L = (cfg["input_size"] // cfg["patch_size"]) ** 3
+x = synth.volume(4, cfg["in_chans"], cfg["input_size"], 40 + rank).to(dev)
+noise = synth.noise(4, L, seed=50 + rank).to(dev)
+
+def fresh(seed_shift):
+    m = H.MaskedAutoencoderViT(**cfg)
+    sdr = {k: (v + 0.01 * seed_shift if v.is_floating_point() else v) for k, v in sd.items()}   # ranks start apart ...
+    m.load_state_dict(sdr, strict=True); m.noise_override = noise
+    return m.to(dev).train()
+
+def opt_of(m):
+    return FusedAdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05, clip_grad=3.0)
+
+# eager: backward, all-reduce(mean) of the gradients, update -- three steps
+me = fresh(rank); parallel.broadcast_params_(me); oe = opt_of(me)          # ... and are put on rank 0's parameters
+start = {k: p.detach().clone() for k, p in me.named_parameters()}
+for _ in range(3):
+    oe.zero_grad(set_to_none=True)
+    me(x)[0].backward()
+    parallel.allreduce_mean_grads_(list(me.parameters()))
+    oe.step()
+# the same three steps replayed from one CUDA graph per rank with the all-reduce captured inside
+mg = fresh(rank); og = opt_of(mg)
+step = H.GraphedTrainStep(mg, og, x)                                        # broadcasts from rank 0 itself
+losses = [float(step(x).item()) for _ in range(3)]
+torch.cuda.synchronize()
+num = den_e = den_g = 0.0
+spread = 0.0
+for (k, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
+    ue, ug = (pe.detach() - start[k]).double().flatten(), (pg.detach() - start[k]).double().flatten()
+    num += float(ue @ ug); den_e += float(ue @ ue); den_g += float(ug @ ug)
+    lo, hi = pg.detach().clone(), pg.detach().clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    spread = max(spread, float((hi - lo).abs().max()))
+if rank == 0:
+    print(json.dumps({"cos_update": num / (den_e * den_g) ** 0.5, "rank_spread": spread, "losses": losses, "world": world}), flush=True)
+del step                       # the graph holds NCCL kernels: it has to go before the communicator does
+torch.cuda.synchronize()
+dist.destroy_process_group()
+'''
+
+
+def test_graphed_step_with_captured_allreduce(cuda, tmp_path):
+    """2 ranks, NCCL: GraphedTrainStep with the gradient all-reduce(mean) captured inside the graph
+    (parallel.allreduce_mean_grads_) follows the eager backward -> all-reduce -> update trajectory, and the ranks'
+    parameters stay bit-identical (same averaged gradients, deterministic update)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    worker = tmp_path / "graph_ddp_worker.py"
+    worker.write_text(_GRAPH_DDP_WORKER)
+    env = dict(os.environ, HCT_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29534", str(worker)], capture_output=True, text=True, env=env,
+                       timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["world"] == 2
+    assert out["rank_spread"] == 0.0, out                   # every rank holds the same parameters after three steps
+    assert out["cos_update"] > 0.95, out                    # wgrad split-K atomics: runs differ in the last bits
+    assert all(v == v and abs(v) < 1e3 for v in out["losses"]), out
+
+
 def test_block_output_with_a_second_consumer(cuda):
     """A block's fp32 output gradient has a bf16 twin that rides to the next backward node in a side table
     (functional.put_bf16_shadow).  When the block output ALSO feeds a second loss term (ViT returns every hidden state,
