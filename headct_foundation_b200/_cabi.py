@@ -81,6 +81,7 @@ _SIGNATURES = {
     "hct_attention_set_dkdv32": [_I32],
     "hct_attention_set_bwd3": [_I32],
     "hct_attention_set_poly": [_I32, _I32],
+    "hct_set_pdl": [_I32],
     "hct_attention_set_bwd3_drain": [_I32],
     "hct_attention_trace": [C.c_void_p],
     "hct_attention_trace3": [C.c_void_p],
@@ -141,6 +142,8 @@ def lib() -> C.CDLL:
             L.hct_gemm_set_cta_pair(0)
         if os.environ.get("HCT_ATTN_TCGEN05", "1") == "0":       # debugging aid: mma.sync attention only
             L.hct_attention_set_tcgen05(0)
+        if "HCT_PDL" in os.environ:                              # A/B: programmatic dependent launch on / off
+            L.hct_set_pdl(int(os.environ["HCT_PDL"] != "0"))
         if "HCT_ATTN_BWD3" in os.environ:                        # A/B: pipelined persistent backward on / off
             L.hct_attention_set_bwd3(int(os.environ["HCT_ATTN_BWD3"] != "0"))
         _lib = L

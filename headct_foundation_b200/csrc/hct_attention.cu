@@ -225,6 +225,8 @@ constexpr int DELTA_TOK = 32;
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta,
                   int S, int H, int HD, long long total) {
+  pdl_wait();                  // launched with programmatic stream serialization (hct_common.cuh)
+  pdl_launch_dependents();
   extern __shared__ float sdelta[];                       // [H][DELTA_TOK + 1]
   const int b = blockIdx.y;
   const int s0 = blockIdx.x * DELTA_TOK;
@@ -620,8 +622,8 @@ extern "C" int hct_attention_bwd_bias(const void* qkv, const void* out, const vo
   {
     HctProfScope prof(st, HCT_PROF_ATTN_BWD, 8.0 * B * static_cast<double>(S) * S * H * hd);   // 2 x forward
     HCT_REQUIRE(hd % 8 == 0 && hd <= 64, "attention_bwd: head dim %d unsupported by the delta pre-pass", hd);
-    attn_delta_kernel<<<dim3((S + DELTA_TOK - 1) / DELTA_TOK, B), 256, H * (DELTA_TOK + 1) * sizeof(float), st>>>(
-        static_cast<const bf16*>(out), static_cast<const bf16*>(dout), delta_ws, S, H, hd, total);
+    hct_launch_pdl(attn_delta_kernel, dim3((S + DELTA_TOK - 1) / DELTA_TOK, B), dim3(256), H * (DELTA_TOK + 1) * sizeof(float), st,
+                   static_cast<const bf16*>(out), static_cast<const bf16*>(dout), delta_ws, S, H, hd, total);
     rc = hct_check_launch("attn_delta_kernel");
     if (rc) return rc;
     if (g_attn_tc && (hd == 64 || hd == 48)) {

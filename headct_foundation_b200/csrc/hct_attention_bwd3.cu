@@ -131,6 +131,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // launched with programmatic stream serialization: nothing above touches global memory
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   // KV: dV at [0,HD), dK at [64,64+HD).  !KV: dQ of accumulator set a at [64 a, 64 a + HD)
   long long* trace = (TRACE && g_trace3 != nullptr && blockIdx.x == 0 && lane == 0 && KV) ? g_trace3 : nullptr;
@@ -551,7 +553,8 @@ int launch_one(const CUtensorMap& q128, const CUtensorMap& do128, const CUtensor
   const int sms = hct_num_sms();
   const int grid = static_cast<int>(items < sms ? items : sms);
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
-  kernel<<<grid, THREADS, SMEM_BYTES, st>>>(q128, do128, q64, do64, out, lse, delta, dqkv, colsum, S, H, n_tiles, static_cast<int>(items), scale, g_bwd3_tma_drain);
+  hct_launch_pdl(kernel, dim3(grid), dim3(THREADS), SMEM_BYTES, st, q128, do128, q64, do64, out, lse, delta, dqkv, colsum, S, H, n_tiles,
+                 static_cast<int>(items), scale, g_bwd3_tma_drain);
   return hct_check_launch(KV ? "attn_bwd3_kernel<dK/dV>" : "attn_bwd3_kernel<dQ>");
 }
 

@@ -81,6 +81,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();                  // launched with programmatic stream serialization: nothing above touches global memory
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
 
@@ -1151,8 +1153,8 @@ static int launch_fwd_tc(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* 
     rc = set_smem(attn_fwd_tc_kernel<48, POLY>, FWD_SMEM); if (rc) return rc;
     cfg = true;
   }
-  if (hd == 64) attn_fwd_tc_kernel<64, POLY><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
-  else attn_fwd_tc_kernel<48, POLY><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
+  if (hd == 64) hct_launch_pdl(attn_fwd_tc_kernel<64, POLY>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
+  else hct_launch_pdl(attn_fwd_tc_kernel<48, POLY>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
   return HCT_OK;
 }
 

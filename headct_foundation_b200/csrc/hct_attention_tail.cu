@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(TAIL_THREADS)
 attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout, const float* __restrict__ lse,
                      const float* __restrict__ delta, bf16* __restrict__ dqkv, float* __restrict__ colsum, int S, int H, int r0, int R,
                      float scale) {
+  pdl_wait();                  // launched with programmatic stream serialization (hct_common.cuh)
+  pdl_launch_dependents();
   __shared__ float red[TAIL_GROUPS][HD + 1];
   __shared__ float sl[RMAX], sdl[RMAX];                 // rows [r0, r0 + R), 1 <= R <= RMAX
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -161,8 +163,8 @@ attn_bwd_tail_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout
 template <int HD, int RMAX>
 int launch_tail(const bf16* qkv, const bf16* dout, const float* lse, const float* delta, bf16* dqkv, float* colsum, int B, int S, int H,
                 int r0, int R, cudaStream_t st) {
-  attn_bwd_tail_kernel<HD, RMAX><<<dim3(H, B), TAIL_THREADS, 0, st>>>(qkv, dout, lse, delta, dqkv, colsum, S, H, r0, R,
-                                                                       1.0f / sqrtf(static_cast<float>(HD)));
+  hct_launch_pdl(attn_bwd_tail_kernel<HD, RMAX>, dim3(H, B), dim3(TAIL_THREADS), 0, st, qkv, dout, lse, delta, dqkv, colsum, S, H, r0, R,
+                 1.0f / sqrtf(static_cast<float>(HD)));
   return hct_check_launch("attn_bwd_tail_kernel");
 }
 

@@ -35,6 +35,27 @@ struct HctProfScope {
 
 typedef __nv_bfloat16 bf16;
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may start before its predecessor in the stream has finished and MUST call pdl_wait() before its first access to global
+// memory (it returns once the predecessor grid has completed and its writes are visible; immediately for a normal launch).
+// pdl_launch_dependents() lets the successor grid be scheduled early; call it only where every CTA of this grid is already
+// resident (persistent grids) or at the end of a CTA's work, so that waiting successor CTAs never take slots this grid needs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool hct_pdl_enabled();    // hct_set_pdl(0) turns the launch attribute off (A/B)
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute; the kernel must call pdl_wait()
+template <typename... KArgs, typename... Args>
+inline cudaError_t hct_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = hct_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

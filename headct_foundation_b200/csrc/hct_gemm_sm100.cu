@@ -638,6 +638,7 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   constexpr int TILE_M = BM * CTAS;
 
   if (threadIdx.x == 0) {
+    pdl_launch_dependents();    // persistent grid, every CTA resident from the start: the successor may queue behind us now
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     if (EpiTraits<EPI>::tma) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmOut)) : "memory");
@@ -662,6 +663,10 @@ hct_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
+  // Programmatic dependent launch: this grid may have been started while its predecessor in the stream was still running
+  // (its CTAs take an SM as soon as the predecessor's CTA there has exited, and get the prologue above out of the way);
+  // nothing before this line touches global memory the predecessor may still write or read.
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   long long* trace = (g_gemm_trace != nullptr && blockIdx.x == 0) ? g_gemm_trace : nullptr;
   // trace layout: [0,512): MMA warp, 8 events per tile; [512, 512+16*64): epilogue warp 4, 16 events per tile
@@ -972,11 +977,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, co
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg<CTAS, EPI>::SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // the kernel waits itself (pdl_wait)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = hct_pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, em.out, em.out2, em.aux, p);
   if (e != cudaSuccess) { hct_set_error("cudaLaunchKernelEx(gemm): %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return HCT_ERR_CUDA; }
   return hct_check_launch("hct_gemm_tcgen05_kernel");

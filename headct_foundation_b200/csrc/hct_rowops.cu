@@ -16,6 +16,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               void* __restrict__ y, int y_bf16, float* __restrict__ mean_out, float* __restrict__ rstd_out,
               long long rows, int dim, float eps) {
+  pdl_wait();                  // launched with programmatic stream serialization (hct_common.cuh)
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = dim >> 2;   // float4 per row
   const bool rms = beta == nullptr;
@@ -94,6 +96,8 @@ ln_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const fl
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres_in,
               float* __restrict__ dx_f32, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dxsum, long long rows, int dim) {
+  pdl_wait();                  // launched with programmatic stream serialization (hct_common.cuh)
+  pdl_launch_dependents();
   extern __shared__ __align__(16) float sbuf[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = dim >> 2;
@@ -406,7 +410,7 @@ extern "C" int hct_layernorm_fwd(const float* x, const float* gamma, const float
                     static_cast<double>(rows) * (dim * (4.0 + (y_bf16 ? 2.0 : 4.0)) + (mean ? 4.0 : 0.0) + (rstd ? 4.0 : 0.0)));
   const int grid = grid_for(rows, LN_WARPS, hct_num_sms() * 8);
 #define HCT_LN_FWD(NV) \
-  ln_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, static_cast<cudaStream_t>(s)>>>(x, gamma, beta, y, y_bf16, mean, rstd, rows, dim, eps)
+  hct_launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(LN_WARPS * 32), 0, static_cast<cudaStream_t>(s), x, gamma, beta, y, y_bf16, mean, rstd, rows, dim, eps)
   if (dim <= 256) HCT_LN_FWD(2); else if (dim <= 768) HCT_LN_FWD(6); else if (dim <= 1024) HCT_LN_FWD(8); else HCT_LN_FWD(16);
 #undef HCT_LN_FWD
   return hct_check_launch("ln_fwd_kernel");
@@ -448,7 +452,7 @@ extern "C" int hct_layernorm_bwd(const void* dy, int dy_bf16, const float* x, co
       cudaFuncSetAttribute(ln_bwd_kernel<NV, BF, ST, BULK, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM_MAX); \
       configured = true;                                                                                                  \
     }                                                                                                                     \
-    ln_bwd_kernel<NV, BF, ST, BULK, NW><<<grid, NW * 32, smem, st>>>(dy, x, gamma, mean, rstd, dres_in, dx_out_f32,        \
+    hct_launch_pdl(ln_bwd_kernel<NV, BF, ST, BULK, NW>, dim3(grid), dim3(NW * 32), smem, st, dy, x, gamma, mean, rstd, dres_in, dx_out_f32,        \
                                                                      dx16, dgamma, dbeta, dxsum, rows, dim);              \
   } while (0)
 #define HCT_LN_BWD_B(NV, BF, ST, NW) do { if (bulk) HCT_LN_BWD(NV, BF, ST, true, NW); else HCT_LN_BWD(NV, BF, ST, false, NW); } while (0)

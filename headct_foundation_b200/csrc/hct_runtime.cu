@@ -91,3 +91,11 @@ extern "C" int hct_profile_collect(double* total_ms, double* total_flops, long l
 extern "C" const char* hct_last_error(void) { return g_err; }
 extern "C" int hct_abi_version(void) { return 1; }
 extern "C" long long hct_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// Programmatic dependent launch of the kernels that support it (they call pdl_wait() themselves); 0 = plain stream order.
+// Off by default: back-to-back GEMM launches gain 3-6 % (5-7 us per launch, tools/gemm_bench.py with HCT_PDL=1), but the
+// batch-256 training step runs at the board power limit and does not get faster (95.6 vs 96.3 ms, tools/graph_vs_eager.py):
+// the cycles it recovers between kernels come back as a lower clock.
+static int g_pdl = 0;
+bool hct_pdl_enabled() { return g_pdl != 0; }
+extern "C" int hct_set_pdl(int enable) { g_pdl = enable != 0; return HCT_OK; }

@@ -220,6 +220,11 @@ int hct_attention_set_bwd3(int enable);
  * -2 leaves a setting unchanged.  Defaults are the measured fastest: fwd -1, bwd 0 (profiles/r02_attn_softmax_ab_v2.txt).
  * A throughput knob: probabilities are rounded to bf16 (2^-9) right after, so results agree to that rounding. */
 int hct_attention_set_poly(int fwd, int bwd);
+/* 1: the GEMM, attention and LayerNorm kernels are launched with programmatic stream serialization -- the next grid's CTAs
+ * start on an SM as soon as the previous grid's CTA there has exited and wait (griddepcontrol.wait) for the rest of it
+ * after their prologue; 0 (default): plain stream order.  Same results.  Worth 5-7 us per launch where the GPU is not at
+ * its power limit (sequences of small GEMMs); neutral on the batch-256 training step. */
+int hct_set_pdl(int enable);
 /* 1 (default): the pipelined backward hands its dQ / dK / dV tiles to cp.async.bulk.tensor stores (when every 128-row tile
  * is full); 0: per-lane store loop (A/B comparison).  Same results. */
 int hct_attention_set_bwd3_drain(int tma);
