@@ -80,6 +80,8 @@ _SIGNATURES = {
     "hct_attention_set_merge_tail": [_I32],
     "hct_attention_set_dkdv32": [_I32],
     "hct_attention_set_bwd3": [_I32],
+    "hct_attention_set_fwd2": [_I32],
+    "hct_attention_set_tail_key": [_I32],
     "hct_attention_set_poly": [_I32, _I32],
     "hct_set_pdl": [_I32],
     "hct_attention_set_bwd3_drain": [_I32],
@@ -144,6 +146,8 @@ def lib() -> C.CDLL:
             L.hct_attention_set_tcgen05(0)
         if "HCT_PDL" in os.environ:                              # A/B: programmatic dependent launch on / off
             L.hct_set_pdl(int(os.environ["HCT_PDL"] != "0"))
+        if "HCT_ATTN_FWD2" in os.environ:                        # A/B: pipelined persistent forward on / off
+            L.hct_attention_set_fwd2(int(os.environ["HCT_ATTN_FWD2"] != "0"))
         if "HCT_ATTN_BWD3" in os.environ:                        # A/B: pipelined persistent backward on / off
             L.hct_attention_set_bwd3(int(os.environ["HCT_ATTN_BWD3"] != "0"))
         _lib = L

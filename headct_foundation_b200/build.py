@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhct_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["hct_runtime.cu", "hct_gemm_sm100.cu", "hct_attention.cu", "hct_attention_sm100.cu", "hct_attention_tail.cu", "hct_attention_bwd3.cu", "hct_rowops.cu", "hct_mae_ops.cu",
+SOURCES = ["hct_runtime.cu", "hct_gemm_sm100.cu", "hct_attention.cu", "hct_attention_sm100.cu", "hct_attention_tail.cu", "hct_attention_bwd3.cu", "hct_attention_fwd2.cu", "hct_rowops.cu", "hct_mae_ops.cu",
            "hct_dino_ops.cu", "hct_head_ops.cu", "hct_fp32_ops.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

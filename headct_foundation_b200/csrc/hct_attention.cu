@@ -571,6 +571,9 @@ int hct_attention_bwd_tc(const void* qkv, const void* dout, const float* lse, co
 int hct_attention_bwd3(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* colsum, int B, int S, int H,
                        int hd, int n_tiles, cudaStream_t st);
 bool hct_attention_bwd_tail_supported(int S, int hd, int r0);
+int hct_attention_fwd2(const void* qkv, void* out, float* lse, int B, int S, int H, int hd, int n_tiles, cudaStream_t st);
+static int g_attn_fwd2 = 0;      // 1: forward on the pipelined persistent kernel of hct_attention_fwd2.cu
+extern "C" int hct_attention_set_fwd2(int enable) { g_attn_fwd2 = enable != 0; return HCT_OK; }
 int hct_attention_bwd_tail(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, float* colsum, int B, int S,
                            int H, int hd, int r0, cudaStream_t st);
 // 0: mma.sync kernels only; 1: tcgen05, forward tail rows (S % 128 <= 32) on mma.sync; 2 (default): tcgen05 for every
@@ -593,7 +596,8 @@ extern "C" int hct_attention_fwd(const void* qkv, void* out, float* lse, int32_t
   if (g_attn_tc && (hd == 64 || hd == 48)) {
     // full 128-row query tiles on tcgen05; the few rows behind them (the cls token makes S = 128 k + 1) on mma.sync
     const int n_tiles = hct_attn_tc_tiles(S, g_attn_tc == 1);   // modes 2 and 3: every forward tile on tcgen05
-    int rc = hct_attention_fwd_tc(qkv, out, lse, B, S, H, hd, n_tiles, st);
+    int rc = g_attn_fwd2 ? hct_attention_fwd2(qkv, out, lse, B, S, H, hd, n_tiles, st)
+                         : hct_attention_fwd_tc(qkv, out, lse, B, S, H, hd, n_tiles, st);
     if (rc != HCT_OK) return rc;
     q_start = n_tiles * 128;
     if (q_start >= S) return HCT_OK;

@@ -49,8 +49,11 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 // S, P and O never leave the SM; P never touches shared memory.
 template <int HD, int POLY>   // POLY of every 8 exponential pairs run on the FMA pipe (hct_tcgen05.cuh)
 __global__ void __launch_bounds__(FWD_THREADS, 4)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                   bf16* __restrict__ out, float* __restrict__ lse, int S, int H, float scale) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const bf16* __restrict__ qkv,
+                   bf16* __restrict__ out, float* __restrict__ lse, int S, int H, float scale, int fold_flags) {
+  __shared__ float s_kt[64], s_vt[64];                       // the key / value row behind the last 64-key block (tail1)
+  __shared__ float s_qt[64], s_p[64];                        // the query row behind the last full tile, its probabilities
+  const int fold_tail_key = fold_flags & 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -67,7 +70,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int D = H * HD;
   const int nkb = (S + FWD_TK - 1) / FWD_TK;
   const bool tail16 = S - (nkb - 1) * FWD_TK <= 16;          // last key block is computed 16 columns wide
+  // S = 64 k + 1 (the cls token): the ONE key behind the last full block does not get a chain step of its own (S MMA ->
+  // softmax -> P V MMA for a single column: 1/9 of a tile's run time at S = 513, 1/3 at S = 129).  Its score is a dot
+  // product per row, its contribution a rank-1 update; both are folded into the epilogue on the CUDA cores.
+  const bool tail1 = fold_tail_key != 0 && nkb >= 2 && S - (nkb - 1) * FWD_TK == 1;
+  const int nkb_eff = tail1 ? nkb - 1 : nkb;
   const float sl2 = scale * LOG2E;
+  // S = 128 k + 1: the grid then holds the FULL query tiles only (host side), and the ONE query row behind them rides with
+  // the CTA of the last full tile of its head: that CTA's producer warp, idle between its TMA issues, runs the row's online
+  // softmax on the CUDA cores against the K_j / V_j blocks that pass through shared memory anyway.  As a tile of its own the
+  // row cost a whole CTA (nine MMA -> softmax -> MMA steps with one live row): 0.51 against 0.41 ms at S = 513 / 512.
+  const bool has_tail_row = (fold_flags & 2) != 0 && qt == static_cast<int>(gridDim.x) - 1;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
@@ -83,6 +96,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   pdl_wait();                  // launched with programmatic stream serialization: nothing above touches global memory
   pdl_launch_dependents();
+  if ((tail1 || has_tail_row) && threadIdx.x < HD) {
+    const bf16* row = qkv + (static_cast<long long>(b) * S + (S - 1)) * (3LL * D) + h * HD + threadIdx.x;
+    s_qt[threadIdx.x] = __bfloat162float(row[0]);
+    s_kt[threadIdx.x] = __bfloat162float(row[D]);
+    s_vt[threadIdx.x] = __bfloat162float(row[2 * D]);
+  }
+  if (tail1 || has_tail_row) __syncthreads();                // CTA-uniform
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
 
@@ -93,7 +113,56 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_expect_tx(q_full, TILE_BYTES);
       tma_load_2d(smem_u32(sQ), &tmQ, q_full, h * HD, b * S + qt * TILE);
     }
-    for (int j = 0; j < nkb; ++j) {
+    // online softmax of the tail query row (has_tail_row): keys lane and lane + 32 of a block per lane, output dims 2 lane, 2 lane + 1
+    float tr_m = -INFINITY, tr_l = 0.f, tr_o0 = 0.f, tr_o1 = 0.f;
+    const int keys_in_blocks = tail1 ? S - 1 : S;
+    auto tail_row_block = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      const int nvalid = min(FWD_TK, keys_in_blocks - j * FWD_TK);
+      const uint8_t* kb = sK + st * FWD_KV_BYTES;
+      const uint8_t* vb = sV + st * FWD_KV_BYTES;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const float4 qa = *reinterpret_cast<const float4*>(s_qt + 8 * c), qb = *reinterpret_cast<const float4*>(s_qt + 8 * c + 4);
+        const uint4 u0 = *reinterpret_cast<const uint4*>(kb + lane * 128 + ((c ^ (lane & 7)) << 4));
+        const uint4 u1 = *reinterpret_cast<const uint4*>(kb + (lane + 32) * 128 + ((c ^ (lane & 7)) << 4));
+        float2 f;
+        f = unpack_bf16x2(u0.x); s0 = fmaf(qa.x, f.x, s0); s0 = fmaf(qa.y, f.y, s0);
+        f = unpack_bf16x2(u0.y); s0 = fmaf(qa.z, f.x, s0); s0 = fmaf(qa.w, f.y, s0);
+        f = unpack_bf16x2(u0.z); s0 = fmaf(qb.x, f.x, s0); s0 = fmaf(qb.y, f.y, s0);
+        f = unpack_bf16x2(u0.w); s0 = fmaf(qb.z, f.x, s0); s0 = fmaf(qb.w, f.y, s0);
+        f = unpack_bf16x2(u1.x); s1 = fmaf(qa.x, f.x, s1); s1 = fmaf(qa.y, f.y, s1);
+        f = unpack_bf16x2(u1.y); s1 = fmaf(qa.z, f.x, s1); s1 = fmaf(qa.w, f.y, s1);
+        f = unpack_bf16x2(u1.z); s1 = fmaf(qb.x, f.x, s1); s1 = fmaf(qb.y, f.y, s1);
+        f = unpack_bf16x2(u1.w); s1 = fmaf(qb.z, f.x, s1); s1 = fmaf(qb.w, f.y, s1);
+      }
+      if (lane >= nvalid) s0 = -INFINITY;
+      if (lane + 32 >= nvalid) s1 = -INFINITY;
+      const float mn = fmaxf(tr_m, warp_max(fmaxf(s0, s1)));
+      const float alpha = ex2f((tr_m - mn) * sl2);            // first block: ex2(-inf) = 0
+      const float p0 = ex2f((s0 - mn) * sl2), p1 = ex2f((s1 - mn) * sl2);
+      tr_l = tr_l * alpha + warp_sum(p0 + p1);
+      tr_m = mn;
+      s_p[lane] = p0;
+      s_p[lane + 32] = p1;
+      __syncwarp();
+      tr_o0 *= alpha;
+      tr_o1 *= alpha;
+      if (lane < HD / 2) {
+#pragma unroll 8
+        for (int k = 0; k < FWD_TK; ++k) {
+          const float2 v2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vb + k * 128 + (((lane >> 2) ^ (k & 7)) << 4) + (lane & 3) * 4));
+          const float pk = s_p[k];
+          tr_o0 = fmaf(pk, v2.x, tr_o0);
+          tr_o1 = fmaf(pk, v2.y, tr_o1);
+        }
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < nkb_eff; ++j) {
       const int st = j & 1;
       const uint32_t ph = ((j >> 1) & 1) ^ 1u;
       mbar_wait(&k_empty[st], ph);
@@ -107,6 +176,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_2d(smem_u32(sV + st * FWD_KV_BYTES), &tmKV, &v_full[st], 2 * D + h * HD, b * S + j * FWD_TK);
       }
       __syncwarp();
+      // block j - 1 for the tail query row: done before this warp issues the load that overwrites that stage (block j + 1)
+      if (has_tail_row && j >= 1) tail_row_block(j - 1);
+    }
+    if (has_tail_row) {
+      tail_row_block(nkb_eff - 1);
+      if (tail1) {                                            // the row's own score against the folded tail key
+        float part = 0.f;
+        for (int d = lane; d < HD; d += 32) part = fmaf(s_qt[d], s_kt[d], part);
+        const float s_t = warp_sum(part);
+        const float mn = fmaxf(tr_m, s_t);
+        const float alpha = ex2f((tr_m - mn) * sl2), p_t = ex2f((s_t - mn) * sl2);
+        tr_l = tr_l * alpha + p_t;
+        tr_m = mn;
+        if (lane < HD / 2) { tr_o0 = fmaf(p_t, s_vt[2 * lane], tr_o0 * alpha); tr_o1 = fmaf(p_t, s_vt[2 * lane + 1], tr_o1 * alpha); }
+      }
+      const float inv = 1.0f / tr_l;
+      if (lane < HD / 2)
+        *reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * S + (S - 1)) * D + h * HD + 2 * lane) =
+            pack_bf16x2(tr_o0 * inv, tr_o1 * inv);
+      if (lane == 0) lse[(static_cast<long long>(b) * H + h) * S + (S - 1)] = tr_m * scale + logf(tr_l);
     }
   } else if (warp == FWD_MMA_WARP) {
     // ===================== MMA issuer =====================
@@ -132,7 +221,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       __syncwarp();
     };
     issue_s(0);
-    for (int j = 0; j < nkb; ++j) {
+    for (int j = 0; j < nkb_eff; ++j) {
       const int st = j & 1;
       mbar_wait(p_full, j & 1);                       // P_j sits in TMEM (and every softmax warp has read S_j)
       mbar_wait(&v_full[st], (j >> 1) & 1);
@@ -147,10 +236,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int ks = 0; ks < FWD_TK / 16; ++ks) tc_mma_ts(tmem_O, tmem_S + ks * 8, dV + ks * 128, idesc_o, ks > 0 ? 1u : acc);
         }
         tc_commit(&v_empty[st]);
-        if (j == nkb - 1) tc_commit(done);
+        if (j == nkb_eff - 1) tc_commit(done);
       }
       __syncwarp();
-      if (j + 1 < nkb) issue_s(j + 1);                // executes after P_j V_j (in-order pipe): safe to overwrite S / P
+      if (j + 1 < nkb_eff) issue_s(j + 1);            // executes after P_j V_j (in-order pipe): safe to overwrite S / P
     }
   } else if (warp < 4) {
     // ===================== softmax / correction / epilogue: one query row per thread =====================
@@ -183,7 +272,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_st16(tmem_O + lane_off + c0, o);
       }
     };
-    for (int j = 0; j < nkb; ++j) {
+    for (int j = 0; j < nkb_eff; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int nvalid = min(FWD_TK, S - j * FWD_TK);         // valid key columns in this block (>= 1)
@@ -306,10 +395,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) mbar_arrive(p_full);
     }
     // ---- epilogue: O / l -> bf16, log-sum-exp
+    // the tail key (tail1): score = q . k_tail on the CUDA cores while the last P V MMAs drain
+    float s_t = 0.f;
+    if (tail1) {
+      if (warp_active) {
+        const int rr = q * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sQ + rr * 128 + ((c ^ (rr & 7)) << 4));
+          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+          const float* kk = s_kt + 8 * c;
+          s_t = fmaf(a0.x, kk[0], s_t); s_t = fmaf(a0.y, kk[1], s_t); s_t = fmaf(a1.x, kk[2], s_t); s_t = fmaf(a1.y, kk[3], s_t);
+          s_t = fmaf(a2.x, kk[4], s_t); s_t = fmaf(a2.y, kk[5], s_t); s_t = fmaf(a3.x, kk[6], s_t); s_t = fmaf(a3.y, kk[7], s_t);
+        }
+      }
+    }
     mbar_wait(done, 0);
     tc_fence_after();
     if (warp_active) {
+      float alpha_t = 1.0f, p_t = 0.f;                        // O_final = (O alpha_t + p_t v_tail) / l
+      if (tail1) {
+        const float mn = fmaxf(m, s_t);
+        alpha_t = ex2f((m - mn) * sl2);
+        p_t = ex2f((s_t - mn) * sl2);
+        l = l * alpha_t + p_t;
+        m = mn;
+      }
       const float inv = 1.0f / l;
+      const float oa = alpha_t * inv, pv = p_t * inv;
       bf16* orow = out + (static_cast<long long>(b) * S + row) * D + h * HD;
 #pragma unroll 1
       for (int c0 = 0; c0 < HD; c0 += 16) {
@@ -318,11 +431,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (row < S) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              f[i] = __uint_as_float(o[8 * g + i]) * oa;
+              if (tail1) f[i] = fmaf(pv, s_vt[c0 + 8 * g + i], f[i]);
+            }
             uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv);
+            u.x = pack_bf16x2(f[0], f[1]);
+            u.y = pack_bf16x2(f[2], f[3]);
+            u.z = pack_bf16x2(f[4], f[5]);
+            u.w = pack_bf16x2(f[6], f[7]);
             *reinterpret_cast<uint4*>(orow + c0 + 8 * g) = u;
           }
         }
@@ -1137,6 +1256,10 @@ int hct_attn_tc_tiles(int S, int tail_on_mma_sync) {
   return (S + TILE - 1) / TILE;
 }
 
+static int g_fold_tail_key = 1;  // 1: a single key behind the last 64-key block is folded into the forward's epilogue
+static int g_fold_tail_row = 1;  // 1: a single query row behind the last full tile rides with that tile's CTA (producer warp)
+static int g_fwd_flags = 0;
+extern "C" int hct_attention_set_tail_key(int fold) { g_fold_tail_key = (fold & 1) != 0; g_fold_tail_row = (fold & 2) != 0; return HCT_OK; }
 static int g_fwd_poly = -1;      // forward softmax arithmetic: -1 scalar fp32, one pass (default: measured fastest, 0.516 vs 0.577 ms); 0 / 3: packed fp32, two passes, 0 or 3 of 8 exponential pairs on the FMA pipe
 int hct_attention_bwd3_set_poly(int n);
 extern "C" int hct_attention_set_poly(int fwd, int bwd) {     // -1: scalar fp32 arithmetic; -2: leave unchanged
@@ -1145,7 +1268,7 @@ extern "C" int hct_attention_set_poly(int fwd, int bwd) {     // -1: scalar fp32
   return HCT_OK;
 }
 template <int POLY>
-static int launch_fwd_tc(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* out, float* lse, int S, int H, int hd, float scale,
+static int launch_fwd_tc(const CUtensorMap& tmq, const CUtensorMap& tmkv, const void* qkv, void* out, float* lse, int S, int H, int hd, float scale,
                          dim3 grid, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) {
@@ -1153,8 +1276,9 @@ static int launch_fwd_tc(const CUtensorMap& tmq, const CUtensorMap& tmkv, void* 
     rc = set_smem(attn_fwd_tc_kernel<48, POLY>, FWD_SMEM); if (rc) return rc;
     cfg = true;
   }
-  if (hd == 64) hct_launch_pdl(attn_fwd_tc_kernel<64, POLY>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
-  else hct_launch_pdl(attn_fwd_tc_kernel<48, POLY>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmq, tmkv, static_cast<bf16*>(out), lse, S, H, scale);
+  const bf16* q = static_cast<const bf16*>(qkv);
+  if (hd == 64) hct_launch_pdl(attn_fwd_tc_kernel<64, POLY>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmq, tmkv, q, static_cast<bf16*>(out), lse, S, H, scale, g_fwd_flags);
+  else hct_launch_pdl(attn_fwd_tc_kernel<48, POLY>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmq, tmkv, q, static_cast<bf16*>(out), lse, S, H, scale, g_fwd_flags);
   return HCT_OK;
 }
 
@@ -1167,10 +1291,13 @@ int hct_attention_fwd_tc(const void* qkv, void* out, float* lse, int B, int S, i
   rc = hct_make_tmap_bf16_2d(&tmkv, qkv, D3, static_cast<long long>(B) * S, D3, 64, FWD_TK);
   if (rc != HCT_OK) return rc;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-  dim3 grid(n_tiles, H, B);
-  rc = g_fwd_poly == 0   ? launch_fwd_tc<0>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
-       : g_fwd_poly == 3 ? launch_fwd_tc<3>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st)
-                         : launch_fwd_tc<-1>(tmq, tmkv, out, lse, S, H, hd, scale, grid, st);
+  // asked to cover every row of an S = 128 k + 1 problem: full tiles only, the last row rides with the last full tile's CTA
+  const bool fold_row = g_fold_tail_row && S > TILE && S % TILE == 1 && n_tiles * TILE >= S;
+  dim3 grid(fold_row ? S / TILE : n_tiles, H, B);
+  g_fwd_flags = (g_fold_tail_key ? 1 : 0) | (fold_row ? 2 : 0);
+  rc = g_fwd_poly == 0   ? launch_fwd_tc<0>(tmq, tmkv, qkv, out, lse, S, H, hd, scale, grid, st)
+       : g_fwd_poly == 3 ? launch_fwd_tc<3>(tmq, tmkv, qkv, out, lse, S, H, hd, scale, grid, st)
+                         : launch_fwd_tc<-1>(tmq, tmkv, qkv, out, lse, S, H, hd, scale, grid, st);
   if (rc) return rc;
   return hct_check_launch("attn_fwd_tc_kernel");
 }

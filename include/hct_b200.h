@@ -214,6 +214,17 @@ int hct_attention_set_dkdv32(int enable);
 /* 1: backward on the pipelined persistent kernels of hct_attention_bwd3.cu (one CTA per SM, three score-buffer pairs in
  * tensor memory, two softmax warp groups); 0: the two-CTA-per-SM kernels.  Same results either way. */
 int hct_attention_set_bwd3(int enable);
+/* 1: forward on the pipelined persistent kernel of hct_attention_fwd2.cu (one CTA per SM, two query tiles of a head in
+ * flight, two score buffers per tile, sixteen softmax warps); 0: four CTAs per SM, one tile each.  Same results up to the
+ * rounding of the probabilities (the two kernels move the running maximum at the same points). */
+int hct_attention_set_fwd2(int enable);
+/* Bit mask, default 3.  Bit 0: when S = 64 k + 1 (the cls token) the tcgen05 forward does not spend a chain step (S MMA ->
+ * softmax -> P V MMA) on the single key behind the last full 64-key block: its score is a dot product per query row and
+ * its contribution a rank-1 update, both folded into the epilogue in fp32.  Bit 1: when S = 128 k + 1 the single query row
+ * behind the last full 128-row tile does not get a CTA of its own: the producer warp of the last full tile's CTA runs its
+ * online softmax on the CUDA cores against the K / V blocks that pass through shared memory.  0: both get their own block /
+ * tile (A/B).  Results agree to the bf16 rounding of the probabilities involved. */
+int hct_attention_set_tail_key(int fold);
 /* Softmax arithmetic of the tcgen05 forward (fwd) and of the pipelined backward (bwd): -1 = scalar fp32; 0 = the packed
  * two-lane fp32 instructions of sm_100 (FFMA2 / FADD2 / FMUL2); n > 0 = packed, and n of every 8 exponential pairs evaluated
  * on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error 7.5e-5) instead of MUFU.EX2 (fwd: 3, bwd: 2);

@@ -231,6 +231,26 @@ def test_attention_bwd_pipelined_persistent(cuda, HF, B, S, H, hd, mode):
         lib().hct_attention_set_tcgen05(2)
 
 
+@pytest.mark.parametrize("B,S,H,hd", [(2, 129, 12, 64), (2, 513, 16, 48), (1, 517, 12, 64), (3, 65, 2, 48), (2, 260, 2, 48),
+                                      (1, 136, 3, 64), (3, 17, 3, 64), (1, 1, 2, 64), (2, 230, 4, 48), (2, 200, 3, 64),
+                                      (1, 300, 2, 48), (2, 144, 2, 64), (1, 128, 2, 64), (2, 256, 2, 48), (1, 385, 1, 64),
+                                      (1, 96, 2, 48), (2, 640, 2, 64), (1, 1000, 1, 48),
+                                      # many more work items than SMs: every CTA walks several (batch, head, tile pair) items
+                                      (40, 129, 12, 64), (12, 513, 16, 48), (90, 40, 4, 64), (70, 100, 3, 48), (9, 517, 12, 64)])
+def test_attention_fwd_pipelined_persistent(cuda, HF, B, S, H, hd):
+    """Forward on the pipelined persistent kernel (hct_attention_set_fwd2(1): two query tiles of a head per CTA, two score
+    buffers each, sixteen softmax warps) against the fp32 torch attention; the backward that follows in the case consumes its
+    outputs and log-sum-exp."""
+    from headct_foundation_b200._cabi import lib
+    lib().hct_attention_set_fwd2(1)
+    lib().hct_attention_set_tcgen05(3)
+    try:
+        _attention_case(cuda, B, S, H, hd)
+    finally:
+        lib().hct_attention_set_tcgen05(2)
+        lib().hct_attention_set_fwd2(0)
+
+
 def _attention_case(cuda, B, S, H, hd):
     from headct_foundation_b200._cabi import call, stream_ptr
     D = H * hd
