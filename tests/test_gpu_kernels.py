@@ -166,7 +166,10 @@ def test_layernorm_fwd_bwd(cuda, HF, rows, dim, eps):
                                       # ragged tails: 38 / 8 / 44 / exactly 16 valid keys in the last 64-key block,
                                       # query tiles with 1-4 live warps, and exact multiples of the tile sizes
                                       (2, 230, 4, 48), (2, 200, 3, 64), (1, 300, 2, 48), (2, 144, 2, 64),
-                                      (1, 128, 2, 64), (2, 256, 2, 48), (1, 385, 1, 64)])
+                                      (1, 128, 2, 64), (2, 256, 2, 48), (1, 385, 1, 64),
+                                      # S = 128 k + 1 and S = 64 k + 1: the forward folds the last key into its epilogue and
+                                      # lets the last query row ride with the last full tile's CTA (hct_attention_set_tail_key)
+                                      (2, 257, 3, 48), (1, 193, 2, 64), (3, 641, 2, 48), (5, 129, 3, 48)])
 def test_attention_fwd_bwd(cuda, HF, B, S, H, hd, mode):
     """mode 2 (default): tcgen05 kernels, backward rows behind the last full 128-row tile on the row kernel; 3: tcgen05 for
     every tile; 1: forward tail rows on mma.sync; 0: mma.sync kernels only.  Backward on the two-CTA-per-SM kernels here
@@ -249,6 +252,32 @@ def test_attention_fwd_pipelined_persistent(cuda, HF, B, S, H, hd):
     finally:
         lib().hct_attention_set_tcgen05(2)
         lib().hct_attention_set_fwd2(0)
+
+
+@pytest.mark.parametrize("B,S,H,hd", [(3, 129, 12, 64), (2, 513, 16, 48), (2, 257, 3, 48), (1, 193, 2, 64), (2, 65, 2, 48)])
+def test_attention_fwd_tail_folds_agree_with_own_block_and_tile(cuda, B, S, H, hd):
+    """hct_attention_set_tail_key: bit 0 folds the single key behind the last 64-key block into the epilogue, bit 1 lets the
+    single query row behind the last full tile ride with that tile's CTA.  Both against the kernel that gives them their own
+    block / tile: outputs within the bf16 rounding of the probabilities involved, log-sum-exp to fp32 rounding."""
+    from headct_foundation_b200._cabi import call, stream_ptr, lib
+    D = H * hd
+    g = torch.Generator(device="cuda").manual_seed(S + hd)
+    qkv = torch.randn(B, S, 3 * D, device=cuda, generator=g).bfloat16()
+    res = {}
+    try:
+        for fold in (0, 1, 3):
+            lib().hct_attention_set_tail_key(fold)
+            out = torch.empty(B, S, D, device=cuda, dtype=torch.bfloat16)
+            lse = torch.empty(B, H, S, device=cuda)
+            call("hct_attention_fwd", qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, hd, stream_ptr(cuda))
+            torch.cuda.synchronize()
+            res[fold] = (out.float(), lse)
+    finally:
+        lib().hct_attention_set_tail_key(3)
+    for fold in (1, 3):
+        assert _rel(res[fold][0], res[0][0]) < 2e-3, fold
+        assert _rel(res[fold][0][:, -1], res[0][0][:, -1]) < 6e-3, fold          # the last row on its own
+        assert (res[fold][1] - res[0][1]).abs().max().item() < 1e-5, fold
 
 
 def _attention_case(cuda, B, S, H, hd):
