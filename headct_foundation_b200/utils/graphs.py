@@ -86,8 +86,9 @@ class GraphedTrainStep:
     noise comes from torch's CUDA generator, which is graph-aware.
 
     Data parallel (`sync_grads`, default: on when torch.distributed runs with more than one rank): the gradient all-reduce
-    (mean over ranks, `parallel.allreduce_mean_grads_`: coalesced NCCL groups, captured like any other kernel) sits between
-    backward and the update INSIDE the graph, so a small per-GPU batch (global batch 256 over 8 GPUs = 32 per GPU, 13 ms of
+    (mean over ranks, `parallel.allreduce_mean_grads_`: coalesced NCCL groups, captured like any other kernel) sits INSIDE
+    the graph -- per ~64 MB bucket on a forked communication stream as soon as backward has produced the bucket's gradients
+    (`overlap_grad_sync`, default), joined before the update --, so a small per-GPU batch (global batch 256 over 8 GPUs = 32 per GPU, 13 ms of
     GPU work) is not capped by the host's ~13 ms of launch work per step.  Pass the bare module, not a DistributedDataParallel
     wrapper (its reducer hooks cannot be captured); parameters are broadcast from rank 0 first, as DDP would.  The graph
     holds NCCL kernels: drop the step (`del step`) before `torch.distributed.destroy_process_group()`, or that call waits
@@ -96,7 +97,7 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: torch.nn.Module, optimizer, example: torch.Tensor, loss_of=None, warmup: int = 3,
-                 sync_grads: Optional[bool] = None):
+                 sync_grads: Optional[bool] = None, overlap_grad_sync: bool = True, bucket_bytes: int = 64 << 20):
         if not example.is_cuda:
             raise RuntimeError("GraphedTrainStep needs a CUDA example input (no CPU fallback)")
         if not hasattr(optimizer, "step_captured"):
@@ -117,14 +118,62 @@ class GraphedTrainStep:
         saved_p = [p.detach().clone() for p in params]
         saved_s = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in optimizer.state[p].items()} if p in optimizer.state
                    and len(optimizer.state[p]) else None for p in params]
+        # Gradient exchange under backward (DDP's overlap, in capturable form): the parameters are bucketed in reverse
+        # registration order (~the order backward produces their gradients); a post-accumulate hook on every parameter counts
+        # its bucket down, and the hook that completes a bucket forks the communication stream off the stream backward
+        # runs on and issues that bucket's coalesced all-reduce there.  Captured, the fork / join become graph edges: the
+        # all-reduce of a bucket runs beside the backward kernels of the layers below it.
+        self._overlap = bool(self.sync_grads and overlap_grad_sync)
+        hooks = []
+        if self._overlap:
+            comm = torch.cuda.Stream(device=dev)
+            buckets, size = [[]], 0
+            for p in reversed([q for q in params if q.requires_grad]):
+                nbytes = p.numel() * 4
+                if buckets[-1] and size + nbytes > bucket_bytes:
+                    buckets.append([])
+                    size = 0
+                buckets[-1].append(p)
+                size += nbytes
+            pending = [0] * len(buckets)
+
+            def arm():
+                for i, b in enumerate(buckets):
+                    pending[i] = len(b)
+
+            def make_hook(bi):
+                def hook(_p):
+                    pending[bi] -= 1
+                    if pending[bi] == 0:
+                        comm.wait_stream(torch.cuda.current_stream(dev))
+                        with torch.cuda.stream(comm):
+                            parallel.allreduce_mean_grads_(buckets[bi], bucket_bytes=1 << 62)
+                return hook
+            for bi, b in enumerate(buckets):
+                for p in b:
+                    hooks.append(p.register_post_accumulate_grad_hook(make_hook(bi)))
+
+            def sync_after_backward():
+                cur = torch.cuda.current_stream(dev)
+                late = [p for i, b in enumerate(buckets) if pending[i] > 0 for p in b]     # a bucket with a gradient-less tensor
+                cur.wait_stream(comm)
+                if late:
+                    parallel.allreduce_mean_grads_(late)
+        else:
+            def arm():
+                pass
+
+            def sync_after_backward():
+                if self.sync_grads:
+                    parallel.allreduce_mean_grads_(params)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
                 optimizer.zero_grad(set_to_none=True)
+                arm()
                 self.loss_of(model(self.static_in)).backward()
-                if self.sync_grads:                    # also brings the NCCL communicator up before the capture
-                    parallel.allreduce_mean_grads_(params)
+                sync_after_backward()                  # also brings the NCCL communicator up before the capture
                 optimizer.step()
             with torch.no_grad():
                 for p, sp, ss in zip(params, saved_p, saved_s):
@@ -147,10 +196,12 @@ class GraphedTrainStep:
             torch.cuda.synchronize(dev)
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self.sync_grads else "global"):
             loss = self.loss_of(model(self.static_in))
+            arm()
             loss.backward()
-            if self.sync_grads:
-                parallel.allreduce_mean_grads_(params)
+            sync_after_backward()
             optimizer.step_captured()
+        for h in hooks:                                    # the graph keeps the exchange; eager use of the model is unaffected
+            h.remove()
         self.static_loss = loss.detach()
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
