@@ -10,8 +10,11 @@
  *
  * Conventions:
  *   - plain pointers + sizes; all pointers are DEVICE pointers unless stated otherwise;
- *   - every call enqueues work on the given stream (cudaStream_t passed as void*), never
- *     synchronises the device and holds no global mutable state besides per-process caches;
+ *   - every call enqueues work on the given stream (cudaStream_t passed as void*) and never
+ *     synchronises the device.  Process-wide state: per-process caches (kernel attributes, the TMA
+ *     encoder entry point), the hct_*_set_* switches and the hct_profile_* timing state -- plain
+ *     globals, meant for ONE host thread per process (one process per GPU, as the reference runs);
+ *     set a switch before the worker threads start if a host is threaded;
  *   - return value: 0 = ok, 1 = invalid argument, 2 = CUDA error, 3 = unsupported shape;
  *     hct_last_error() returns a thread-local message for the last non-zero return;
  *   - "bf16" = __nv_bfloat16 storage, row-major with an explicit leading dimension in ELEMENTS.
